@@ -1,0 +1,734 @@
+// pmm_engine.cu -- the C ABI of include/pairhmm_cuda.h: host-side packing, task queue construction, kernel
+// sequencing, result collection.  This is the layer that stands where the reference has pack_fpga_input +
+// OpenCL buffer migration + clEnqueueTask (/root/reference/pairhmm/task/xlnx/PairHMMTask.cpp:27-143,
+// /root/reference/pairhmm/host/PairHMMFpga.cpp:125-162).  There is no CPU compute path in this file: without a
+// GPU every entry point fails with PMM_ERR_NO_DEVICE.
+#include "../../include/pairhmm_cuda.h"
+#include "pmm_kernels.cuh"
+#include "pmm_tables.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <numeric>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace pmm;
+
+namespace {
+
+std::string g_create_error;
+
+constexpr size_t kAlign = 256;
+inline size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = std::max(n, (size_t)4096);
+        want += want / 4;                         // grow-only with slack: buffers are recycled across jobs like the
+        cudaError_t e = cudaMalloc(&p, want);     // reference's scratch blocks (PairHMMTask.cpp:19-25,48,70)
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct PinBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = std::max(n, (size_t)4096);
+        want += want / 4;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct Variant { int K, W; bool striped; };
+inline bool operator==(const Variant& a, const Variant& b) { return a.K == b.K && a.W == b.W && a.striped == b.striped; }
+
+struct LaunchSeg { Variant v; uint32_t task_first, task_count; };
+
+// Issue slots one step of K cells costs in the float kernel (from the SASS of the steady loop: 12 FP per cell,
+// one LDS.128 per 4 rows, and 3 SHFL + LDG + 2 sum FADD + address/loop overhead per step).
+inline double step_cost(int K) { return 12.25 * K + 9.0; }
+
+}  // namespace
+
+struct pmm_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::string err;
+    int tasks_per_warp = 6;
+
+    // device-resident tables
+    DevBuf tables;
+    DeviceTables dtab{};
+
+    // job state
+    PinBuf h_in;  DevBuf d_in;          // one arena: read blob | descs | hap blob | descs | spos | tasks | regions
+    DevBuf d_stream, d_iyf, d_iyd, d_raw, d_fb_tasks, d_fb_idx, d_tiny_tasks, d_dres, d_ctrl, d_scratch, d_probe;
+    PinBuf h_out;                       // raw floats | fb idx | dres
+    size_t off_rblob = 0, off_rdesc = 0, off_hblob = 0, off_hdesc = 0, off_spos = 0, off_tasks = 0, off_regions = 0;
+    uint32_t num_read = 0, num_hap = 0, num_region = 0, num_tasks = 0;
+    uint64_t pairs = 0, cells = 0;
+    uint32_t max_hap_len = 0;
+    std::vector<LaunchSeg> segs;
+    std::vector<pmm_region_t> regions;
+    bool staged = false, launched = false;
+    pmm_stats_t stats{};
+
+    // scratch reused by the one-shot calls
+    std::vector<uint32_t> tmp_roff, tmp_hoff;
+    std::vector<uint8_t> tmp_tracks[5], tmp_hap;
+    std::vector<float> tmp_raw;
+
+    int fail_cuda(cudaError_t e, const char* what)
+    {
+        err = std::string(what) + ": " + cudaGetErrorString(e);
+        return PMM_ERR_CUDA;
+    }
+    int fail(int code, const std::string& m) { err = m; return code; }
+};
+
+#define PMM_CUDA(ctx, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return (ctx)->fail_cuda(e__, #call); } while (0)
+
+namespace {
+
+// ---- variant choice -------------------------------------------------------------------------------------
+// Best (K, W) for a read of R bases: maximise useful FP work per issue slot, 12*R / (W * step_cost(K)), subject to
+// R + 1 <= K * W (one boundary row), with a mild penalty for variants whose register count halves occupancy.
+Variant pick_variant(int R)
+{
+    Variant best{8, 32, true};
+    double best_eff = -1.0;
+    for (int W = 8; W <= 32; W *= 2)
+        for (int K = 4; K <= 16; ++K) {
+            if (!forward_f32_has_variant(K, W) || R + 1 > K * W) continue;
+            double eff = 12.0 * R / (W * step_cost(K));
+            if (K > 12) eff *= 0.97;
+            if (eff > best_eff) { best_eff = eff; best = Variant{K, W, false}; }
+        }
+    return best;
+}
+
+int ensure_tables(pmm_ctx* c)
+{
+    if (c->tables.p) return PMM_OK;
+    const HostTables& t = host_tables();
+    const size_t nf = kPh2prSize + kM2mSize;
+    const size_t bytes = align_up(nf * sizeof(float)) + nf * sizeof(double);
+    PMM_CUDA(c, c->tables.reserve(bytes));
+    char* base = static_cast<char*>(c->tables.p);
+    float* f = reinterpret_cast<float*>(base);
+    double* d = reinterpret_cast<double*>(base + align_up(nf * sizeof(float)));
+    PMM_CUDA(c, cudaMemcpy(f, t.ph2pr_f, sizeof t.ph2pr_f, cudaMemcpyHostToDevice));
+    PMM_CUDA(c, cudaMemcpy(f + kPh2prSize, t.m2m_f, sizeof t.m2m_f, cudaMemcpyHostToDevice));
+    PMM_CUDA(c, cudaMemcpy(d, t.ph2pr_d, sizeof t.ph2pr_d, cudaMemcpyHostToDevice));
+    PMM_CUDA(c, cudaMemcpy(d + kPh2prSize, t.m2m_d, sizeof t.m2m_d, cudaMemcpyHostToDevice));
+    c->dtab = DeviceTables{f, f + kPh2prSize, d, d + kPh2prSize};
+    return PMM_OK;
+}
+
+struct ReadSrc {
+    // track t of read r lives at base[t] + off[r]
+    const uint8_t* base[5];
+};
+
+// Common staging: reads are given as (offset, length) into five tracks, haplotypes likewise into one.
+int stage_common(pmm_ctx* c, uint32_t num_read, const uint32_t* read_off, const ReadSrc& rs,
+                 uint32_t num_hap, const uint32_t* hap_off, const uint8_t* hap_bases,
+                 uint32_t num_region, const pmm_region_t* regions)
+{
+    auto t0 = std::chrono::steady_clock::now();
+    c->staged = false; c->launched = false;
+    if (!num_read || !num_hap || !num_region || !read_off || !hap_off || !regions)
+        return c->fail(PMM_ERR_INVALID, "empty job");
+    int rc = ensure_tables(c);
+    if (rc) return rc;
+
+    const uint64_t total_bases = read_off[num_read] - read_off[0];
+    const uint64_t total_hap = hap_off[num_hap] - hap_off[0];
+    if (total_bases * 5 + total_hap >= (1ull << 31)) return c->fail(PMM_ERR_INVALID, "job larger than 2 GiB: split it");
+    uint32_t max_hap = 0, max_read = 0;
+    for (uint32_t i = 0; i < num_read; ++i) {
+        const uint32_t len = read_off[i + 1] - read_off[i];
+        if (len == 0 || read_off[i + 1] < read_off[i]) return c->fail(PMM_ERR_INVALID, "read of length 0");
+        max_read = std::max(max_read, len);
+    }
+    for (uint32_t h = 0; h < num_hap; ++h) {
+        const uint32_t len = hap_off[h + 1] - hap_off[h];
+        if (len == 0 || hap_off[h + 1] < hap_off[h]) return c->fail(PMM_ERR_INVALID, "haplotype of length 0");
+        max_hap = std::max(max_hap, len);
+    }
+    c->max_hap_len = max_hap;
+
+    // ---- regions, result offsets, cell count ---------------------------------------------------------------
+    std::vector<RegionDesc> rdesc(num_region);
+    uint64_t pairs = 0, cells = 0;
+    for (uint32_t g = 0; g < num_region; ++g) {
+        const pmm_region_t& r = regions[g];
+        if (!r.num_read || !r.num_hap || (uint64_t)r.read_first + r.num_read > num_read ||
+            (uint64_t)r.hap_first + r.num_hap > num_hap)
+            return c->fail(PMM_ERR_INVALID, "region out of range");
+        rdesc[g] = RegionDesc{r.read_first, r.num_read, r.hap_first, r.num_hap, (uint32_t)pairs};
+        pairs += (uint64_t)r.num_read * r.num_hap;
+        cells += (uint64_t)(read_off[r.read_first + r.num_read] - read_off[r.read_first]) *
+                 (uint64_t)(hap_off[r.hap_first + r.num_hap] - hap_off[r.hap_first]);
+    }
+    if (pairs >= (1ull << 31)) return c->fail(PMM_ERR_INVALID, "more than 2^31 pairs in one job: split it");
+
+    // ---- cut every region into warp-tasks --------------------------------------------------------------------
+    // Reads of a region are sorted by length (longest first); the longest unassigned read picks the (K, W)
+    // variant and shares its warp with the next 32/W - 1 reads.  Haplotypes are cut into runs so that the queue
+    // holds about tasks_per_warp tasks per resident warp.
+    struct Group { Variant v; uint32_t region; uint32_t reads[kMaxGroups]; uint32_t n; };
+    std::vector<Group> groups;
+    std::vector<uint32_t> order;
+    uint64_t group_haps = 0;
+    for (uint32_t g = 0; g < num_region; ++g) {
+        const pmm_region_t& r = regions[g];
+        order.resize(r.num_read);
+        std::iota(order.begin(), order.end(), r.read_first);
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+            return read_off[x + 1] - read_off[x] > read_off[y + 1] - read_off[y]; });
+        for (uint32_t k = 0; k < r.num_read;) {
+            const int R = (int)(read_off[order[k] + 1] - read_off[order[k]]);
+            Group gr; gr.v = pick_variant(R); gr.region = g; gr.n = 0;
+            const uint32_t G = gr.v.striped ? 1u : (uint32_t)(32 / gr.v.W);
+            for (; gr.n < G && k < r.num_read; ++k) gr.reads[gr.n++] = order[k];
+            for (uint32_t z = gr.n; z < kMaxGroups; ++z) gr.reads[z] = 0;
+            groups.push_back(gr);
+            group_haps += r.num_hap;
+        }
+    }
+    const uint64_t resident_warps = (uint64_t)c->sm_count * 16;
+    const uint64_t target_tasks = std::max<uint64_t>(1, resident_warps * (uint64_t)c->tasks_per_warp);
+    const uint32_t haps_per_task = (uint32_t)std::max<uint64_t>(1, (group_haps + target_tasks - 1) / target_tasks);
+
+    // order launches by variant (largest footprint first); stable within a variant
+    std::vector<uint32_t> gorder(groups.size());
+    std::iota(gorder.begin(), gorder.end(), 0u);
+    auto vkey = [](const Variant& v) { return (v.striped ? 1 << 20 : 0) + v.K * v.W * 64 + v.W; };
+    std::stable_sort(gorder.begin(), gorder.end(), [&](uint32_t x, uint32_t y) { return vkey(groups[x].v) > vkey(groups[y].v); });
+
+    std::vector<Task> tasks;
+    c->segs.clear();
+    for (uint32_t gi : gorder) {
+        const Group& gr = groups[gi];
+        const RegionDesc& r = rdesc[gr.region];
+        const uint32_t hpt = gr.v.striped ? 1u : std::min(haps_per_task, r.nhaps);
+        if (c->segs.empty() || !(c->segs.back().v == gr.v)) c->segs.push_back(LaunchSeg{gr.v, (uint32_t)tasks.size(), 0});
+        // balance the run lengths: ceil(nhaps / ceil(nhaps / hpt))
+        const uint32_t nruns = (r.nhaps + hpt - 1) / hpt;
+        for (uint32_t run = 0; run < nruns; ++run) {
+            const uint32_t h0 = (uint32_t)((uint64_t)r.nhaps * run / nruns), h1 = (uint32_t)((uint64_t)r.nhaps * (run + 1) / nruns);
+            Task t;
+            for (uint32_t z = 0; z < kMaxGroups; ++z) {
+                t.read[z] = gr.reads[z];
+                t.out_base[z] = z < gr.n ? r.out_first + (gr.reads[z] - r.read_first) * r.nhaps + h0 : 0;
+            }
+            t.hap_first = r.hap_first + h0; t.nhaps = h1 - h0; t.nreads = gr.n; t.reserved = 0;
+            tasks.push_back(t);
+            c->segs.back().task_count++;
+        }
+    }
+
+    // ---- pack the input arena ---------------------------------------------------------------------------------
+    const size_t sz_rblob = total_bases * 5, sz_rdesc = sizeof(ReadDesc) * num_read;
+    const size_t sz_hblob = total_hap, sz_hdesc = sizeof(HapDesc) * num_hap;
+    const size_t sz_spos = sizeof(uint32_t) * (num_hap + 1), sz_tasks = sizeof(Task) * tasks.size();
+    const size_t sz_regions = sizeof(RegionDesc) * num_region;
+    size_t off = 0;
+    c->off_rblob = off; off = align_up(off + sz_rblob);
+    c->off_rdesc = off; off = align_up(off + sz_rdesc);
+    c->off_hblob = off; off = align_up(off + sz_hblob);
+    c->off_hdesc = off; off = align_up(off + sz_hdesc);
+    c->off_spos = off; off = align_up(off + sz_spos);
+    c->off_tasks = off; off = align_up(off + sz_tasks);
+    c->off_regions = off; off = align_up(off + sz_regions);
+    const size_t arena = off;
+    PMM_CUDA(c, c->h_in.reserve(arena));
+    PMM_CUDA(c, c->d_in.reserve(arena));
+    char* hb = static_cast<char*>(c->h_in.p);
+    const uint32_t r_base = read_off[0], h_base = hap_off[0];
+    for (int t = 0; t < 5; ++t) memcpy(hb + c->off_rblob + (size_t)t * total_bases, rs.base[t] + r_base, total_bases);
+    ReadDesc* rd = reinterpret_cast<ReadDesc*>(hb + c->off_rdesc);
+    for (uint32_t i = 0; i < num_read; ++i)
+        rd[i] = ReadDesc{read_off[i] - r_base, (uint32_t)total_bases, read_off[i + 1] - read_off[i]};
+    memcpy(hb + c->off_hblob, hap_bases + h_base, total_hap);
+    HapDesc* hd = reinterpret_cast<HapDesc*>(hb + c->off_hdesc);
+    uint32_t* spos = reinterpret_cast<uint32_t*>(hb + c->off_spos);
+    uint32_t pos = 0;
+    for (uint32_t h = 0; h < num_hap; ++h) {
+        const uint32_t len = hap_off[h + 1] - hap_off[h];
+        hd[h] = HapDesc{hap_off[h] - h_base, len};
+        spos[h] = pos; pos += len + 1;
+    }
+    spos[num_hap] = pos;                           // final separator
+    memcpy(hb + c->off_tasks, tasks.data(), sz_tasks);
+    memcpy(hb + c->off_regions, rdesc.data(), sz_regions);
+
+    // ---- device buffers -------------------------------------------------------------------------------------
+    const size_t stream_bytes = kStreamFrontPad + (size_t)pos + 1 + kStreamTailPad;
+    PMM_CUDA(c, c->d_stream.reserve(stream_bytes));
+    PMM_CUDA(c, c->d_iyf.reserve(sizeof(float) * num_hap));
+    PMM_CUDA(c, c->d_iyd.reserve(sizeof(double) * num_hap));
+    PMM_CUDA(c, c->d_raw.reserve(sizeof(float) * pairs));
+    PMM_CUDA(c, c->d_fb_tasks.reserve(sizeof(Task) * pairs));
+    PMM_CUDA(c, c->d_tiny_tasks.reserve(sizeof(Task) * pairs));
+    PMM_CUDA(c, c->d_fb_idx.reserve(sizeof(uint32_t) * pairs));
+    PMM_CUDA(c, c->d_dres.reserve(sizeof(double) * pairs));
+    PMM_CUDA(c, c->d_ctrl.reserve(sizeof(uint32_t) * 256));
+    PMM_CUDA(c, c->h_out.reserve(256 + align_up(sizeof(float) * pairs) + align_up(sizeof(uint32_t) * pairs) + sizeof(double) * pairs + 256));
+    // carry rows of the striped kernels: one haplotype (+2 separators) per warp, three rows of doubles
+    {
+        const int ctas64 = std::max(forward_f64_ctas_per_sm(false), forward_f64_ctas_per_sm(true));
+        const int ctas32 = forward_f32_ctas_per_sm(8, 32, true);
+        const size_t warps = (size_t)c->sm_count * std::max(ctas64, ctas32) * kWarpsPerCta;
+        PMM_CUDA(c, c->d_scratch.reserve(warps * 3 * (size_t)(max_hap + 8) * sizeof(double)));
+    }
+
+    cudaStream_t s = c->stream;
+    PMM_CUDA(c, cudaMemcpyAsync(c->d_in.p, c->h_in.p, arena, cudaMemcpyHostToDevice, s));
+    PMM_CUDA(c, cudaMemsetAsync(c->d_stream.p, 0, kStreamFrontPad, s));
+    PMM_CUDA(c, cudaMemsetAsync(static_cast<char*>(c->d_stream.p) + kStreamFrontPad + pos + 1, 0, kStreamTailPad, s));
+    char* db = static_cast<char*>(c->d_in.p);
+    const HostTables& ht = host_tables();
+    PMM_CUDA(c, launch_build_stream(reinterpret_cast<uint8_t*>(db + c->off_hblob), reinterpret_cast<HapDesc*>(db + c->off_hdesc),
+                                    reinterpret_cast<uint32_t*>(db + c->off_spos), num_hap,
+                                    static_cast<uint8_t*>(c->d_stream.p) + kStreamFrontPad,
+                                    static_cast<float*>(c->d_iyf.p), static_cast<double*>(c->d_iyd.p), ht.ic_f, ht.ic_d, s));
+
+    c->num_read = num_read; c->num_hap = num_hap; c->num_region = num_region; c->num_tasks = (uint32_t)tasks.size();
+    c->pairs = pairs; c->cells = cells;
+    c->regions.assign(regions, regions + num_region);
+    c->stats = pmm_stats_t{};
+    c->stats.pairs = pairs; c->stats.cells = cells; c->stats.h2d_bytes = arena; c->stats.f32_tasks = c->num_tasks;
+    c->stats.ms_stage = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    c->staged = true;
+    return PMM_OK;
+}
+
+// Walk the reference's wire format (PairHMMHostInterface.cpp:175-207) and return offsets into the blob.
+bool scan_reads(const uint8_t* p, uint64_t n, std::vector<uint32_t>& off, std::vector<uint32_t>& len)
+{
+    if (n < 4) return false;
+    int32_t num; memcpy(&num, p, 4);
+    if (num < 0) return false;
+    uint64_t pos = 4;
+    off.resize(num); len.resize(num);
+    for (int32_t i = 0; i < num; ++i) {
+        if (pos + 4 > n) return false;
+        int32_t l; memcpy(&l, p + pos, 4); pos += 4;
+        if (l < 0 || pos + 5ull * l > n) return false;
+        off[i] = (uint32_t)pos; len[i] = (uint32_t)l; pos += 5ull * l;
+    }
+    return true;
+}
+
+bool scan_haps(const uint8_t* p, uint64_t n, std::vector<uint32_t>& off, std::vector<uint32_t>& len)
+{
+    if (n < 4) return false;
+    int32_t num; memcpy(&num, p, 4);
+    if (num < 0) return false;
+    uint64_t pos = 4;
+    off.resize(num); len.resize(num);
+    for (int32_t i = 0; i < num; ++i) {
+        if (pos + 4 > n) return false;
+        int32_t l; memcpy(&l, p + pos, 4); pos += 4;
+        if (l < 0 || pos + (uint64_t)l > n) return false;
+        off[i] = (uint32_t)pos; len[i] = (uint32_t)l; pos += l;
+    }
+    return true;
+}
+
+// Gather the wire format into the flat layout (five tracks + offsets) the stager takes.
+int flatten_serialized(pmm_ctx* c, const void* reads_ser, uint64_t reads_bytes, const void* haps_ser, uint64_t haps_bytes)
+{
+    std::vector<uint32_t> roff, rlen, hoff, hlen;
+    const uint8_t* rp = static_cast<const uint8_t*>(reads_ser);
+    const uint8_t* hp = static_cast<const uint8_t*>(haps_ser);
+    if (!rp || !hp || !scan_reads(rp, reads_bytes, roff, rlen) || !scan_haps(hp, haps_bytes, hoff, hlen))
+        return c->fail(PMM_ERR_INVALID, "malformed serialized block");
+    const size_t nr = roff.size(), nh = hoff.size();
+    c->tmp_roff.assign(nr + 1, 0); c->tmp_hoff.assign(nh + 1, 0);
+    for (size_t i = 0; i < nr; ++i) c->tmp_roff[i + 1] = c->tmp_roff[i] + rlen[i];
+    for (size_t i = 0; i < nh; ++i) c->tmp_hoff[i + 1] = c->tmp_hoff[i] + hlen[i];
+    for (int t = 0; t < 5; ++t) c->tmp_tracks[t].resize(c->tmp_roff[nr]);
+    c->tmp_hap.resize(c->tmp_hoff[nh]);
+    for (size_t i = 0; i < nr; ++i)
+        for (int t = 0; t < 5; ++t)
+            memcpy(c->tmp_tracks[t].data() + c->tmp_roff[i], rp + roff[i] + (size_t)t * rlen[i], rlen[i]);
+    for (size_t i = 0; i < nh; ++i) memcpy(c->tmp_hap.data() + c->tmp_hoff[i], hp + hoff[i], hlen[i]);
+    return PMM_OK;
+}
+
+int stage_tmp_single_region(pmm_ctx* c)
+{
+    const uint32_t nr = (uint32_t)c->tmp_roff.size() - 1, nh = (uint32_t)c->tmp_hoff.size() - 1;
+    if (nr == 0 || nh == 0) return c->fail(PMM_ERR_INVALID, "empty batch");
+    ReadSrc rs;
+    for (int t = 0; t < 5; ++t) rs.base[t] = c->tmp_tracks[t].data();
+    pmm_region_t reg{0, nr, 0, nh};
+    return stage_common(c, nr, c->tmp_roff.data(), rs, nh, c->tmp_hoff.data(), c->tmp_hap.data(), 1, &reg);
+}
+
+void parallel_for(uint64_t n, uint64_t grain, const std::function<void(uint64_t, uint64_t)>& f)
+{
+    unsigned hw = std::thread::hardware_concurrency();
+    uint64_t nt = std::min<uint64_t>(std::max(1u, std::min(hw, 16u)), (n + grain - 1) / std::max<uint64_t>(grain, 1));
+    if (nt <= 1) { f(0, n); return; }
+    std::vector<std::thread> th;
+    for (uint64_t t = 0; t + 1 < nt; ++t) th.emplace_back(f, n * t / nt, n * (t + 1) / nt);
+    f(n * (nt - 1) / nt, n);
+    for (auto& x : th) x.join();
+}
+}  // namespace
+
+// =========================================================================================================
+extern "C" {
+
+int pmm_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int pmm_create(int device, pmm_ctx** out)
+{
+    if (!out) return PMM_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        g_create_error = "no CUDA device visible; this engine has no CPU fallback";
+        return PMM_ERR_NO_DEVICE;
+    }
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+    if (device >= n) { g_create_error = "device index out of range"; return PMM_ERR_INVALID; }
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        g_create_error = cudaGetErrorString(e); return PMM_ERR_CUDA;
+    }
+    if (prop.major != 10) {
+        g_create_error = std::string("kernels are built for sm_100a only; device is ") + prop.name;
+        return PMM_ERR_NO_DEVICE;
+    }
+    pmm_ctx* c = new pmm_ctx();
+    c->device = device; c->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_create_error = cudaGetErrorString(e); delete c; return PMM_ERR_CUDA;
+    }
+    c->stream = c->own_stream;
+    for (auto& ev : c->ev) cudaEventCreate(&ev);
+    *out = c;
+    return PMM_OK;
+}
+
+void pmm_destroy(pmm_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (DevBuf* b : {&c->tables, &c->d_in, &c->d_stream, &c->d_iyf, &c->d_iyd, &c->d_raw, &c->d_fb_tasks, &c->d_fb_idx,
+                      &c->d_tiny_tasks, &c->d_dres, &c->d_ctrl, &c->d_scratch, &c->d_probe}) b->release();
+    c->h_in.release(); c->h_out.release();
+    for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+const char* pmm_last_error(const pmm_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int pmm_set_option(pmm_ctx* c, const char* key, const char* value)
+{
+    if (!c || !key || !value) return PMM_ERR_INVALID;
+    const std::string k(key);
+    if (k == "stream") {
+        const unsigned long long v = strtoull(value, nullptr, 0);
+        c->stream = v ? reinterpret_cast<cudaStream_t>(v) : c->own_stream;
+        return PMM_OK;
+    }
+    if (k == "tasks_per_warp") {
+        const int v = atoi(value);
+        if (v < 1 || v > 64) return c->fail(PMM_ERR_INVALID, "tasks_per_warp out of range");
+        c->tasks_per_warp = v;
+        return PMM_OK;
+    }
+    return c->fail(PMM_ERR_INVALID, "unknown option " + k);
+}
+
+int pmm_stage_flat(pmm_ctx* c, uint32_t num_read, const uint32_t* read_off,
+                   const uint8_t* bases, const uint8_t* q, const uint8_t* i, const uint8_t* d, const uint8_t* cc,
+                   uint32_t num_hap, const uint32_t* hap_off, const uint8_t* hap_bases,
+                   uint32_t num_region, const pmm_region_t* regions)
+{
+    if (!c) return PMM_ERR_INVALID;
+    if (!bases || !q || !i || !d || !cc || !hap_bases) return c->fail(PMM_ERR_INVALID, "null track");
+    cudaSetDevice(c->device);
+    ReadSrc rs{{bases, q, i, d, cc}};
+    return stage_common(c, num_read, read_off, rs, num_hap, hap_off, hap_bases, num_region, regions);
+}
+
+int pmm_launch(pmm_ctx* c)
+{
+    if (!c) return PMM_ERR_INVALID;
+    if (!c->staged) return c->fail(PMM_ERR_STATE, "pmm_launch before pmm_stage_*");
+    cudaSetDevice(c->device);
+    cudaStream_t s = c->stream;
+    char* db = static_cast<char*>(c->d_in.p);
+    uint32_t* ctrl = static_cast<uint32_t*>(c->d_ctrl.p);       // [0] fallback count, [1] flush count, [2..] queue cursors
+    uint32_t launches = 0;
+    PMM_CUDA(c, cudaEventRecord(c->ev[0], s));
+    PMM_CUDA(c, cudaMemsetAsync(ctrl, 0, sizeof(uint32_t) * 256, s));
+
+    ForwardArgs a{};
+    a.read_blob = reinterpret_cast<uint8_t*>(db + c->off_rblob);
+    a.reads = reinterpret_cast<ReadDesc*>(db + c->off_rdesc);
+    a.stream = static_cast<uint8_t*>(c->d_stream.p) + kStreamFrontPad;
+    a.spos = reinterpret_cast<uint32_t*>(db + c->off_spos);
+    a.tab = c->dtab;
+    a.scratch = c->d_scratch.p;
+    a.scratch_stride = c->max_hap_len + 8;
+
+    // ---- float pass, one launch per (K, W) variant present in the job -----------------------------------------
+    if (c->segs.size() > 200) return c->fail(PMM_ERR_INVALID, "too many kernel variants in one job");
+    uint32_t cursor = 2;
+    for (const LaunchSeg& seg : c->segs) {
+        a.inity = c->d_iyf.p;
+        a.tasks = reinterpret_cast<Task*>(db + c->off_tasks) + seg.task_first;
+        a.ntasks = seg.task_count; a.ntasks_dev = nullptr;
+        a.counter = ctrl + cursor++;
+        a.out = c->d_raw.p;
+        const int per_sm = forward_f32_ctas_per_sm(seg.v.K, seg.v.W, seg.v.striped);
+        if (per_sm <= 0) return c->fail(PMM_ERR_INVALID, "kernel variant unavailable");
+        const int ctas = (int)std::min<uint64_t>((seg.task_count + kWarpsPerCta - 1) / kWarpsPerCta, (uint64_t)c->sm_count * per_sm);
+        PMM_CUDA(c, launch_forward_f32(seg.v.K, seg.v.W, seg.v.striped, a, ctas, s));
+        ++launches;
+    }
+    PMM_CUDA(c, cudaEventRecord(c->ev[1], s));
+
+    // ---- fallback: compaction, double re-run, flush-to-zero re-run of the tiny ones ---------------------------
+    PMM_CUDA(c, launch_compact_fallback(static_cast<float*>(c->d_raw.p), reinterpret_cast<RegionDesc*>(db + c->off_regions),
+                                        c->num_region, (uint32_t)c->pairs, static_cast<Task*>(c->d_fb_tasks.p),
+                                        static_cast<uint32_t*>(c->d_fb_idx.p), ctrl + 0, (uint32_t)c->pairs, s));
+    ++launches;
+    a.inity = c->d_iyd.p;
+    a.out = c->d_dres.p;
+    a.tasks = static_cast<Task*>(c->d_fb_tasks.p); a.ntasks = 0; a.ntasks_dev = ctrl + 0; a.counter = ctrl + cursor++;
+    PMM_CUDA(c, launch_forward_f64(false, a, c->sm_count * std::max(1, forward_f64_ctas_per_sm(false)), s));
+    ++launches;
+    // Intermediate products below DBL_MIN are flushed to zero on the reference's x86 (FTZ on); they can only
+    // influence results that are themselves tiny.  Everything below 2^-800 (scaled by 2^1020) is recomputed with
+    // the flush emulated after every product; above it the two arithmetics agree ("FTZ").
+    PMM_CUDA(c, launch_compact_tiny(static_cast<double*>(c->d_dres.p), static_cast<Task*>(c->d_fb_tasks.p), ctrl + 0,
+                                    ldexp(1.0, -800), static_cast<Task*>(c->d_tiny_tasks.p), ctrl + 1, s));
+    ++launches;
+    a.tasks = static_cast<Task*>(c->d_tiny_tasks.p); a.ntasks_dev = ctrl + 1; a.counter = ctrl + cursor++;
+    PMM_CUDA(c, launch_forward_f64(true, a, c->sm_count * std::max(1, forward_f64_ctas_per_sm(true)), s));
+    ++launches;
+    PMM_CUDA(c, cudaEventRecord(c->ev[2], s));
+    c->stats.kernel_launches = launches;
+    c->launched = true;
+    return PMM_OK;
+}
+
+int pmm_sync(pmm_ctx* c)
+{
+    if (!c) return PMM_ERR_INVALID;
+    cudaSetDevice(c->device);
+    PMM_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->launched) {
+        cudaEventElapsedTime(&c->stats.ms_f32, c->ev[0], c->ev[1]);
+        cudaEventElapsedTime(&c->stats.ms_fallback, c->ev[1], c->ev[2]);
+    }
+    return PMM_OK;
+}
+
+static int fetch_common(pmm_ctx* c, bool want_lists, uint32_t* nfb_out, uint32_t* ntiny_out)
+{
+    if (!c->launched) return c->fail(PMM_ERR_STATE, "fetch before pmm_launch");
+    cudaSetDevice(c->device);
+    cudaStream_t s = c->stream;
+    char* ho = static_cast<char*>(c->h_out.p);
+    uint32_t* hctrl = reinterpret_cast<uint32_t*>(ho);                          // 256 B header
+    float* hraw = reinterpret_cast<float*>(ho + 256);
+    PMM_CUDA(c, cudaMemcpyAsync(hctrl, c->d_ctrl.p, 8, cudaMemcpyDeviceToHost, s));
+    PMM_CUDA(c, cudaMemcpyAsync(hraw, c->d_raw.p, sizeof(float) * c->pairs, cudaMemcpyDeviceToHost, s));
+    PMM_CUDA(c, cudaStreamSynchronize(s));
+    const uint32_t nfb = hctrl[0], ntiny = hctrl[1];
+    uint64_t d2h = 8 + sizeof(float) * c->pairs;
+    if (want_lists && nfb) {
+        uint32_t* hidx = reinterpret_cast<uint32_t*>(ho + 256 + align_up(sizeof(float) * c->pairs));
+        double* hd = reinterpret_cast<double*>(reinterpret_cast<char*>(hidx) + align_up(sizeof(uint32_t) * c->pairs));
+        PMM_CUDA(c, cudaMemcpyAsync(hidx, c->d_fb_idx.p, sizeof(uint32_t) * nfb, cudaMemcpyDeviceToHost, s));
+        PMM_CUDA(c, cudaMemcpyAsync(hd, c->d_dres.p, sizeof(double) * nfb, cudaMemcpyDeviceToHost, s));
+        PMM_CUDA(c, cudaStreamSynchronize(s));
+        d2h += (sizeof(uint32_t) + sizeof(double)) * nfb;
+    }
+    c->stats.fallback_pairs = nfb; c->stats.flush_pairs = ntiny; c->stats.d2h_bytes = d2h;
+    cudaEventElapsedTime(&c->stats.ms_f32, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&c->stats.ms_fallback, c->ev[1], c->ev[2]);
+    if (nfb_out) *nfb_out = nfb;
+    if (ntiny_out) *ntiny_out = ntiny;
+    return PMM_OK;
+}
+
+int pmm_fetch_raw(pmm_ctx* c, float* out_raw, uint64_t cap)
+{
+    if (!c || !out_raw) return PMM_ERR_INVALID;
+    if (cap < c->pairs) return c->fail(PMM_ERR_INVALID, "output buffer too small");
+    auto t0 = std::chrono::steady_clock::now();
+    int rc = fetch_common(c, false, nullptr, nullptr);
+    if (rc) return rc;
+    memcpy(out_raw, static_cast<char*>(c->h_out.p) + 256, sizeof(float) * c->pairs);
+    c->stats.ms_fetch = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return PMM_OK;
+}
+
+int pmm_fetch_fallback_mask(pmm_ctx* c, uint8_t* mask, uint64_t cap)
+{
+    if (!c || !mask) return PMM_ERR_INVALID;
+    if (cap < c->pairs) return c->fail(PMM_ERR_INVALID, "mask buffer too small");
+    uint32_t nfb = 0;
+    int rc = fetch_common(c, true, &nfb, nullptr);
+    if (rc) return rc;
+    memset(mask, 0, c->pairs);
+    const char* ho = static_cast<const char*>(c->h_out.p);
+    const uint32_t* hidx = reinterpret_cast<const uint32_t*>(ho + 256 + align_up(sizeof(float) * c->pairs));
+    for (uint32_t k = 0; k < nfb; ++k) mask[hidx[k]] = 1;
+    return PMM_OK;
+}
+
+int pmm_fetch_log10(pmm_ctx* c, double* out, uint64_t cap, uint64_t* n_fallback)
+{
+    if (!c || !out) return PMM_ERR_INVALID;
+    if (cap < c->pairs) return c->fail(PMM_ERR_INVALID, "output buffer too small");
+    auto t0 = std::chrono::steady_clock::now();
+    uint32_t nfb = 0;
+    int rc = fetch_common(c, true, &nfb, nullptr);
+    if (rc) return rc;
+    const char* ho = static_cast<const char*>(c->h_out.p);
+    const float* hraw = reinterpret_cast<const float*>(ho + 256);
+    const uint32_t* hidx = reinterpret_cast<const uint32_t*>(ho + 256 + align_up(sizeof(float) * c->pairs));
+    const double* hd = reinterpret_cast<const double*>(reinterpret_cast<const char*>(hidx) + align_up(sizeof(uint32_t) * c->pairs));
+    const HostTables& t = host_tables();
+    const float licf = t.log10_ic_f; const double licd = t.log10_ic_d;
+    // (double)(log10f(v) - log10f(2^120)), float subtraction (PairHMMWorker.cpp:190); host libm on purpose
+    parallel_for(c->pairs, 1 << 15, [&](uint64_t a, uint64_t b) { for (uint64_t k = a; k < b; ++k) out[k] = (double)(log10f(hraw[k]) - licf); });
+    // log10(d) - log10(2^1020) for the pairs that fell back (PairHMMWorker.cpp:184)
+    for (uint32_t k = 0; k < nfb; ++k) out[hidx[k]] = log10(hd[k]) - licd;
+    if (n_fallback) *n_fallback = nfb;
+    c->stats.ms_fetch = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return PMM_OK;
+}
+
+int pmm_get_stats(const pmm_ctx* c, pmm_stats_t* out)
+{
+    if (!c || !out) return PMM_ERR_INVALID;
+    *out = c->stats;
+    return PMM_OK;
+}
+
+int pmm_forward_raw_serialized(pmm_ctx* c, const void* reads_ser, uint64_t reads_bytes, const void* haps_ser,
+                               uint64_t haps_bytes, float* out_raw, uint64_t cap, int* num_read, int* num_hap)
+{
+    if (!c || !out_raw) return PMM_ERR_INVALID;
+    cudaSetDevice(c->device);
+    int rc = flatten_serialized(c, reads_ser, reads_bytes, haps_ser, haps_bytes);
+    if (rc) return rc;
+    if (num_read) *num_read = (int)c->tmp_roff.size() - 1;
+    if (num_hap) *num_hap = (int)c->tmp_hoff.size() - 1;
+    if ((rc = stage_tmp_single_region(c))) return rc;
+    if ((rc = pmm_launch(c))) return rc;
+    return pmm_fetch_raw(c, out_raw, cap);
+}
+
+int pmm_forward_log10_serialized(pmm_ctx* c, const void* reads_ser, uint64_t reads_bytes, const void* haps_ser,
+                                 uint64_t haps_bytes, double* out, uint64_t cap, int* num_read, int* num_hap,
+                                 uint64_t* n_fallback)
+{
+    if (!c || !out) return PMM_ERR_INVALID;
+    cudaSetDevice(c->device);
+    int rc = flatten_serialized(c, reads_ser, reads_bytes, haps_ser, haps_bytes);
+    if (rc) return rc;
+    if (num_read) *num_read = (int)c->tmp_roff.size() - 1;
+    if (num_hap) *num_hap = (int)c->tmp_hoff.size() - 1;
+    if ((rc = stage_tmp_single_region(c))) return rc;
+    if ((rc = pmm_launch(c))) return rc;
+    return pmm_fetch_log10(c, out, cap, n_fallback);
+}
+
+int pmm_forward_log10(pmm_ctx* c, const pmm_read_t* reads, int num_read, const pmm_hap_t* haps, int num_hap,
+                      double* out, uint64_t* n_fallback)
+{
+    if (!c || !reads || !haps || !out || num_read <= 0 || num_hap <= 0) return c ? c->fail(PMM_ERR_INVALID, "bad arguments") : PMM_ERR_INVALID;
+    cudaSetDevice(c->device);
+    c->tmp_roff.assign(num_read + 1, 0); c->tmp_hoff.assign(num_hap + 1, 0);
+    for (int i = 0; i < num_read; ++i) {
+        if (reads[i].len <= 0) return c->fail(PMM_ERR_INVALID, "read of length 0");
+        c->tmp_roff[i + 1] = c->tmp_roff[i] + (uint32_t)reads[i].len;
+    }
+    for (int i = 0; i < num_hap; ++i) {
+        if (haps[i].len <= 0) return c->fail(PMM_ERR_INVALID, "haplotype of length 0");
+        c->tmp_hoff[i + 1] = c->tmp_hoff[i] + (uint32_t)haps[i].len;
+    }
+    for (int t = 0; t < 5; ++t) c->tmp_tracks[t].resize(c->tmp_roff[num_read]);
+    c->tmp_hap.resize(c->tmp_hoff[num_hap]);
+    for (int i = 0; i < num_read; ++i) {
+        const char* src[5] = {reads[i]._b, reads[i]._q, reads[i]._i, reads[i]._d, reads[i]._c};
+        for (int t = 0; t < 5; ++t) memcpy(c->tmp_tracks[t].data() + c->tmp_roff[i], src[t], reads[i].len);
+    }
+    for (int i = 0; i < num_hap; ++i) memcpy(c->tmp_hap.data() + c->tmp_hoff[i], haps[i]._b, haps[i].len);
+    int rc = stage_tmp_single_region(c);
+    if (rc) return rc;
+    if ((rc = pmm_launch(c))) return rc;
+    return pmm_fetch_log10(c, out, (uint64_t)num_read * num_hap, n_fallback);
+}
+
+int pmm_measure_fp32_peak(pmm_ctx* c, double* lane_instr_per_s, double* sm_mhz)
+{
+    if (!c || !lane_instr_per_s) return PMM_ERR_INVALID;
+    cudaSetDevice(c->device);
+    const int ctas = c->sm_count * 8, iters = 4000;
+    PMM_CUDA(c, c->d_probe.reserve(sizeof(float) * ctas * 256));
+    cudaStream_t s = c->stream;
+    PMM_CUDA(c, launch_fp32_probe(static_cast<float*>(c->d_probe.p), 200, ctas, s));
+    double best = 0;
+    for (int rep = 0; rep < 3; ++rep) {
+        PMM_CUDA(c, cudaEventRecord(c->ev[3], s));
+        PMM_CUDA(c, launch_fp32_probe(static_cast<float*>(c->d_probe.p), iters, ctas, s));
+        cudaEvent_t e1; cudaEventCreate(&e1);
+        PMM_CUDA(c, cudaEventRecord(e1, s));
+        PMM_CUDA(c, cudaEventSynchronize(e1));
+        float ms = 0; cudaEventElapsedTime(&ms, c->ev[3], e1); cudaEventDestroy(e1);
+        const double ops = (double)ctas * 256 * iters * 64.0;
+        best = std::max(best, ops / (ms * 1e-3));
+    }
+    *lane_instr_per_s = best;
+    if (sm_mhz) *sm_mhz = best / ((double)c->sm_count * 128.0) * 1e-6;   // lower bound: assumes 128 lanes/clk/SM fully used
+    return PMM_OK;
+}
+
+}  // extern "C"

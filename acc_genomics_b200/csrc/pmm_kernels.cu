@@ -1,0 +1,489 @@
+// pmm_kernels.cu -- sm_100a kernels of the PairHMM forward path.
+//
+// The recurrence and its operation order are those of the reference's AVX implementation
+// (/root/reference/pairhmm/xlnx/host/avx-pairhmm-template.h:183-198 computeMXY, :136-177 boundary conditions,
+// :308-343 reduction); SURVEY.md appendix A restates them.  Every multiply and add below is an individually
+// rounded __fmul_rn/__fadd_rn (never contracted), the file is compiled with -ftz=true, and the tables come from
+// the host libm, so the float result is bit-identical to the reference built without FMA contraction.
+//
+// Mapping to the machine (B200-first, not a translation of the AVX or FPGA code):
+//   * One read occupies W lanes of a warp (W = 8, 16 or 32); each lane keeps K consecutive rows of the M/X/Y
+//     matrices and their transition parameters in registers.  Rows are end-aligned: the read's last row is row
+//     K-1 of lane W-1, the unused rows at the top are "boundary rows" (M = X = 0, Y = 2^120/haplen), which also
+//     absorb the undefined value lane 0 receives from the shuffle.
+//   * The anti-diagonal wavefront runs across lanes: at step t lane l works on column t - l.  The last row of
+//     lane l-1 reaches lane l through three __shfl_up_sync per step (M, X, Y), i.e. 3/K shuffles per cell.
+//   * A warp does not handle one pair at a time: the haplotypes of a region are concatenated into one stream
+//     with separator elements, and the wavefront flows from one haplotype straight into the next, so the
+//     fill/drain bubble (W-1 steps) is paid once per task instead of once per pair.  A separator step resets the
+//     lane's state and (in lane W-1) stores the previous haplotype's result.
+//   * The match/mismatch emission weight is not selected per cell (that would cost a LOP3 + FSEL issue slot each;
+//     the measured issue rate is 1 instr/clk/SMSP for FP32 and ALU alike, tools/microbench/issue_mix2.cu): each
+//     warp stages a [5 classes][K rows] weight table for its reads in shared memory, laid out so that one
+//     conflict-free LDS.128 per 4 rows fetches the weights for whatever haplotype base the lane is looking at.
+//   * Steady-state steps are branch-free; only the W+1 steps around a separator run the checked variant.
+//   * Work is pulled by warps from a global queue (atomicAdd), grid = SMs x resident CTAs.
+#include "pmm_kernels.cuh"
+
+#include <cfloat>
+
+namespace pmm {
+namespace {
+
+__device__ __forceinline__ int base_class(unsigned ch)
+{
+    // A,C,T,G,N -> 0..4, everything else 0 (ConvertChar's zero-initialised table, host_type.h:123-143)
+    return ch == 'C' ? 1 : ch == 'T' ? 2 : ch == 'G' ? 3 : ch == 'N' ? 4 : 0;
+}
+
+template <typename T> struct Arith;
+
+template <> struct Arith<float> {
+    static constexpr int kStripe = 8;          // AVX float vector = 8 rows (avx-functions-float.h AVX_LENGTH)
+    static constexpr int kVec = 4;             // elements per 16-byte shared-memory access
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+    static __device__ __forceinline__ float ph2pr(const DeviceTables& t, int q) { return __ldg(t.ph2pr_f + q); }
+    static __device__ __forceinline__ float m2m(const DeviceTables& t, int i) { return __ldg(t.m2m_f + i); }
+};
+
+template <> struct Arith<double> {
+    static constexpr int kStripe = 4;          // AVX double vector = 4 rows
+    static constexpr int kVec = 2;
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+    static __device__ __forceinline__ double ph2pr(const DeviceTables& t, int q) { return __ldg(t.ph2pr_d + q); }
+    static __device__ __forceinline__ double m2m(const DeviceTables& t, int i) { return __ldg(t.m2m_d + i); }
+};
+
+// x86 flush-to-zero for doubles: a product below DBL_MIN becomes +0 (all operands here are non-negative).
+// Sums of flushed, non-negative operands can never be subnormal, so only products need it.
+template <bool FLUSH> __device__ __forceinline__ double flush(double x)
+{
+    if (FLUSH) return x < DBL_MIN ? 0.0 : x;
+    return x;
+}
+template <bool FLUSH> __device__ __forceinline__ float flush(float x) { return x; }   // -ftz=true does it in hardware
+
+template <typename T> __device__ __forceinline__ T ld_cg(const T* p) { return __ldcg(p); }
+
+template <typename T, int K>
+__host__ __device__ constexpr int wtab_elems() { return 5 * ((K + Arith<T>::kVec - 1) / Arith<T>::kVec) * 32 * Arith<T>::kVec; }
+
+// ---------------------------------------------------------------------------------------------------------
+// The forward kernel.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T, int K, int W, bool STRIPED, bool FLUSH>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) pmm_forward_kernel(const ForwardArgs a)
+{
+    using A = Arith<T>;
+    constexpr int VEC = A::kVec;
+    constexpr int KQ = (K + VEC - 1) / VEC;           // 16-byte weight vectors per lane and class
+    constexpr int CLS_STRIDE = KQ * 32 * VEC;         // elements between the tables of two haplotype classes
+    static_assert(W == 8 || W == 16 || W == 32, "W");
+    static_assert(!STRIPED || W == 32, "striped variant handles one read per warp");
+
+    extern __shared__ uint4 smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane / W, l = lane % W;
+    T* wtab = reinterpret_cast<T*>(smem_raw) + warp * wtab_elems<T, K>();
+    T* wlane = wtab + lane * VEC;
+
+    const uint32_t ntasks = a.ntasks_dev ? *a.ntasks_dev : a.ntasks;
+    const T* inity = static_cast<const T*>(a.inity);
+    T* out = static_cast<T*>(a.out);
+    const uint32_t gwarp = blockIdx.x * kWarpsPerCta + warp;
+
+    for (;;) {
+        uint32_t ti = 0;
+        if (lane == 0) ti = atomicAdd(a.counter, 1u);
+        ti = __shfl_sync(0xffffffffu, ti, 0);
+        if (ti >= ntasks) break;
+
+        const Task* tk = a.tasks + ti;
+        const uint32_t hap_first = tk->hap_first, nhaps = tk->nhaps;
+        const bool valid = (uint32_t)g < tk->nreads;
+        ReadDesc rd = {0u, 0u, 0u};
+        uint32_t out_base = 0;
+        if (valid) { rd = a.reads[tk->read[g]]; out_base = tk->out_base[g]; }
+        const int R = (int)rd.len;
+        const int nstripes = STRIPED ? (R + W * K) / (W * K) : 1;       // ceil((R + 1) / (W*K))
+        const int pad = nstripes * W * K - R;                            // >= 1 boundary rows at the top
+
+        const uint32_t s0 = a.spos[hap_first];
+        const int Lc = (int)(a.spos[hap_first + nhaps] - s0) + 1;        // elements incl. the terminal separator
+        const int Tsteps = Lc + W - 1;
+        const uint8_t* sp = a.stream + s0 - l;                           // this lane's element at step t is sp[t]
+
+        T* scM = nullptr; T* scX = nullptr; T* scY = nullptr;
+        if (STRIPED) {
+            scM = static_cast<T*>(a.scratch) + (size_t)gwarp * 3 * a.scratch_stride;
+            scX = scM + a.scratch_stride; scY = scX + a.scratch_stride;
+        }
+
+        #pragma unroll 1
+        for (int stripe = 0; stripe < nstripes; ++stripe) {
+            // ---- per-row parameters (avx-pairhmm-template.h:108-127, :155-158) --------------------------
+            T pMM[K], pG[K], pMX[K], pXX[K], pMY[K], pYY[K];
+            unsigned padmask = 0, quirkmask = 0;
+            __syncwarp();                                                // previous task / stripe done with wtab
+            #pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const int r0 = stripe * W * K + l * K + j - pad;          // 0-based read base of this row
+                T mw = (T)0, xw = (T)0;
+                int cls = 0;
+                if (r0 >= 0 && valid) {
+                    const uint8_t* b = a.read_blob + rd.off + r0;
+                    cls = base_class(b[0]);
+                    const int q_ = b[rd.stride] & 127, i_ = b[2 * rd.stride] & 127;
+                    const int d_ = b[3 * rd.stride] & 127, c_ = b[4 * rd.stride] & 127;
+                    const int mx = max(i_, d_), mn = min(i_, d_);
+                    pMM[j] = A::m2m(a.tab, ((mx * (mx + 1)) >> 1) + mn);
+                    const T pc = A::ph2pr(a.tab, c_);
+                    pG[j] = A::sub((T)1.0, pc);
+                    pMX[j] = A::ph2pr(a.tab, i_);
+                    pXX[j] = pc;
+                    pMY[j] = A::ph2pr(a.tab, d_);
+                    pYY[j] = pc;
+                    const T dm = A::ph2pr(a.tab, q_);
+                    mw = A::sub((T)1.0, dm);
+                    xw = A::div(dm, (T)3.0);
+                    // first row of every AVX stripe but the first inherits M[r-1][1] as its "left M" in
+                    // column 1 (avx-pairhmm-template.h:171-176); r0 is 0-based, so rows r0 = 8,16,.. (4,8,.. double)
+                    if (r0 > 0 && (r0 % A::kStripe) == 0) quirkmask |= 1u << j;
+                } else {
+                    // boundary row: M = X = 0, Y keeps its value
+                    pMM[j] = (T)0; pG[j] = (T)0; pMX[j] = (T)0; pXX[j] = (T)0; pMY[j] = (T)0; pYY[j] = (T)1.0;
+                    padmask |= 1u << j;
+                }
+                #pragma unroll
+                for (int h = 0; h < 5; ++h) {
+                    const bool match = (cls == h) || cls == 4 || h == 4;
+                    wlane[h * CLS_STRIDE + (j / VEC) * 32 * VEC + (j % VEC)] = match ? mw : xw;
+                }
+            }
+            __syncwarp();
+
+            T M[K], X[K], Y[K];
+            #pragma unroll
+            for (int j = 0; j < K; ++j) { M[j] = (T)0; X[j] = (T)0; Y[j] = (T)0; }
+            T dM = (T)0, dX = (T)0, dY = (T)0;        // last row of the lane above, previous column (diagonal)
+            T sM = (T)0, sX = (T)0;                   // running sums of the read's last row
+            int nsep = 0;
+            bool done = false, first = false;
+            const bool last_stripe = stripe == nstripes - 1;
+            const bool carry_in = STRIPED && stripe > 0 && l == 0;
+            const bool carry_out = STRIPED && !last_stripe && l == W - 1;
+
+            // One column of K cells.  inM/inX/inY: last row of the lane above at this column.
+            auto cells = [&](unsigned e, T inM, T inX, T inY, bool fix_first) {
+                const T* wp = wlane + e * CLS_STRIDE;
+                T w[KQ * VEC];
+                #pragma unroll
+                for (int m = 0; m < KQ; ++m) {
+                    if (VEC == 4) {
+                        const float4 v = *reinterpret_cast<const float4*>(wp + m * 32 * VEC);
+                        w[m * VEC + 0] = v.x; w[m * VEC + 1] = v.y; w[m * VEC + 2] = v.z; w[m * VEC + 3] = v.w;
+                    } else {
+                        const double2 v = *reinterpret_cast<const double2*>(wp + m * 32 * VEC);
+                        w[m * VEC + 0] = v.x; w[m * VEC + 1] = v.y;
+                    }
+                }
+                T Mn[K], Xn[K], Yn[K];
+                #pragma unroll
+                for (int j = K - 1; j >= 0; --j) {
+                    const T md = j ? M[j - 1] : dM, xd = j ? X[j - 1] : dX, yd = j ? Y[j - 1] : dY;
+                    // M = ((Md*pMM + Xd*pGAPM) + Yd*pGAPM) * w        (avx-pairhmm-template.h:188)
+                    const T t3 = A::add(flush<FLUSH>(A::mul(md, pMM[j])), flush<FLUSH>(A::mul(xd, pG[j])));
+                    const T t5 = A::add(t3, flush<FLUSH>(A::mul(yd, pG[j])));
+                    Mn[j] = flush<FLUSH>(A::mul(t5, w[j]));
+                    // Y = Mleft*pMY + Yleft*pYY                        (:197)
+                    Yn[j] = A::add(flush<FLUSH>(A::mul(M[j], pMY[j])), flush<FLUSH>(A::mul(Y[j], pYY[j])));
+                }
+                #pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    const T mu = j ? Mn[j - 1] : inM, xu = j ? Xn[j - 1] : inX;
+                    // X = Mup*pMX + Xup*pXX                             (:194)
+                    Xn[j] = A::add(flush<FLUSH>(A::mul(mu, pMX[j])), flush<FLUSH>(A::mul(xu, pXX[j])));
+                }
+                if (fix_first) {
+                    // column 1 of a haplotype: the AVX stripe artefact (see quirkmask)
+                    #pragma unroll
+                    for (int j = 0; j < K; ++j)
+                        if (quirkmask & (1u << j)) Yn[j] = flush<FLUSH>(A::mul(j ? Mn[j - 1] : inM, pMY[j]));
+                }
+                #pragma unroll
+                for (int j = 0; j < K; ++j) { M[j] = Mn[j]; X[j] = Xn[j]; Y[j] = Yn[j]; }
+                sM = A::add(sM, M[K - 1]);          // (:328,:331) two sums, left to right
+                sX = A::add(sX, X[K - 1]);
+                dM = inM; dX = inX; dY = inY;
+            };
+
+            // Step with every check: separators, fill/drain, first column, stripe carries.
+            auto checked_step = [&](int t, unsigned e) {
+                T inM = __shfl_up_sync(0xffffffffu, M[K - 1], 1, W);
+                T inX = __shfl_up_sync(0xffffffffu, X[K - 1], 1, W);
+                T inY = __shfl_up_sync(0xffffffffu, Y[K - 1], 1, W);
+                const int p = t - l;
+                const bool active = p >= 0 && !done;
+                if (carry_in && active) { inM = ld_cg(scM + p); inX = ld_cg(scX + p); inY = ld_cg(scY + p); }
+                if (active) {
+                    if (e == kSep) {
+                        if (nsep > 0 && l == W - 1 && valid && last_stripe) out[out_base + nsep - 1] = A::add(sM, sX);
+                        done = nsep == (int)nhaps;
+                        const T iy = done ? (T)0 : inity[hap_first + nsep];
+                        ++nsep;
+                        #pragma unroll
+                        for (int j = 0; j < K; ++j) { M[j] = (T)0; X[j] = (T)0; Y[j] = (padmask >> j) & 1 ? iy : (T)0; }
+                        sM = (T)0; sX = (T)0;
+                        dM = inM; dX = inX; dY = inY;
+                        first = true;
+                    } else {
+                        cells(e, inM, inX, inY, first);
+                        first = false;
+                    }
+                    if (carry_out) { scM[p] = M[K - 1]; scX[p] = X[K - 1]; scY[p] = Y[K - 1]; }
+                }
+            };
+
+            // Branch-free step: every lane is inside the bases of a haplotype, past its first column.
+            auto steady_step = [&](int t, unsigned e) {
+                T inM = __shfl_up_sync(0xffffffffu, M[K - 1], 1, W);
+                T inX = __shfl_up_sync(0xffffffffu, X[K - 1], 1, W);
+                T inY = __shfl_up_sync(0xffffffffu, Y[K - 1], 1, W);
+                if (STRIPED) {
+                    const int p = t - l;
+                    if (carry_in) { inM = ld_cg(scM + p); inX = ld_cg(scX + p); inY = ld_cg(scY + p); }
+                    cells(e, inM, inX, inY, false);
+                    if (carry_out) { scM[p] = M[K - 1]; scX[p] = X[K - 1]; scY[p] = Y[K - 1]; }
+                } else {
+                    cells(e, inM, inX, inY, false);
+                }
+            };
+
+            int t = 0;
+            uint32_t hn = 0;                      // index (within the task) of the next separator lane 0 will meet
+            int next_sep = 0;                     // step at which lane 0 meets it
+            unsigned e = sp[0];
+            while (t < Tsteps) {
+                // checked window: lane l meets the separator at next_sep + l and its first column one step later
+                int wend = next_sep + W + 1;
+                if (wend > Tsteps) wend = Tsteps;
+                for (; t < wend; ++t) {
+                    const unsigned en = sp[t + 1];
+                    checked_step(t, e);
+                    e = en;
+                }
+                ++hn;
+                next_sep = hn <= nhaps ? (int)(a.spos[hap_first + hn] - s0) : Tsteps + W + 1;
+                int send = next_sep < Tsteps ? next_sep : Tsteps;
+                #pragma unroll 2
+                for (; t < send; ++t) {
+                    const unsigned en = sp[t + 1];
+                    steady_step(t, e);
+                    e = en;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Haplotype stream builder: one CTA per haplotype.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void build_stream_kernel(const uint8_t* __restrict__ blob, const HapDesc* __restrict__ haps,
+                                    const uint32_t* __restrict__ spos, uint32_t num_hap, uint8_t* __restrict__ stream,
+                                    float* __restrict__ iy_f, double* __restrict__ iy_d, float ic_f, double ic_d)
+{
+    const uint32_t h = blockIdx.x;
+    if (h >= num_hap) return;
+    const HapDesc d = haps[h];
+    uint8_t* dst = stream + spos[h];
+    if (threadIdx.x == 0) {
+        dst[0] = kSep;
+        // INITIAL_CONSTANT / haplen with the int converted to NUMBER first (avx-pairhmm-template.h:86)
+        iy_f[h] = __fdiv_rn(ic_f, (float)(int)d.len);
+        iy_d[h] = __ddiv_rn(ic_d, (double)(int)d.len);
+        if (h + 1 == num_hap) dst[1 + d.len] = kSep;
+    }
+    for (uint32_t k = threadIdx.x; k < d.len; k += blockDim.x) dst[1 + k] = (uint8_t)base_class(blob[d.off + k]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Fallback compaction: raw < 1e-28f  ->  single-pair task for the double kernel (PairHMMWorker.cpp:176).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void compact_fallback_kernel(const float* __restrict__ raw, const RegionDesc* __restrict__ regions,
+                                        uint32_t nregions, uint32_t total_pairs, Task* __restrict__ fb_tasks,
+                                        uint32_t* __restrict__ fb_out_index, uint32_t* fb_count, uint32_t cap)
+{
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total_pairs) return;
+    const float v = raw[idx];
+    if (!(v < 1e-28f)) return;                    // float compare, NaN -> false, exactly the reference's test
+    // locate the region by binary search on out_first
+    uint32_t lo = 0, hi = nregions - 1;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (regions[mid].out_first <= idx) lo = mid; else hi = mid - 1;
+    }
+    const RegionDesc r = regions[lo];
+    const uint32_t local = idx - r.out_first;
+    const uint32_t slot = atomicAdd(fb_count, 1u);
+    if (slot >= cap) return;
+    Task t;
+    t.read[0] = r.read_first + local / r.nhaps; t.read[1] = t.read[2] = t.read[3] = 0;
+    t.out_base[0] = slot; t.out_base[1] = t.out_base[2] = t.out_base[3] = 0;
+    t.hap_first = r.hap_first + local % r.nhaps;
+    t.nhaps = 1; t.nreads = 1; t.reserved = 0;
+    fb_tasks[slot] = t;
+    fb_out_index[slot] = idx;
+}
+
+__global__ void compact_tiny_kernel(const double* __restrict__ dres, const Task* __restrict__ fb_tasks,
+                                    const uint32_t* __restrict__ fb_count, double threshold,
+                                    Task* __restrict__ tiny_tasks, uint32_t* tiny_count)
+{
+    const uint32_t n = *fb_count;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (dres[i] < threshold) {
+            const uint32_t slot = atomicAdd(tiny_count, 1u);
+            tiny_tasks[slot] = fb_tasks[i];       // same read, hap and result slot: the re-run overwrites dres[i]
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// FP32 issue-rate probe (roofline denominator): 8 independent FMUL/FADD chains per thread.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fp32_probe_kernel(float* sink, int iters)
+{
+    float x[8];
+    #pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = 1.0f + threadIdx.x * 1e-3f + i;
+    const float m = 0.99999f, c = 1e-6f;
+    for (int it = 0; it < iters; ++it) {
+        #pragma unroll
+        for (int rep = 0; rep < 8; ++rep) {
+            #pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = (rep & 1) ? __fadd_rn(x[i], c) : __fmul_rn(x[i], m);
+        }
+    }
+    float s = 0;
+    #pragma unroll
+    for (int i = 0; i < 8; ++i) s += x[i];
+    sink[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Variant table
+// ---------------------------------------------------------------------------------------------------------
+template <typename T, int K, int W, bool STRIPED, bool FLUSH>
+cudaError_t launch_variant(const ForwardArgs& a, int ctas, cudaStream_t s)
+{
+    constexpr int smem = kWarpsPerCta * wtab_elems<T, K>() * (int)sizeof(T);
+    auto kern = pmm_forward_kernel<T, K, W, STRIPED, FLUSH>;
+    // per device, cheap: the context may live on any GPU of the box
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    kern<<<ctas, kWarpsPerCta * 32, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+template <typename T, int K, int W, bool STRIPED, bool FLUSH>
+int variant_ctas_per_sm()
+{
+    constexpr int smem = kWarpsPerCta * wtab_elems<T, K>() * (int)sizeof(T);
+    auto kern = pmm_forward_kernel<T, K, W, STRIPED, FLUSH>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kWarpsPerCta * 32, smem) != cudaSuccess) return 0;
+    return n;
+}
+
+// (K, W) variants of the float kernel.  Chosen so that every read length up to 32*16-1 has a variant with
+// >= ~85 % row utilisation: see pick_variant() in pmm_engine.cu.
+#define PMM_F32_VARIANTS(X) \
+    X(4, 8) X(5, 8) X(6, 8) X(7, 8) X(8, 8) X(10, 8) X(12, 8) X(13, 8) X(14, 8) X(16, 8) \
+    X(4, 16) X(5, 16) X(6, 16) X(7, 16) X(8, 16) X(9, 16) X(10, 16) X(11, 16) X(12, 16) X(14, 16) X(16, 16) \
+    X(4, 32) X(5, 32) X(6, 32) X(7, 32) X(8, 32) X(9, 32) X(10, 32) X(12, 32) X(14, 32) X(16, 32)
+
+}  // namespace
+
+bool forward_f32_has_variant(int K, int W)
+{
+#define X(k, w) if (K == k && W == w) return true;
+    PMM_F32_VARIANTS(X)
+#undef X
+    return false;
+}
+
+cudaError_t launch_forward_f32(int K, int W, bool striped, const ForwardArgs& a, int ctas, cudaStream_t s)
+{
+    if (striped) {
+        if (K == 8 && W == 32) return launch_variant<float, 8, 32, true, false>(a, ctas, s);
+        return cudaErrorInvalidValue;
+    }
+#define X(k, w) if (K == k && W == w) return launch_variant<float, k, w, false, false>(a, ctas, s);
+    PMM_F32_VARIANTS(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+int forward_f32_ctas_per_sm(int K, int W, bool striped)
+{
+    if (striped) return (K == 8 && W == 32) ? variant_ctas_per_sm<float, 8, 32, true, false>() : 0;
+#define X(k, w) if (K == k && W == w) return variant_ctas_per_sm<float, k, w, false, false>();
+    PMM_F32_VARIANTS(X)
+#undef X
+    return 0;
+}
+
+cudaError_t launch_forward_f64(bool flush, const ForwardArgs& a, int ctas, cudaStream_t s)
+{
+    return flush ? launch_variant<double, kF64K, 32, true, true>(a, ctas, s)
+                 : launch_variant<double, kF64K, 32, true, false>(a, ctas, s);
+}
+
+int forward_f64_ctas_per_sm(bool flush)
+{
+    return flush ? variant_ctas_per_sm<double, kF64K, 32, true, true>()
+                 : variant_ctas_per_sm<double, kF64K, 32, true, false>();
+}
+
+cudaError_t launch_build_stream(const uint8_t* hap_blob, const HapDesc* haps, const uint32_t* spos, uint32_t num_hap,
+                                uint8_t* stream, float* inity_f, double* inity_d, float ic_f, double ic_d,
+                                cudaStream_t s)
+{
+    if (num_hap == 0) return cudaSuccess;
+    build_stream_kernel<<<num_hap, 128, 0, s>>>(hap_blob, haps, spos, num_hap, stream, inity_f, inity_d, ic_f, ic_d);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_compact_fallback(const float* raw, const RegionDesc* regions, uint32_t nregions,
+                                    uint32_t total_pairs, Task* fb_tasks, uint32_t* fb_out_index,
+                                    uint32_t* fb_count, uint32_t fb_capacity, cudaStream_t s)
+{
+    if (total_pairs == 0) return cudaSuccess;
+    compact_fallback_kernel<<<(total_pairs + 255) / 256, 256, 0, s>>>(raw, regions, nregions, total_pairs, fb_tasks,
+                                                                     fb_out_index, fb_count, fb_capacity);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_compact_tiny(const double* dres, const Task* fb_tasks, const uint32_t* fb_count,
+                                double threshold, Task* tiny_tasks, uint32_t* tiny_count, cudaStream_t s)
+{
+    compact_tiny_kernel<<<148, 256, 0, s>>>(dres, fb_tasks, fb_count, threshold, tiny_tasks, tiny_count);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fp32_probe(float* sink, int iters, int ctas, cudaStream_t s)
+{
+    fp32_probe_kernel<<<ctas, 256, 0, s>>>(sink, iters);
+    return cudaGetLastError();
+}
+
+}  // namespace pmm

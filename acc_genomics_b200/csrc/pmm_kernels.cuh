@@ -1,0 +1,97 @@
+// pmm_kernels.cuh -- device-side data model of the B200 PairHMM forward engine (declarations shared by the
+// kernels in pmm_kernels.cu and the C ABI in pmm_engine.cu).
+//
+// Layout in HBM (one "job" = any number of active regions, each a reads x haplotypes cross product):
+//   read blob      bytes; per read five tracks (_b,_q,_i,_d,_c) found through ReadDesc{off, stride, len}: track t of
+//                  read r is blob[off + t*stride .. +len).  stride = len for the reference's wire format
+//                  (PairHMMHostInterface.cpp:175-192), stride = total bases for five flat arrays.
+//   hap blob       bytes; HapDesc{off, len}.
+//   hap stream     bytes; all haplotypes of the job back to back, each preceded by a separator:
+//                  SEP c c c ... c SEP c c ... c SEP(final).  c = base class 0..4 (A,C,T,G,N; every other byte is
+//                  class 0 exactly like ConvertChar, host_type.h:123-143).  hap h starts at stream[spos[h]] (its SEP).
+//   initY          per hap, INITIAL_CONSTANT / haplen in float and double (avx-pairhmm-template.h:86,151).
+//   tasks          one warp-task = up to 32/W reads x a run of consecutive haplotypes (see Task).
+//   raw            float [pairs], read-major per region: the raw scaled likelihoods the reference's accelerator
+//                  returns (task/xlnx/PairHMMTask.cpp:69-79).
+//   fallback list  device-built tasks for pairs with raw < 1e-28f (PairHMMWorker.cpp:176), + their double results.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace pmm {
+
+constexpr uint8_t kSep = 0xFF;          // separator element of the hap stream
+constexpr int kStreamFrontPad = 64;     // bytes before stream[0] that lanes may read (and ignore) while filling
+constexpr int kStreamTailPad = 128;
+constexpr int kWarpsPerCta = 4;
+constexpr int kMaxGroups = 4;           // 32 / W, W >= 8
+
+struct ReadDesc { uint32_t off, stride, len; };
+struct HapDesc  { uint32_t off, len; };
+
+// One unit of work for one warp.  Group g (lanes g*W .. g*W+W-1) owns read[g]; all groups walk the same run of
+// haplotypes [hap_first, hap_first + nhaps).  The result for (read[g], hap_first + n) goes to out[out_base[g] + n].
+struct Task {
+    uint32_t read[kMaxGroups];
+    uint32_t out_base[kMaxGroups];
+    uint32_t hap_first;
+    uint32_t nhaps;
+    uint32_t nreads;
+    uint32_t reserved;
+};
+static_assert(sizeof(Task) == 48, "Task layout");
+
+struct DeviceTables {
+    const float*  ph2pr_f;
+    const float*  m2m_f;
+    const double* ph2pr_d;
+    const double* m2m_d;
+};
+
+struct ForwardArgs {
+    const uint8_t*  read_blob;
+    const ReadDesc* reads;
+    const uint8_t*  stream;        // points at stream[0]; kStreamFrontPad readable bytes precede it
+    const uint32_t* spos;          // [num_hap + 1]; spos[num_hap] = position of the final SEP
+    const void*     inity;         // float* or double* [num_hap]
+    const Task*     tasks;
+    const uint32_t* ntasks_dev;    // if non-null the task count is read from device memory (fallback list)
+    uint32_t        ntasks;
+    uint32_t*       counter;       // work-queue cursor, zeroed before launch
+    void*           out;           // float* or double*
+    void*           scratch;       // STRIPED only: per-warp carry rows, 3 * scratch_stride elements per warp
+    uint32_t        scratch_stride;
+    DeviceTables    tab;
+};
+
+// Launch helpers implemented in pmm_kernels.cu -------------------------------------------------------------
+
+// Float pass.  (K rows per lane) x (W lanes per read); W in {8,16,32}.  Returns cudaErrorInvalidValue for an
+// uninstantiated (K, W).  `striped` selects the multi-stripe variant for reads longer than W*K - 1 bases.
+cudaError_t launch_forward_f32(int K, int W, bool striped, const ForwardArgs& a, int ctas, cudaStream_t s);
+// Double re-run (fallback list).  flush = emulate x86 flush-to-zero on every product.
+cudaError_t launch_forward_f64(bool flush, const ForwardArgs& a, int ctas, cudaStream_t s);
+// Shared memory one CTA of the given variant needs (bytes) and CTAs per SM it reaches.
+int forward_f32_ctas_per_sm(int K, int W, bool striped);
+int forward_f64_ctas_per_sm(bool flush);
+bool forward_f32_has_variant(int K, int W);
+constexpr int kF64K = 6;            // rows per lane of the double kernel (W = 32): 191-base reads in one stripe
+
+cudaError_t launch_build_stream(const uint8_t* hap_blob, const HapDesc* haps, const uint32_t* spos, uint32_t num_hap,
+                                uint8_t* stream, float* inity_f, double* inity_d, float ic_f, double ic_d,
+                                cudaStream_t s);
+
+struct RegionDesc { uint32_t read_first, nreads, hap_first, nhaps, out_first; };
+
+// Scan raw[] for values below 1e-28f and append one single-pair Task per hit (read, hap, slot) to fb_tasks.
+cudaError_t launch_compact_fallback(const float* raw, const RegionDesc* regions, uint32_t nregions,
+                                    uint32_t total_pairs, Task* fb_tasks, uint32_t* fb_out_index,
+                                    uint32_t* fb_count, uint32_t fb_capacity, cudaStream_t s);
+// Second-level scan: double results below `threshold` are re-queued for the flush-emulating kernel.
+cudaError_t launch_compact_tiny(const double* dres, const Task* fb_tasks, const uint32_t* fb_count,
+                                double threshold, Task* tiny_tasks, uint32_t* tiny_count, cudaStream_t s);
+
+// FP32 issue-rate probe used for the roofline denominator (dependent-free FMUL/FADD streams).
+cudaError_t launch_fp32_probe(float* sink, int iters, int ctas, cudaStream_t s);
+
+}  // namespace pmm

@@ -1,0 +1,227 @@
+"""ctypes binding of libpairhmm_b200.so (include/pairhmm_cuda.h) -- the same C ABI the C++ host layer
+(pairhmm/client, pairhmm/task, pairhmm/host) links against.  Used by the tests and by bench.py.
+
+There is no fallback of any kind here: a missing library or a missing GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Sequence
+
+import numpy as np
+
+from .batch import Batch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpairhmm_b200.so")
+
+PMM_OK, PMM_ERR_INVALID, PMM_ERR_CUDA, PMM_ERR_NO_DEVICE, PMM_ERR_STATE = 0, 1, 2, 3, 4
+
+EXPORTS = [
+    "pmm_create", "pmm_destroy", "pmm_last_error", "pmm_device_count", "pmm_set_option",
+    "pmm_forward_raw_serialized", "pmm_forward_log10", "pmm_forward_log10_serialized",
+    "pmm_stage_flat", "pmm_launch", "pmm_sync", "pmm_fetch_raw", "pmm_fetch_log10", "pmm_fetch_fallback_mask",
+    "pmm_get_stats", "pmm_measure_fp32_peak",
+]
+
+
+class PmmRegion(C.Structure):
+    _fields_ = [("read_first", C.c_uint32), ("num_read", C.c_uint32), ("hap_first", C.c_uint32), ("num_hap", C.c_uint32)]
+
+
+class PmmStats(C.Structure):
+    _fields_ = [("pairs", C.c_uint64), ("cells", C.c_uint64), ("fallback_pairs", C.c_uint64), ("flush_pairs", C.c_uint64),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("kernel_launches", C.c_uint32),
+                ("f32_tasks", C.c_uint32), ("ms_stage", C.c_float), ("ms_f32", C.c_float), ("ms_fallback", C.c_float),
+                ("ms_fetch", C.c_float)]
+
+
+class PmmRead(C.Structure):
+    _fields_ = [("len", C.c_int), ("_b", C.c_char_p), ("_q", C.c_char_p), ("_i", C.c_char_p), ("_d", C.c_char_p),
+                ("_c", C.c_char_p)]
+
+
+class PmmHap(C.Structure):
+    _fields_ = [("len", C.c_int), ("_b", C.c_char_p)]
+
+
+class PmmError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"pairhmm_cuda error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load the engine; raises if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(f"{LIB_PATH} is missing: build it with __graft_entry__.build(); "
+                                    "there is no CPU fallback for the PairHMM engine")
+        L = C.CDLL(LIB_PATH)
+        vp, u64, u32 = C.c_void_p, C.c_uint64, C.c_uint32
+        L.pmm_create.argtypes = [C.c_int, C.POINTER(vp)]; L.pmm_create.restype = C.c_int
+        L.pmm_destroy.argtypes = [vp]; L.pmm_destroy.restype = None
+        L.pmm_last_error.argtypes = [vp]; L.pmm_last_error.restype = C.c_char_p
+        L.pmm_device_count.argtypes = []; L.pmm_device_count.restype = C.c_int
+        L.pmm_set_option.argtypes = [vp, C.c_char_p, C.c_char_p]; L.pmm_set_option.restype = C.c_int
+        L.pmm_forward_raw_serialized.argtypes = [vp, vp, u64, vp, u64, vp, u64, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.pmm_forward_log10_serialized.argtypes = [vp, vp, u64, vp, u64, vp, u64, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(u64)]
+        L.pmm_forward_log10.argtypes = [vp, C.POINTER(PmmRead), C.c_int, C.POINTER(PmmHap), C.c_int, vp, C.POINTER(u64)]
+        L.pmm_stage_flat.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp, u32, vp, vp, u32, vp]
+        L.pmm_launch.argtypes = [vp]; L.pmm_sync.argtypes = [vp]
+        L.pmm_fetch_raw.argtypes = [vp, vp, u64]
+        L.pmm_fetch_log10.argtypes = [vp, vp, u64, C.POINTER(u64)]
+        L.pmm_fetch_fallback_mask.argtypes = [vp, vp, u64]
+        L.pmm_get_stats.argtypes = [vp, C.POINTER(PmmStats)]
+        L.pmm_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        for n in EXPORTS:
+            if n not in ("pmm_destroy", "pmm_last_error"):
+                getattr(L, n).restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def concat_regions(batches: Sequence[Batch]):
+    """Flatten a list of regions into the multi-region layout of pmm_stage_flat."""
+    ro, ho = [np.zeros(1, dtype=np.uint32)], [np.zeros(1, dtype=np.uint32)]
+    regs = (PmmRegion * len(batches))()
+    nr = nh = 0
+    rb = hb = 0
+    for k, b in enumerate(batches):
+        regs[k] = PmmRegion(nr, b.num_read, nh, b.num_hap)
+        ro.append(b.read_off[1:].astype(np.uint32) + np.uint32(rb)); ho.append(b.hap_off[1:].astype(np.uint32) + np.uint32(hb))
+        nr += b.num_read; nh += b.num_hap; rb += int(b.read_off[-1]); hb += int(b.hap_off[-1])
+
+    def cat(name):
+        return np.ascontiguousarray(np.concatenate([getattr(b, name) for b in batches]), dtype=np.uint8)
+    return dict(num_read=nr, read_off=np.ascontiguousarray(np.concatenate(ro)), rs=cat("rs"), q=cat("q"), i=cat("i"),
+                d=cat("d"), c=cat("c"), num_hap=nh, hap_off=np.ascontiguousarray(np.concatenate(ho)), hap=cat("hap"),
+                regions=regs, num_region=len(batches), pairs=sum(b.num_pairs for b in batches))
+
+
+class PairHMMEngine:
+    """One GPU context (pmm_ctx).  Not thread-safe; one engine per host thread."""
+
+    def __init__(self, device: int = -1):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.pmm_create(device, C.byref(h))
+        if rc != PMM_OK:
+            raise PmmError(rc, self.lib.pmm_last_error(None).decode())
+        self.h = h
+        self._job = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pmm_destroy(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != PMM_OK:
+            raise PmmError(rc, self.lib.pmm_last_error(self.h).decode())
+
+    def set_option(self, key: str, value) -> None:
+        self._ck(self.lib.pmm_set_option(self.h, key.encode(), str(value).encode()))
+
+    # ---- staged path -----------------------------------------------------------------------------------
+    def stage(self, batches: Sequence[Batch] | Batch):
+        if isinstance(batches, Batch):
+            batches = [batches]
+        j = concat_regions(batches)
+        self._job = j        # keeps the arrays alive; the library copies during the call anyway
+        self._ck(self.lib.pmm_stage_flat(self.h, j["num_read"], j["read_off"].ctypes.data, j["rs"].ctypes.data,
+                                         j["q"].ctypes.data, j["i"].ctypes.data, j["d"].ctypes.data, j["c"].ctypes.data,
+                                         j["num_hap"], j["hap_off"].ctypes.data, j["hap"].ctypes.data,
+                                         j["num_region"], C.cast(j["regions"], C.c_void_p)))
+        return j
+
+    def restage(self):
+        """Repeat the last stage() from the already flattened host arrays (the e2e timing loop of bench.py)."""
+        j = self._job
+        self._ck(self.lib.pmm_stage_flat(self.h, j["num_read"], j["read_off"].ctypes.data, j["rs"].ctypes.data,
+                                         j["q"].ctypes.data, j["i"].ctypes.data, j["d"].ctypes.data, j["c"].ctypes.data,
+                                         j["num_hap"], j["hap_off"].ctypes.data, j["hap"].ctypes.data,
+                                         j["num_region"], C.cast(j["regions"], C.c_void_p)))
+
+    def launch(self):
+        self._ck(self.lib.pmm_launch(self.h))
+
+    def sync(self):
+        self._ck(self.lib.pmm_sync(self.h))
+
+    def fetch_raw(self) -> np.ndarray:
+        out = np.empty(self._job["pairs"], dtype=np.float32)
+        self._ck(self.lib.pmm_fetch_raw(self.h, out.ctypes.data, out.size))
+        return out
+
+    def fetch_log10(self, out: np.ndarray | None = None):
+        if out is None:
+            out = np.empty(self._job["pairs"], dtype=np.float64)
+        nfb = C.c_uint64()
+        self._ck(self.lib.pmm_fetch_log10(self.h, out.ctypes.data, out.size, C.byref(nfb)))
+        return out, int(nfb.value)
+
+    def fetch_fallback_mask(self) -> np.ndarray:
+        m = np.empty(self._job["pairs"], dtype=np.uint8)
+        self._ck(self.lib.pmm_fetch_fallback_mask(self.h, m.ctypes.data, m.size))
+        return m.astype(bool)
+
+    def stats(self) -> dict:
+        s = PmmStats()
+        self._ck(self.lib.pmm_get_stats(self.h, C.byref(s)))
+        return {n: getattr(s, n) for n, _ in s._fields_}
+
+    def measure_fp32_peak(self):
+        r, mhz = C.c_double(), C.c_double()
+        self._ck(self.lib.pmm_measure_fp32_peak(self.h, C.byref(r), C.byref(mhz)))
+        return r.value, mhz.value
+
+    # ---- one-shot paths ---------------------------------------------------------------------------------
+    def forward(self, b: Batch):
+        """raw [R,H] float32, log10 [R,H] float64, fallback mask [R,H] -- one region through the staged path."""
+        self.stage([b]); self.launch()
+        raw = self.fetch_raw().reshape(b.num_read, b.num_hap)
+        out, _ = self.fetch_log10()
+        mask = self.fetch_fallback_mask().reshape(b.num_read, b.num_hap)
+        return raw, out.reshape(b.num_read, b.num_hap), mask
+
+    def forward_raw_serialized(self, reads_ser: bytes, haps_ser: bytes, capacity: int) -> np.ndarray:
+        out = np.empty(capacity, dtype=np.float32)
+        nr, nh = C.c_int(), C.c_int()
+        self._ck(self.lib.pmm_forward_raw_serialized(self.h, reads_ser, len(reads_ser), haps_ser, len(haps_ser),
+                                                     out.ctypes.data, capacity, C.byref(nr), C.byref(nh)))
+        return out[: nr.value * nh.value].reshape(nr.value, nh.value)
+
+    def forward_log10_serialized(self, reads_ser: bytes, haps_ser: bytes, capacity: int):
+        out = np.empty(capacity, dtype=np.float64)
+        nr, nh, nfb = C.c_int(), C.c_int(), C.c_uint64()
+        self._ck(self.lib.pmm_forward_log10_serialized(self.h, reads_ser, len(reads_ser), haps_ser, len(haps_ser),
+                                                       out.ctypes.data, capacity, C.byref(nr), C.byref(nh), C.byref(nfb)))
+        return out[: nr.value * nh.value].reshape(nr.value, nh.value), int(nfb.value)
+
+    def forward_log10_structs(self, b: Batch):
+        """Through pmm_forward_log10 with read_t / hap_t arrays (the client-side entry)."""
+        keep = []
+        reads = (PmmRead * b.num_read)()
+        for k in range(b.num_read):
+            bs = [bytes(x) for x in b.read(k)]
+            keep.append(bs)
+            reads[k] = PmmRead(len(bs[0]), *bs)
+        haps = (PmmHap * b.num_hap)()
+        for k in range(b.num_hap):
+            hb = bytes(b.haplotype(k)); keep.append(hb)
+            haps[k] = PmmHap(len(hb), hb)
+        out = np.empty(b.num_pairs, dtype=np.float64)
+        nfb = C.c_uint64()
+        self._ck(self.lib.pmm_forward_log10(self.h, reads, b.num_read, haps, b.num_hap, out.ctypes.data, C.byref(nfb)))
+        return out.reshape(b.num_read, b.num_hap), int(nfb.value)

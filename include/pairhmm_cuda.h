@@ -1,0 +1,121 @@
+/*
+ * pairhmm_cuda.h -- C ABI of the B200 PairHMM forward engine (libpairhmm_b200.so).
+ *
+ * This is the thin layer that replaces the reference's FPGA/OpenCL dispatch for the PairHMM path.  Plain C,
+ * plain pointers and sizes, integer status codes, no exceptions across the boundary, caller-owned output
+ * buffers.  Every entry point names the reference interface it stands in for (paths under
+ * /root/reference/pairhmm/).  INTEGRATION.md shows the bindings a maintainer of the reference would add.
+ *
+ * Semantics common to all compute calls
+ *   - A "region" is a cross product: num_read reads against num_hap haplotypes; results are read-major,
+ *     out[i * num_hap + j] for read i and haplotype j (host/main.cpp:365, client/PairHMMWorker.cpp:171-193).
+ *   - "raw" results are the float likelihoods scaled by 2^120 that the reference's accelerators return in the
+ *     task's output block (task/xlnx/PairHMMTask.cpp:69-79) and that compute_fp_avxs returns on the CPU
+ *     (xlnx/host/avx_impl.cpp:4); they are bit-identical to the AVX implementation built without FMA contraction.
+ *   - "log10" results are the final doubles of PairHMMWorker::getOutput (client/PairHMMWorker.cpp:157-197):
+ *     raw < 1e-28f selects the double-precision re-run, log10(d) - log10(2^1020); otherwise
+ *     (double)(log10f(raw) - log10f(2^120)).  The re-run happens on the GPU; log10 is taken with the host libm.
+ *   - Quality bytes are used modulo 128 and any base other than A,C,G,T,N counts as A, like the reference
+ *     (xlnx/host/avx-pairhmm-template.h:110-112, xlnx/host/host_type.h:123-143).  Reads and haplotypes of length 0
+ *     are rejected with PMM_ERR_INVALID (the reference reads uninitialised memory for them).
+ *   - A pmm_ctx is bound to one GPU and is not thread-safe; use one context per host thread (as the reference
+ *     uses one PairHMMClient per thread).  Different contexts may be used concurrently.
+ */
+#ifndef PAIRHMM_CUDA_H
+#define PAIRHMM_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pmm_ctx pmm_ctx;
+
+enum {
+    PMM_OK = 0,
+    PMM_ERR_INVALID = 1,     /* bad argument / malformed buffer                     */
+    PMM_ERR_CUDA = 2,        /* CUDA runtime error, text in pmm_last_error()        */
+    PMM_ERR_NO_DEVICE = 3,   /* no usable GPU: the engine has NO CPU fallback       */
+    PMM_ERR_STATE = 4        /* call sequence violated (e.g. fetch before launch)   */
+};
+
+/* Same field order and meaning as read_t / hap_t (interface/PairHMMHostInterface.h:27-39). */
+typedef struct { int len; char* _b; char* _q; char* _i; char* _d; char* _c; } pmm_read_t;
+typedef struct { int len; char* _b; } pmm_hap_t;
+
+/* One region of a flat multi-region job: reads [read_first, +num_read) x haplotypes [hap_first, +num_hap). */
+typedef struct { uint32_t read_first, num_read, hap_first, num_hap; } pmm_region_t;
+
+typedef struct {
+    uint64_t pairs, cells;            /* cells = sum over regions of sum(read_len) * sum(hap_len) (host/main.cpp:305-313) */
+    uint64_t fallback_pairs;          /* pairs re-run in double (raw < 1e-28f)                              */
+    uint64_t flush_pairs;             /* of those, re-run again with x86 flush-to-zero emulation             */
+    uint64_t h2d_bytes, d2h_bytes;
+    uint32_t kernel_launches;         /* kernels launched by the last pmm_launch                             */
+    uint32_t f32_tasks;               /* warp-tasks of the float pass                                        */
+    float    ms_stage, ms_f32, ms_fallback, ms_fetch;   /* CUDA-event / host timings of the last job          */
+} pmm_stats_t;
+
+/* ---- lifetime ------------------------------------------------------------------------------------------
+ * Replaces: lazy `new OpenCLEnv(bit_path, KERNEL_NAME)` in compute_fpga (host/PairHMMFpga.cpp:131-133) and the
+ * Blaze TaskEnv the task obtains with getEnv() (task/xlnx/PairHMMTask.cpp:30).  device < 0 picks the current one. */
+int  pmm_create(int device, pmm_ctx** out);
+void pmm_destroy(pmm_ctx* ctx);
+const char* pmm_last_error(const pmm_ctx* ctx);     /* ctx may be NULL: last error of pmm_create */
+int  pmm_device_count(void);
+
+/* Options (strings, like the task's get_conf(key, value), task/xlnx/PairHMMTask.h:73-77):
+ *   "stream"          = decimal value of a cudaStream_t to run on instead of the context's own stream
+ *   "tasks_per_warp"  = target queue depth per resident warp used when cutting regions into warp-tasks        */
+int  pmm_set_option(pmm_ctx* ctx, const char* key, const char* value);
+
+/* ---- one-shot calls, host buffers in, host buffers out --------------------------------------------------
+ * pmm_forward_raw_serialized replaces PairHMM::prepare() + PairHMM::compute() (task/xlnx/PairHMMTask.cpp:27-143)
+ * and compute_fpga (host/PairHMMFpga.h:16-20): inputs are the task's input blocks 1 and 2 -- the byte streams of
+ * serialize() (interface/PairHMMHostInterface.cpp:175-207) -- and the output is the task's output block 0.
+ * out_raw must hold num_read * num_hap floats; the counts are returned through num_read / num_hap. */
+int  pmm_forward_raw_serialized(pmm_ctx* ctx, const void* reads_ser, uint64_t reads_bytes,
+                                const void* haps_ser, uint64_t haps_bytes,
+                                float* out_raw, uint64_t out_capacity, int* num_read, int* num_hap);
+
+/* Replaces PairHMMWorker::run() + getOutput() (client/PairHMMWorker.cpp:157-271) and
+ * FalconPairHMM::computePairhmmAVX (xlnx/host/FalconPairHMM.cpp:69-95) for one region. */
+int  pmm_forward_log10(pmm_ctx* ctx, const pmm_read_t* reads, int num_read, const pmm_hap_t* haps, int num_hap,
+                       double* out, uint64_t* n_fallback);
+int  pmm_forward_log10_serialized(pmm_ctx* ctx, const void* reads_ser, uint64_t reads_bytes,
+                                  const void* haps_ser, uint64_t haps_bytes,
+                                  double* out, uint64_t out_capacity, int* num_read, int* num_hap,
+                                  uint64_t* n_fallback);
+
+/* ---- staged calls: many regions per job, device-resident between steps -----------------------------------
+ * The flat layout is five parallel byte arrays for the reads (bases, base / insertion / deletion /
+ * gap-continuation qualities) indexed by read_off[0..num_read], one byte array for the haplotypes indexed by
+ * hap_off[0..num_hap], and a list of regions.  Results of region g start at sum over earlier regions of
+ * num_read * num_hap.
+ *   pmm_stage_flat : pack into pinned memory, copy to the GPU, build the haplotype stream and the task queue
+ *   pmm_launch     : float pass + fallback compaction + double re-run; asynchronous on the context's stream
+ *   pmm_fetch_*    : wait, copy results back, (log10) finish on the host
+ * pmm_launch may be called repeatedly on one staged job (bench.py times it with inputs resident in HBM). */
+int  pmm_stage_flat(pmm_ctx* ctx, uint32_t num_read, const uint32_t* read_off,
+                    const uint8_t* bases, const uint8_t* q, const uint8_t* i, const uint8_t* d, const uint8_t* c,
+                    uint32_t num_hap, const uint32_t* hap_off, const uint8_t* hap_bases,
+                    uint32_t num_region, const pmm_region_t* regions);
+int  pmm_launch(pmm_ctx* ctx);
+int  pmm_sync(pmm_ctx* ctx);
+int  pmm_fetch_raw(pmm_ctx* ctx, float* out_raw, uint64_t out_capacity);
+int  pmm_fetch_log10(pmm_ctx* ctx, double* out, uint64_t out_capacity, uint64_t* n_fallback);
+/* The fallback decision of the last launched job: mask[k] = 1 where raw[k] < 1e-28f. */
+int  pmm_fetch_fallback_mask(pmm_ctx* ctx, uint8_t* mask, uint64_t capacity);
+
+int  pmm_get_stats(const pmm_ctx* ctx, pmm_stats_t* out);
+
+/* Measured FP32 instruction issue rate of this GPU in lane-instructions per second (the roofline denominator of
+ * SURVEY.md section 8d; an independent FMUL/FADD stream, ~20 ms).  Also returns the SM clock seen while measuring. */
+int  pmm_measure_fp32_peak(pmm_ctx* ctx, double* lane_instr_per_s, double* sm_mhz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PAIRHMM_CUDA_H */
