@@ -5,6 +5,7 @@
 // GPU every entry point fails with PMM_ERR_NO_DEVICE.
 #include "../../include/pairhmm_cuda.h"
 #include "pmm_kernels.cuh"
+#include "pmm_plan.h"
 #include "pmm_tables.h"
 
 #include <algorithm>
@@ -60,15 +61,6 @@ struct PinBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
-struct Variant { int K, W; bool striped; };
-inline bool operator==(const Variant& a, const Variant& b) { return a.K == b.K && a.W == b.W && a.striped == b.striped; }
-
-struct LaunchSeg { Variant v; uint32_t task_first, task_count; };
-
-// Issue slots one step of K cells costs in the float kernel (from the SASS of the steady loop: 12 FP per cell,
-// one LDS.128 per 4 rows, and 3 SHFL + LDG + 2 sum FADD + address/loop overhead per step).
-inline double step_cost(int K) { return 12.25 * K + 9.0; }
-
 }  // namespace
 
 struct pmm_ctx {
@@ -113,23 +105,6 @@ struct pmm_ctx {
 
 namespace {
 
-// ---- variant choice -------------------------------------------------------------------------------------
-// Best (K, W) for a read of R bases: maximise useful FP work per issue slot, 12*R / (W * step_cost(K)), subject to
-// R + 1 <= K * W (one boundary row), with a mild penalty for variants whose register count halves occupancy.
-Variant pick_variant(int R)
-{
-    Variant best{8, 32, true};
-    double best_eff = -1.0;
-    for (int W = 8; W <= 32; W *= 2)
-        for (int K = 4; K <= 16; ++K) {
-            if (!forward_f32_has_variant(K, W) || R + 1 > K * W) continue;
-            double eff = 12.0 * R / (W * step_cost(K));
-            if (K > 12) eff *= 0.97;
-            if (eff > best_eff) { best_eff = eff; best = Variant{K, W, false}; }
-        }
-    return best;
-}
-
 int ensure_tables(pmm_ctx* c)
 {
     if (c->tables.p) return PMM_OK;
@@ -160,97 +135,23 @@ int stage_common(pmm_ctx* c, uint32_t num_read, const uint32_t* read_off, const 
 {
     auto t0 = std::chrono::steady_clock::now();
     c->staged = false; c->launched = false;
-    if (!num_read || !num_hap || !num_region || !read_off || !hap_off || !regions)
-        return c->fail(PMM_ERR_INVALID, "empty job");
     int rc = ensure_tables(c);
     if (rc) return rc;
 
+    Plan plan;
+    {
+        std::string perr;
+        rc = plan_job(num_read, read_off, num_hap, hap_off, num_region, regions, c->sm_count, c->tasks_per_warp, plan, perr);
+        if (rc) return c->fail(rc, perr);
+    }
     const uint64_t total_bases = read_off[num_read] - read_off[0];
     const uint64_t total_hap = hap_off[num_hap] - hap_off[0];
-    if (total_bases * 5 + total_hap >= (1ull << 31)) return c->fail(PMM_ERR_INVALID, "job larger than 2 GiB: split it");
-    uint32_t max_hap = 0, max_read = 0;
-    for (uint32_t i = 0; i < num_read; ++i) {
-        const uint32_t len = read_off[i + 1] - read_off[i];
-        if (len == 0 || read_off[i + 1] < read_off[i]) return c->fail(PMM_ERR_INVALID, "read of length 0");
-        max_read = std::max(max_read, len);
-    }
-    for (uint32_t h = 0; h < num_hap; ++h) {
-        const uint32_t len = hap_off[h + 1] - hap_off[h];
-        if (len == 0 || hap_off[h + 1] < hap_off[h]) return c->fail(PMM_ERR_INVALID, "haplotype of length 0");
-        max_hap = std::max(max_hap, len);
-    }
+    const uint32_t max_hap = plan.max_hap_len;
+    const uint64_t pairs = plan.pairs, cells = plan.cells;
+    const std::vector<Task>& tasks = plan.tasks;
+    const std::vector<RegionDesc>& rdesc = plan.regions;
     c->max_hap_len = max_hap;
-
-    // ---- regions, result offsets, cell count ---------------------------------------------------------------
-    std::vector<RegionDesc> rdesc(num_region);
-    uint64_t pairs = 0, cells = 0;
-    for (uint32_t g = 0; g < num_region; ++g) {
-        const pmm_region_t& r = regions[g];
-        if (!r.num_read || !r.num_hap || (uint64_t)r.read_first + r.num_read > num_read ||
-            (uint64_t)r.hap_first + r.num_hap > num_hap)
-            return c->fail(PMM_ERR_INVALID, "region out of range");
-        rdesc[g] = RegionDesc{r.read_first, r.num_read, r.hap_first, r.num_hap, (uint32_t)pairs};
-        pairs += (uint64_t)r.num_read * r.num_hap;
-        cells += (uint64_t)(read_off[r.read_first + r.num_read] - read_off[r.read_first]) *
-                 (uint64_t)(hap_off[r.hap_first + r.num_hap] - hap_off[r.hap_first]);
-    }
-    if (pairs >= (1ull << 31)) return c->fail(PMM_ERR_INVALID, "more than 2^31 pairs in one job: split it");
-
-    // ---- cut every region into warp-tasks --------------------------------------------------------------------
-    // Reads of a region are sorted by length (longest first); the longest unassigned read picks the (K, W)
-    // variant and shares its warp with the next 32/W - 1 reads.  Haplotypes are cut into runs so that the queue
-    // holds about tasks_per_warp tasks per resident warp.
-    struct Group { Variant v; uint32_t region; uint32_t reads[kMaxGroups]; uint32_t n; };
-    std::vector<Group> groups;
-    std::vector<uint32_t> order;
-    uint64_t group_haps = 0;
-    for (uint32_t g = 0; g < num_region; ++g) {
-        const pmm_region_t& r = regions[g];
-        order.resize(r.num_read);
-        std::iota(order.begin(), order.end(), r.read_first);
-        std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
-            return read_off[x + 1] - read_off[x] > read_off[y + 1] - read_off[y]; });
-        for (uint32_t k = 0; k < r.num_read;) {
-            const int R = (int)(read_off[order[k] + 1] - read_off[order[k]]);
-            Group gr; gr.v = pick_variant(R); gr.region = g; gr.n = 0;
-            const uint32_t G = gr.v.striped ? 1u : (uint32_t)(32 / gr.v.W);
-            for (; gr.n < G && k < r.num_read; ++k) gr.reads[gr.n++] = order[k];
-            for (uint32_t z = gr.n; z < kMaxGroups; ++z) gr.reads[z] = 0;
-            groups.push_back(gr);
-            group_haps += r.num_hap;
-        }
-    }
-    const uint64_t resident_warps = (uint64_t)c->sm_count * 16;
-    const uint64_t target_tasks = std::max<uint64_t>(1, resident_warps * (uint64_t)c->tasks_per_warp);
-    const uint32_t haps_per_task = (uint32_t)std::max<uint64_t>(1, (group_haps + target_tasks - 1) / target_tasks);
-
-    // order launches by variant (largest footprint first); stable within a variant
-    std::vector<uint32_t> gorder(groups.size());
-    std::iota(gorder.begin(), gorder.end(), 0u);
-    auto vkey = [](const Variant& v) { return (v.striped ? 1 << 20 : 0) + v.K * v.W * 64 + v.W; };
-    std::stable_sort(gorder.begin(), gorder.end(), [&](uint32_t x, uint32_t y) { return vkey(groups[x].v) > vkey(groups[y].v); });
-
-    std::vector<Task> tasks;
-    c->segs.clear();
-    for (uint32_t gi : gorder) {
-        const Group& gr = groups[gi];
-        const RegionDesc& r = rdesc[gr.region];
-        const uint32_t hpt = gr.v.striped ? 1u : std::min(haps_per_task, r.nhaps);
-        if (c->segs.empty() || !(c->segs.back().v == gr.v)) c->segs.push_back(LaunchSeg{gr.v, (uint32_t)tasks.size(), 0});
-        // balance the run lengths: ceil(nhaps / ceil(nhaps / hpt))
-        const uint32_t nruns = (r.nhaps + hpt - 1) / hpt;
-        for (uint32_t run = 0; run < nruns; ++run) {
-            const uint32_t h0 = (uint32_t)((uint64_t)r.nhaps * run / nruns), h1 = (uint32_t)((uint64_t)r.nhaps * (run + 1) / nruns);
-            Task t;
-            for (uint32_t z = 0; z < kMaxGroups; ++z) {
-                t.read[z] = gr.reads[z];
-                t.out_base[z] = z < gr.n ? r.out_first + (gr.reads[z] - r.read_first) * r.nhaps + h0 : 0;
-            }
-            t.hap_first = r.hap_first + h0; t.nhaps = h1 - h0; t.nreads = gr.n; t.reserved = 0;
-            tasks.push_back(t);
-            c->segs.back().task_count++;
-        }
-    }
+    c->segs = plan.segs;
 
     // ---- pack the input arena ---------------------------------------------------------------------------------
     const size_t sz_rblob = total_bases * 5, sz_rdesc = sizeof(ReadDesc) * num_read;
@@ -705,6 +606,45 @@ int pmm_forward_log10(pmm_ctx* c, const pmm_read_t* reads, int num_read, const p
     if (rc) return rc;
     if ((rc = pmm_launch(c))) return rc;
     return pmm_fetch_log10(c, out, (uint64_t)num_read * num_hap, n_fallback);
+}
+
+int pmm_plan_flat(uint32_t num_read, const uint32_t* read_off, uint32_t num_hap, const uint32_t* hap_off,
+                  uint32_t num_region, const pmm_region_t* regions, int sm_count, int tasks_per_warp,
+                  pmm_task_info_t* out, uint64_t capacity, uint64_t* num_tasks)
+{
+    Plan plan; std::string perr;
+    int rc = plan_job(num_read, read_off, num_hap, hap_off, num_region, regions, sm_count, tasks_per_warp, plan, perr);
+    if (rc) { g_create_error = perr; return rc; }
+    if (num_tasks) *num_tasks = plan.tasks.size();
+    if (!out) return PMM_OK;
+    if (capacity < plan.tasks.size()) { g_create_error = "task buffer too small"; return PMM_ERR_INVALID; }
+    for (const LaunchSeg& seg : plan.segs)
+        for (uint32_t k = seg.task_first; k < seg.task_first + seg.task_count; ++k) {
+            const Task& t = plan.tasks[k];
+            pmm_task_info_t& o = out[k];
+            for (int z = 0; z < 4; ++z) { o.read[z] = t.read[z]; o.out_base[z] = t.out_base[z]; }
+            o.hap_first = t.hap_first; o.num_hap = t.nhaps; o.num_read = t.nreads;
+            o.rows_per_lane = (uint32_t)seg.v.K; o.lanes_per_read = (uint32_t)seg.v.W; o.striped = seg.v.striped ? 1u : 0u;
+        }
+    return PMM_OK;
+}
+
+int pmm_host_table(int which, void* out, uint64_t capacity_bytes)
+{
+    const HostTables& t = host_tables();
+    const void* src = nullptr; size_t n = 0;
+    switch (which) {
+        case 0: src = t.ph2pr_f; n = sizeof t.ph2pr_f; break;
+        case 1: src = t.m2m_f;   n = sizeof t.m2m_f;   break;
+        case 2: src = t.ph2pr_d; n = sizeof t.ph2pr_d; break;
+        case 3: src = t.m2m_d;   n = sizeof t.m2m_d;   break;
+        case 4: src = &t.log10_ic_f; n = sizeof(float); break;
+        case 5: src = &t.log10_ic_d; n = sizeof(double); break;
+        default: return PMM_ERR_INVALID;
+    }
+    if (!out || capacity_bytes < n) return PMM_ERR_INVALID;
+    memcpy(out, src, n);
+    return PMM_OK;
 }
 
 int pmm_measure_fp32_peak(pmm_ctx* c, double* lane_instr_per_s, double* sm_mhz)

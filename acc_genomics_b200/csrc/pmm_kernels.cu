@@ -21,7 +21,9 @@
 //     the measured issue rate is 1 instr/clk/SMSP for FP32 and ALU alike, tools/microbench/issue_mix2.cu): each
 //     warp stages a [5 classes][K rows] weight table for its reads in shared memory, laid out so that one
 //     conflict-free LDS.128 per 4 rows fetches the weights for whatever haplotype base the lane is looking at.
-//   * Steady-state steps are branch-free; only the W+1 steps around a separator run the checked variant.
+//   * Steady-state steps are branch-free; only the W steps around a separator run the checked variant.
+//   * The AVX code's stripe initialisation feeds M[r-1][1] into Y[r][1] for the first row of every 8-row stripe
+//     (avx-pairhmm-template.h:171-176); that value is exactly 0 for r >= 3, so there is nothing to reproduce.
 //   * Work is pulled by warps from a global queue (atomicAdd), grid = SMs x resident CTAs.
 #include "pmm_kernels.cuh"
 
@@ -39,7 +41,6 @@ __device__ __forceinline__ int base_class(unsigned ch)
 template <typename T> struct Arith;
 
 template <> struct Arith<float> {
-    static constexpr int kStripe = 8;          // AVX float vector = 8 rows (avx-functions-float.h AVX_LENGTH)
     static constexpr int kVec = 4;             // elements per 16-byte shared-memory access
     static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
     static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
@@ -50,7 +51,6 @@ template <> struct Arith<float> {
 };
 
 template <> struct Arith<double> {
-    static constexpr int kStripe = 4;          // AVX double vector = 4 rows
     static constexpr int kVec = 2;
     static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
     static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) pmm_forward_kernel(const Fo
         for (int stripe = 0; stripe < nstripes; ++stripe) {
             // ---- per-row parameters (avx-pairhmm-template.h:108-127, :155-158) --------------------------
             T pMM[K], pG[K], pMX[K], pXX[K], pMY[K], pYY[K];
-            unsigned padmask = 0, quirkmask = 0;
+            unsigned padmask = 0;
             __syncwarp();                                                // previous task / stripe done with wtab
             #pragma unroll
             for (int j = 0; j < K; ++j) {
@@ -152,9 +152,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) pmm_forward_kernel(const Fo
                     const T dm = A::ph2pr(a.tab, q_);
                     mw = A::sub((T)1.0, dm);
                     xw = A::div(dm, (T)3.0);
-                    // first row of every AVX stripe but the first inherits M[r-1][1] as its "left M" in
-                    // column 1 (avx-pairhmm-template.h:171-176); r0 is 0-based, so rows r0 = 8,16,.. (4,8,.. double)
-                    if (r0 > 0 && (r0 % A::kStripe) == 0) quirkmask |= 1u << j;
                 } else {
                     // boundary row: M = X = 0, Y keeps its value
                     pMM[j] = (T)0; pG[j] = (T)0; pMX[j] = (T)0; pXX[j] = (T)0; pMY[j] = (T)0; pYY[j] = (T)1.0;
@@ -174,13 +171,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) pmm_forward_kernel(const Fo
             T dM = (T)0, dX = (T)0, dY = (T)0;        // last row of the lane above, previous column (diagonal)
             T sM = (T)0, sX = (T)0;                   // running sums of the read's last row
             int nsep = 0;
-            bool done = false, first = false;
+            bool done = false;
             const bool last_stripe = stripe == nstripes - 1;
             const bool carry_in = STRIPED && stripe > 0 && l == 0;
             const bool carry_out = STRIPED && !last_stripe && l == W - 1;
 
             // One column of K cells.  inM/inX/inY: last row of the lane above at this column.
-            auto cells = [&](unsigned e, T inM, T inX, T inY, bool fix_first) {
+            auto cells = [&](unsigned e, T inM, T inX, T inY) {
                 const T* wp = wlane + e * CLS_STRIDE;
                 T w[KQ * VEC];
                 #pragma unroll
@@ -210,12 +207,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) pmm_forward_kernel(const Fo
                     // X = Mup*pMX + Xup*pXX                             (:194)
                     Xn[j] = A::add(flush<FLUSH>(A::mul(mu, pMX[j])), flush<FLUSH>(A::mul(xu, pXX[j])));
                 }
-                if (fix_first) {
-                    // column 1 of a haplotype: the AVX stripe artefact (see quirkmask)
-                    #pragma unroll
-                    for (int j = 0; j < K; ++j)
-                        if (quirkmask & (1u << j)) Yn[j] = flush<FLUSH>(A::mul(j ? Mn[j - 1] : inM, pMY[j]));
-                }
                 #pragma unroll
                 for (int j = 0; j < K; ++j) { M[j] = Mn[j]; X[j] = Xn[j]; Y[j] = Yn[j]; }
                 sM = A::add(sM, M[K - 1]);          // (:328,:331) two sums, left to right
@@ -223,7 +214,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) pmm_forward_kernel(const Fo
                 dM = inM; dX = inX; dY = inY;
             };
 
-            // Step with every check: separators, fill/drain, first column, stripe carries.
+            // Step with every check: separators, fill/drain, stripe carries.
             auto checked_step = [&](int t, unsigned e) {
                 T inM = __shfl_up_sync(0xffffffffu, M[K - 1], 1, W);
                 T inX = __shfl_up_sync(0xffffffffu, X[K - 1], 1, W);
@@ -241,16 +232,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) pmm_forward_kernel(const Fo
                         for (int j = 0; j < K; ++j) { M[j] = (T)0; X[j] = (T)0; Y[j] = (padmask >> j) & 1 ? iy : (T)0; }
                         sM = (T)0; sX = (T)0;
                         dM = inM; dX = inX; dY = inY;
-                        first = true;
                     } else {
-                        cells(e, inM, inX, inY, first);
-                        first = false;
+                        cells(e, inM, inX, inY);
                     }
                     if (carry_out) { scM[p] = M[K - 1]; scX[p] = X[K - 1]; scY[p] = Y[K - 1]; }
                 }
             };
 
-            // Branch-free step: every lane is inside the bases of a haplotype, past its first column.
+            // Branch-free step: every lane is inside the bases of a haplotype.
             auto steady_step = [&](int t, unsigned e) {
                 T inM = __shfl_up_sync(0xffffffffu, M[K - 1], 1, W);
                 T inX = __shfl_up_sync(0xffffffffu, X[K - 1], 1, W);
@@ -258,10 +247,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) pmm_forward_kernel(const Fo
                 if (STRIPED) {
                     const int p = t - l;
                     if (carry_in) { inM = ld_cg(scM + p); inX = ld_cg(scX + p); inY = ld_cg(scY + p); }
-                    cells(e, inM, inX, inY, false);
+                    cells(e, inM, inX, inY);
                     if (carry_out) { scM[p] = M[K - 1]; scX[p] = X[K - 1]; scY[p] = Y[K - 1]; }
                 } else {
-                    cells(e, inM, inX, inY, false);
+                    cells(e, inM, inX, inY);
                 }
             };
 
@@ -270,8 +259,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) pmm_forward_kernel(const Fo
             int next_sep = 0;                     // step at which lane 0 meets it
             unsigned e = sp[0];
             while (t < Tsteps) {
-                // checked window: lane l meets the separator at next_sep + l and its first column one step later
-                int wend = next_sep + W + 1;
+                // checked window: lane l meets the separator at step next_sep + l
+                int wend = next_sep + W;
                 if (wend > Tsteps) wend = Tsteps;
                 for (; t < wend; ++t) {
                     const unsigned en = sp[t + 1];
@@ -279,7 +268,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) pmm_forward_kernel(const Fo
                     e = en;
                 }
                 ++hn;
-                next_sep = hn <= nhaps ? (int)(a.spos[hap_first + hn] - s0) : Tsteps + W + 1;
+                next_sep = hn <= nhaps ? (int)(a.spos[hap_first + hn] - s0) : Tsteps + W;
                 int send = next_sep < Tsteps ? next_sep : Tsteps;
                 #pragma unroll 2
                 for (; t < send; ++t) {
@@ -404,27 +393,12 @@ int variant_ctas_per_sm()
     return n;
 }
 
-// (K, W) variants of the float kernel.  Chosen so that every read length up to 32*16-1 has a variant with
-// >= ~85 % row utilisation: see pick_variant() in pmm_engine.cu.
-#define PMM_F32_VARIANTS(X) \
-    X(4, 8) X(5, 8) X(6, 8) X(7, 8) X(8, 8) X(10, 8) X(12, 8) X(13, 8) X(14, 8) X(16, 8) \
-    X(4, 16) X(5, 16) X(6, 16) X(7, 16) X(8, 16) X(9, 16) X(10, 16) X(11, 16) X(12, 16) X(14, 16) X(16, 16) \
-    X(4, 32) X(5, 32) X(6, 32) X(7, 32) X(8, 32) X(9, 32) X(10, 32) X(12, 32) X(14, 32) X(16, 32)
-
 }  // namespace
-
-bool forward_f32_has_variant(int K, int W)
-{
-#define X(k, w) if (K == k && W == w) return true;
-    PMM_F32_VARIANTS(X)
-#undef X
-    return false;
-}
 
 cudaError_t launch_forward_f32(int K, int W, bool striped, const ForwardArgs& a, int ctas, cudaStream_t s)
 {
     if (striped) {
-        if (K == 8 && W == 32) return launch_variant<float, 8, 32, true, false>(a, ctas, s);
+        if (K == kStripedK && W == 32) return launch_variant<float, kStripedK, 32, true, false>(a, ctas, s);
         return cudaErrorInvalidValue;
     }
 #define X(k, w) if (K == k && W == w) return launch_variant<float, k, w, false, false>(a, ctas, s);
@@ -435,7 +409,7 @@ cudaError_t launch_forward_f32(int K, int W, bool striped, const ForwardArgs& a,
 
 int forward_f32_ctas_per_sm(int K, int W, bool striped)
 {
-    if (striped) return (K == 8 && W == 32) ? variant_ctas_per_sm<float, 8, 32, true, false>() : 0;
+    if (striped) return (K == kStripedK && W == 32) ? variant_ctas_per_sm<float, kStripedK, 32, true, false>() : 0;
 #define X(k, w) if (K == k && W == w) return variant_ctas_per_sm<float, k, w, false, false>();
     PMM_F32_VARIANTS(X)
 #undef X

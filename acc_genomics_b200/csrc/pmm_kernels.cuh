@@ -18,28 +18,15 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "pmm_types.h"
+
 namespace pmm {
 
 constexpr uint8_t kSep = 0xFF;          // separator element of the hap stream
 constexpr int kStreamFrontPad = 64;     // bytes before stream[0] that lanes may read (and ignore) while filling
 constexpr int kStreamTailPad = 128;
-constexpr int kWarpsPerCta = 4;
-constexpr int kMaxGroups = 4;           // 32 / W, W >= 8
 
-struct ReadDesc { uint32_t off, stride, len; };
-struct HapDesc  { uint32_t off, len; };
 
-// One unit of work for one warp.  Group g (lanes g*W .. g*W+W-1) owns read[g]; all groups walk the same run of
-// haplotypes [hap_first, hap_first + nhaps).  The result for (read[g], hap_first + n) goes to out[out_base[g] + n].
-struct Task {
-    uint32_t read[kMaxGroups];
-    uint32_t out_base[kMaxGroups];
-    uint32_t hap_first;
-    uint32_t nhaps;
-    uint32_t nreads;
-    uint32_t reserved;
-};
-static_assert(sizeof(Task) == 48, "Task layout");
 
 struct DeviceTables {
     const float*  ph2pr_f;
@@ -74,14 +61,10 @@ cudaError_t launch_forward_f64(bool flush, const ForwardArgs& a, int ctas, cudaS
 // Shared memory one CTA of the given variant needs (bytes) and CTAs per SM it reaches.
 int forward_f32_ctas_per_sm(int K, int W, bool striped);
 int forward_f64_ctas_per_sm(bool flush);
-bool forward_f32_has_variant(int K, int W);
-constexpr int kF64K = 6;            // rows per lane of the double kernel (W = 32): 191-base reads in one stripe
 
 cudaError_t launch_build_stream(const uint8_t* hap_blob, const HapDesc* haps, const uint32_t* spos, uint32_t num_hap,
                                 uint8_t* stream, float* inity_f, double* inity_d, float ic_f, double ic_d,
                                 cudaStream_t s);
-
-struct RegionDesc { uint32_t read_first, nreads, hap_first, nhaps, out_first; };
 
 // Scan raw[] for values below 1e-28f and append one single-pair Task per hit (read, hap, slot) to fb_tasks.
 cudaError_t launch_compact_fallback(const float* raw, const RegionDesc* regions, uint32_t nregions,

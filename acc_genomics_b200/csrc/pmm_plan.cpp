@@ -1,0 +1,120 @@
+// pmm_plan.cpp -- see pmm_plan.h.
+//
+// What the reference does at this point is device-specific load balancing for its FPGA processing units
+// (/root/reference/pairhmm/interface/PairHMMFpgaInterface.cpp:67-170) and tiling to the device limits
+// (/root/reference/pairhmm/client/PairHMMWorker.cpp:217-221).  On the GPU there are no length limits; the
+// planner's job is to keep lanes full (pick K x W per read length), keep the wavefront bubbles rare (runs of
+// haplotypes per task) and keep the work queue deep enough for ~2400 resident warps.
+#include "pmm_plan.h"
+
+#include <algorithm>
+#include <numeric>
+
+namespace pmm {
+
+// Maximise useful FP work per issue slot, 12*R / (W * step_cost(K)), subject to R + 1 <= K * W (one boundary row),
+// with a mild penalty for variants whose register count lowers occupancy.
+Variant pick_variant(int R)
+{
+    Variant best{kStripedK, 32, true};
+    double best_eff = -1.0;
+    for (int W = 8; W <= 32; W *= 2)
+        for (int K = 4; K <= 16; ++K) {
+            if (!forward_f32_has_variant(K, W) || R + 1 > K * W) continue;
+            double eff = 12.0 * R / (W * step_cost(K));
+            if (K > 12) eff *= 0.97;
+            if (eff > best_eff) { best_eff = eff; best = Variant{K, W, false}; }
+        }
+    return best;
+}
+
+int plan_job(uint32_t num_read, const uint32_t* read_off, uint32_t num_hap, const uint32_t* hap_off,
+             uint32_t num_region, const pmm_region_t* regions, int sm_count, int tasks_per_warp,
+             Plan& plan, std::string& err)
+{
+    plan = Plan();
+    if (!num_read || !num_hap || !num_region || !read_off || !hap_off || !regions) { err = "empty job"; return PMM_ERR_INVALID; }
+    const uint64_t total_bases = (uint64_t)read_off[num_read] - read_off[0];
+    const uint64_t total_hap = (uint64_t)hap_off[num_hap] - hap_off[0];
+    if (read_off[num_read] < read_off[0] || hap_off[num_hap] < hap_off[0] || total_bases * 5 + total_hap >= (1ull << 31)) {
+        err = "job larger than 2 GiB: split it"; return PMM_ERR_INVALID;
+    }
+    for (uint32_t i = 0; i < num_read; ++i) {
+        if (read_off[i + 1] <= read_off[i]) { err = "read of length 0"; return PMM_ERR_INVALID; }
+        plan.max_read_len = std::max(plan.max_read_len, read_off[i + 1] - read_off[i]);
+    }
+    for (uint32_t h = 0; h < num_hap; ++h) {
+        if (hap_off[h + 1] <= hap_off[h]) { err = "haplotype of length 0"; return PMM_ERR_INVALID; }
+        plan.max_hap_len = std::max(plan.max_hap_len, hap_off[h + 1] - hap_off[h]);
+    }
+
+    // ---- regions, result offsets, the reference's cell count (host/main.cpp:305-313) -------------------------
+    plan.regions.resize(num_region);
+    for (uint32_t g = 0; g < num_region; ++g) {
+        const pmm_region_t& r = regions[g];
+        if (!r.num_read || !r.num_hap || (uint64_t)r.read_first + r.num_read > num_read ||
+            (uint64_t)r.hap_first + r.num_hap > num_hap) { err = "region out of range"; return PMM_ERR_INVALID; }
+        plan.regions[g] = RegionDesc{r.read_first, r.num_read, r.hap_first, r.num_hap, (uint32_t)plan.pairs};
+        plan.pairs += (uint64_t)r.num_read * r.num_hap;
+        plan.cells += (uint64_t)(read_off[r.read_first + r.num_read] - read_off[r.read_first]) *
+                      (uint64_t)(hap_off[r.hap_first + r.num_hap] - hap_off[r.hap_first]);
+        if (plan.pairs >= (1ull << 31)) { err = "more than 2^31 pairs in one job: split it"; return PMM_ERR_INVALID; }
+    }
+
+    // ---- read groups --------------------------------------------------------------------------------------------
+    // Reads of a region are sorted by length (longest first); the longest unassigned read picks the (K, W)
+    // variant and shares its warp with the next 32/W - 1 reads.
+    struct Group { Variant v; uint32_t region; uint32_t reads[kMaxGroups]; uint32_t n; };
+    std::vector<Group> groups;
+    std::vector<uint32_t> order;
+    uint64_t group_haps = 0;
+    for (uint32_t g = 0; g < num_region; ++g) {
+        const pmm_region_t& r = regions[g];
+        order.resize(r.num_read);
+        std::iota(order.begin(), order.end(), r.read_first);
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+            return read_off[x + 1] - read_off[x] > read_off[y + 1] - read_off[y]; });
+        for (uint32_t k = 0; k < r.num_read;) {
+            const int R = (int)(read_off[order[k] + 1] - read_off[order[k]]);
+            Group gr; gr.v = pick_variant(R); gr.region = g; gr.n = 0;
+            const uint32_t G = gr.v.striped ? 1u : (uint32_t)(32 / gr.v.W);
+            for (; gr.n < G && k < r.num_read; ++k) gr.reads[gr.n++] = order[k];
+            for (uint32_t z = gr.n; z < (uint32_t)kMaxGroups; ++z) gr.reads[z] = 0;
+            groups.push_back(gr);
+            group_haps += r.num_hap;
+        }
+    }
+
+    // ---- runs of haplotypes: about tasks_per_warp queued tasks per resident warp --------------------------------
+    const uint64_t resident_warps = (uint64_t)std::max(1, sm_count) * 16;
+    const uint64_t target_tasks = std::max<uint64_t>(1, resident_warps * (uint64_t)std::max(1, tasks_per_warp));
+    plan.haps_per_task = (uint32_t)std::max<uint64_t>(1, (group_haps + target_tasks - 1) / target_tasks);
+
+    // launches ordered by variant (largest footprint first); stable within a variant
+    std::vector<uint32_t> gorder(groups.size());
+    std::iota(gorder.begin(), gorder.end(), 0u);
+    auto vkey = [](const Variant& v) { return (v.striped ? 1 << 20 : 0) + v.K * v.W * 64 + v.W; };
+    std::stable_sort(gorder.begin(), gorder.end(), [&](uint32_t x, uint32_t y) { return vkey(groups[x].v) > vkey(groups[y].v); });
+
+    for (uint32_t gi : gorder) {
+        const Group& gr = groups[gi];
+        const RegionDesc& r = plan.regions[gr.region];
+        const uint32_t hpt = gr.v.striped ? 1u : std::min(plan.haps_per_task, r.nhaps);
+        if (plan.segs.empty() || !(plan.segs.back().v == gr.v)) plan.segs.push_back(LaunchSeg{gr.v, (uint32_t)plan.tasks.size(), 0});
+        const uint32_t nruns = (r.nhaps + hpt - 1) / hpt;          // runs of near-equal length
+        for (uint32_t run = 0; run < nruns; ++run) {
+            const uint32_t h0 = (uint32_t)((uint64_t)r.nhaps * run / nruns), h1 = (uint32_t)((uint64_t)r.nhaps * (run + 1) / nruns);
+            Task t;
+            for (uint32_t z = 0; z < (uint32_t)kMaxGroups; ++z) {
+                t.read[z] = gr.reads[z];
+                t.out_base[z] = z < gr.n ? r.out_first + (gr.reads[z] - r.read_first) * r.nhaps + h0 : 0;
+            }
+            t.hap_first = r.hap_first + h0; t.nhaps = h1 - h0; t.nreads = gr.n; t.reserved = 0;
+            plan.tasks.push_back(t);
+            plan.segs.back().task_count++;
+        }
+    }
+    return PMM_OK;
+}
+
+}  // namespace pmm

@@ -1,0 +1,35 @@
+// pmm_plan.h -- host-side planner: cuts a job (regions of reads x haplotypes) into warp-tasks.  Pure C++, no CUDA,
+// so that the CPU test-suite can check it (tests/test_plan.py through pmm_plan_flat).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "../../include/pairhmm_cuda.h"
+#include "pmm_types.h"
+
+namespace pmm {
+
+struct LaunchSeg { Variant v; uint32_t task_first, task_count; };
+
+struct Plan {
+    std::vector<RegionDesc> regions;
+    std::vector<Task> tasks;            // grouped by variant, see segs
+    std::vector<LaunchSeg> segs;        // one kernel launch each, largest footprint first
+    uint64_t pairs = 0, cells = 0;
+    uint32_t max_hap_len = 0, max_read_len = 0;
+    uint32_t haps_per_task = 0;
+};
+
+// Issue slots one step of K cells costs in the float kernel (from the SASS of the steady loop: 12 FP per cell,
+// one LDS.128 per 4 rows, and 3 SHFL + LDG + 2 sum FADD + address/loop overhead per step).
+inline double step_cost(int K) { return 12.25 * K + 9.0; }
+
+// Best (K, W) for a read of R bases.
+Variant pick_variant(int R);
+
+// Returns PMM_OK or PMM_ERR_INVALID with a message.
+int plan_job(uint32_t num_read, const uint32_t* read_off, uint32_t num_hap, const uint32_t* hap_off,
+             uint32_t num_region, const pmm_region_t* regions, int sm_count, int tasks_per_warp,
+             Plan& plan, std::string& err);
+
+}  // namespace pmm

@@ -22,7 +22,7 @@ EXPORTS = [
     "pmm_create", "pmm_destroy", "pmm_last_error", "pmm_device_count", "pmm_set_option",
     "pmm_forward_raw_serialized", "pmm_forward_log10", "pmm_forward_log10_serialized",
     "pmm_stage_flat", "pmm_launch", "pmm_sync", "pmm_fetch_raw", "pmm_fetch_log10", "pmm_fetch_fallback_mask",
-    "pmm_get_stats", "pmm_measure_fp32_peak",
+    "pmm_get_stats", "pmm_measure_fp32_peak", "pmm_plan_flat", "pmm_host_table",
 ]
 
 
@@ -35,6 +35,11 @@ class PmmStats(C.Structure):
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("kernel_launches", C.c_uint32),
                 ("f32_tasks", C.c_uint32), ("ms_stage", C.c_float), ("ms_f32", C.c_float), ("ms_fallback", C.c_float),
                 ("ms_fetch", C.c_float)]
+
+
+class PmmTaskInfo(C.Structure):
+    _fields_ = [("read", C.c_uint32 * 4), ("out_base", C.c_uint32 * 4), ("hap_first", C.c_uint32), ("num_hap", C.c_uint32),
+                ("num_read", C.c_uint32), ("rows_per_lane", C.c_uint32), ("lanes_per_read", C.c_uint32), ("striped", C.c_uint32)]
 
 
 class PmmRead(C.Structure):
@@ -79,6 +84,8 @@ def load_library() -> C.CDLL:
         L.pmm_fetch_fallback_mask.argtypes = [vp, vp, u64]
         L.pmm_get_stats.argtypes = [vp, C.POINTER(PmmStats)]
         L.pmm_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.pmm_plan_flat.argtypes = [u32, vp, u32, vp, u32, vp, C.c_int, C.c_int, vp, u64, C.POINTER(u64)]
+        L.pmm_host_table.argtypes = [C.c_int, vp, u64]
         for n in EXPORTS:
             if n not in ("pmm_destroy", "pmm_last_error"):
                 getattr(L, n).restype = C.c_int
@@ -102,6 +109,38 @@ def concat_regions(batches: Sequence[Batch]):
     return dict(num_read=nr, read_off=np.ascontiguousarray(np.concatenate(ro)), rs=cat("rs"), q=cat("q"), i=cat("i"),
                 d=cat("d"), c=cat("c"), num_hap=nh, hap_off=np.ascontiguousarray(np.concatenate(ho)), hap=cat("hap"),
                 regions=regs, num_region=len(batches), pairs=sum(b.num_pairs for b in batches))
+
+
+def host_table(which: int) -> np.ndarray:
+    """Tables the engine uploads (host libm); see pmm_host_table in include/pairhmm_cuda.h.  No GPU needed."""
+    L = load_library()
+    dt, n = {0: (np.float32, 128), 1: (np.float32, 8256), 2: (np.float64, 128), 3: (np.float64, 8256),
+             4: (np.float32, 1), 5: (np.float64, 1)}[which]
+    out = np.zeros(n, dtype=dt)
+    rc = L.pmm_host_table(which, out.ctypes.data, out.nbytes)
+    if rc != PMM_OK:
+        raise PmmError(rc, "pmm_host_table")
+    return out
+
+
+def plan(batches: Sequence[Batch] | Batch, sm_count: int = 148, tasks_per_warp: int = 6):
+    """Host-only: the warp-tasks pmm_stage_flat would build.  Returns a list of dicts.  No GPU needed."""
+    if isinstance(batches, Batch):
+        batches = [batches]
+    L = load_library()
+    j = concat_regions(batches)
+    n = C.c_uint64()
+    args = (j["num_read"], j["read_off"].ctypes.data, j["num_hap"], j["hap_off"].ctypes.data, j["num_region"],
+            C.cast(j["regions"], C.c_void_p), sm_count, tasks_per_warp)
+    rc = L.pmm_plan_flat(*args, None, 0, C.byref(n))
+    if rc != PMM_OK:
+        raise PmmError(rc, L.pmm_last_error(None).decode())
+    buf = (PmmTaskInfo * n.value)()
+    rc = L.pmm_plan_flat(*args, C.cast(buf, C.c_void_p), n.value, C.byref(n))
+    if rc != PMM_OK:
+        raise PmmError(rc, L.pmm_last_error(None).decode())
+    return [dict(read=list(t.read)[: t.num_read], out_base=list(t.out_base)[: t.num_read], hap_first=t.hap_first,
+                 num_hap=t.num_hap, K=t.rows_per_lane, W=t.lanes_per_read, striped=bool(t.striped)) for t in buf]
 
 
 class PairHMMEngine:

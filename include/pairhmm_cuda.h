@@ -111,6 +111,25 @@ int  pmm_fetch_fallback_mask(pmm_ctx* ctx, uint8_t* mask, uint64_t capacity);
 
 int  pmm_get_stats(const pmm_ctx* ctx, pmm_stats_t* out);
 
+/* ---- host-only entry points (no GPU needed) -------------------------------------------------------------
+ * pmm_plan_flat: how pmm_stage_flat would cut a job into warp-tasks on a GPU with sm_count SMs.  This is the
+ * planner that stands where the reference balances reads over FPGA processing units and tiles batches to
+ * 2048 x 128 (interface/PairHMMFpgaInterface.cpp:67-170, client/PairHMMWorker.cpp:217-221).  With out == NULL
+ * only the count is returned.  Errors are reported through pmm_last_error(NULL). */
+typedef struct {
+    uint32_t read[4];          /* reads sharing the warp (num_read of them are valid)                    */
+    uint32_t out_base[4];      /* result index of (read[g], hap_first)                                    */
+    uint32_t hap_first, num_hap, num_read;
+    uint32_t rows_per_lane, lanes_per_read, striped;   /* kernel variant: K, W, multi-stripe flag         */
+} pmm_task_info_t;
+int  pmm_plan_flat(uint32_t num_read, const uint32_t* read_off, uint32_t num_hap, const uint32_t* hap_off,
+                   uint32_t num_region, const pmm_region_t* regions, int sm_count, int tasks_per_warp,
+                   pmm_task_info_t* out, uint64_t capacity, uint64_t* num_tasks);
+/* The probability tables the engine uploads, as generated by the host libm following Context<NUMBER>
+ * (xlnx/host/Context.h:42-61,:105-110,:145-151).  which: 0 ph2pr f32[128], 1 matchToMatch f32[8256],
+ * 2 ph2pr f64[128], 3 matchToMatch f64[8256], 4 log10(2^120) f32, 5 log10(2^1020) f64. */
+int  pmm_host_table(int which, void* out, uint64_t capacity_bytes);
+
 /* Measured FP32 instruction issue rate of this GPU in lane-instructions per second (the roofline denominator of
  * SURVEY.md section 8d; an independent FMUL/FADD stream, ~20 ms).  Also returns the SM clock seen while measuring. */
 int  pmm_measure_fp32_peak(pmm_ctx* ctx, double* lane_instr_per_s, double* sm_mhz);

@@ -14,10 +14,11 @@
  *   - threshold, double re-run and log10        FalconPairHMM.cpp:69-95 == ../../client/PairHMMWorker.cpp:171-193
  *
  * The restatement is scalar and row-major, but reproduces the *arithmetic* of the AVX implementation bit for
- * bit, including one artefact of its striping: for every stripe after the first, stripeINITIALIZATION sets
- * M_t_1_y = M_t_1 = {shiftOutM[AVX_LENGTH], 0, ...} (avx-pairhmm-template.h:171-176), so the first row of the
- * stripe sees M[r-1][1] instead of M[r][0] = 0 as its "left M" when it computes Y[r][1].  Stripe height is the
- * SIMD width: 8 rows for float, 4 for double (avx-functions-float.h: AVX_LENGTH 8, avx-functions-double.h: 4).
+ * bit.  One oddity of the AVX striping needs no special case: for every stripe after the first,
+ * stripeINITIALIZATION sets M_t_1_y = M_t_1 = {shiftOutM[AVX_LENGTH], 0, ...} (avx-pairhmm-template.h:171-176),
+ * so the first row of the stripe uses M[r-1][1] instead of M[r][0] as its "left M" in column 1 -- but M[r-1][1]
+ * is exactly 0 for r-1 >= 2 (column 0 of every row below the first is all zeros), so nothing changes
+ * (tests/test_oracle.py::test_stripe_artefact_is_void).
  *
  * Pinning: oracle/_ref/libpairhmm_ref.so is the reference's own source compiled with -O3 -mavx
  * -ffp-contract=off (see oracle/Makefile); tests/test_oracle.py checks this file against it bit for bit, and
@@ -123,7 +124,7 @@ static int m2m_index(int ins, int del)
     return ((mx * (mx + 1)) >> 1) + mn;
 }
 
-#define DEFINE_FORWARD(NAME, T, STRIPE, PH2PR, M2M, IC)                                                       \
+#define DEFINE_FORWARD(NAME, T, PH2PR, M2M, IC)                                                               \
 static T NAME(int R, int C, const char* rs, const char* q, const char* ins, const char* del,                  \
               const char* gcp, const char* hap)                                                               \
 {                                                                                                             \
@@ -147,7 +148,6 @@ static T NAME(int R, int C, const char* rs, const char* q, const char* ins, cons
         const T w_match = (T)1.0 - dm;             /* :156 */                                                 \
         const T w_mis = dm / (T)3.0;               /* :158 */                                                 \
         const unsigned char rc = cls_tab[(unsigned char)rs[r - 1]];                                           \
-        const int stripe_first = (r > 1) && ((r - 1) % STRIPE == 0);                                          \
         cM[0] = (T)0; cX[0] = (T)0; cY[0] = (T)0;                                                             \
         for (int c = 1; c <= C; c++) {                                                                        \
             const int match = (rc == hc[c - 1]) || rc == 4 || hc[c - 1] == 4;                                 \
@@ -163,9 +163,8 @@ static T NAME(int R, int C, const char* rs, const char* q, const char* ins, cons
             T x1 = pM[c] * pMX;                                                                               \
             T x2 = pX[c] * pXX;                                                                               \
             cX[c] = x1 + x2;                                                                                  \
-            /* :197  Y = Mleft*pMY + Yleft*pYY ; :171-176 the stripe artefact at c == 1 */                    \
-            T mleft = (c == 1 && stripe_first) ? pM[1] : cM[c - 1];                                           \
-            T y1 = mleft * pMY;                                                                               \
+            /* :197  Y = Mleft*pMY + Yleft*pYY */                                                             \
+            T y1 = cM[c - 1] * pMY;                                                                           \
             T y2 = cY[c - 1] * pYY;                                                                           \
             cY[c] = y1 + y2;                                                                                  \
         }                                                                                                     \
@@ -180,8 +179,8 @@ static T NAME(int R, int C, const char* rs, const char* q, const char* ins, cons
     return res;                                                                                               \
 }
 
-DEFINE_FORWARD(forward_f32, float, 8, ph2pr_f, m2m_f, IC_f)
-DEFINE_FORWARD(forward_f64, double, 4, ph2pr_d, m2m_d, IC_d)
+DEFINE_FORWARD(forward_f32, float, ph2pr_f, m2m_f, IC_f)
+DEFINE_FORWARD(forward_f64, double, ph2pr_d, m2m_d, IC_d)
 
 float pmm_oracle_f32(int R, int C, const char* rs, const char* q, const char* ins, const char* del,
                      const char* gcp, const char* hap)

@@ -1,0 +1,78 @@
+"""Host logic: cutting a job into warp-tasks (pmm_plan_flat, no GPU needed)."""
+import numpy as np
+import pytest
+
+from acc_genomics_b200 import synth
+from acc_genomics_b200.batch import Batch
+
+
+def coverage(batches, tasks):
+    """Every (read, hap) pair of every region is produced exactly once, at the right output index."""
+    total = sum(b.num_pairs for b in batches)
+    seen = np.zeros(total, dtype=np.int32)
+    # global read/hap index -> (region, local index)
+    rfirst = np.cumsum([0] + [b.num_read for b in batches]); hfirst = np.cumsum([0] + [b.num_hap for b in batches])
+    ofirst = np.cumsum([0] + [b.num_pairs for b in batches])
+    for t in tasks:
+        for g, r in enumerate(t["read"]):
+            reg = int(np.searchsorted(rfirst, r, side="right") - 1)
+            b = batches[reg]
+            assert hfirst[reg] <= t["hap_first"] and t["hap_first"] + t["num_hap"] <= hfirst[reg + 1]
+            for n in range(t["num_hap"]):
+                want = ofirst[reg] + (r - rfirst[reg]) * b.num_hap + (t["hap_first"] + n - hfirst[reg])
+                assert t["out_base"][g] + n == want
+                seen[want] += 1
+    assert (seen == 1).all()
+
+
+@pytest.mark.parametrize("cfg,scale", [(1, 1.0), (2, 0.2), (4, 0.25), (5, 0.004)])
+def test_every_pair_covered_once(built, cfg, scale):
+    from acc_genomics_b200 import engine
+    batches = synth.config(cfg, scale=scale)
+    tasks = engine.plan(batches)
+    coverage(batches, tasks)
+    lens = np.concatenate([b.read_lens for b in batches])
+    for t in tasks:
+        assert 1 <= len(t["read"]) <= 32 // t["W"]
+        for r in t["read"]:
+            assert t["striped"] or lens[r] + 1 <= t["K"] * t["W"], "read does not fit its row block"
+
+
+def test_variant_choice(built):
+    from acc_genomics_b200 import engine
+
+    def variant(length):
+        b = synth.region(np.random.Generator(np.random.PCG64(1)), [length] * 8, [length + 50] * 2)
+        t = engine.plan(b)[0]
+        return t["K"], t["W"], t["striped"]
+    assert variant(151) == (10, 16, False)       # 2 reads per warp, 152 of 160 rows used
+    k, w, s = variant(250)
+    assert not s and 251 <= k * w <= 256
+    k, w, s = variant(101)
+    assert not s and k * w >= 102 and k * w <= 112
+    assert variant(511)[:2] == (16, 32) and not variant(511)[2]
+    assert variant(512)[2] and variant(3000)[2]  # longer than 32 x 16 - 1: multi-stripe kernel
+    k, w, s = variant(1)
+    assert not s and w == 8
+
+
+def test_queue_depth_follows_gpu_size(built):
+    from acc_genomics_b200 import engine
+    b = synth.config(2, scale=0.5)
+    small = engine.plan(b, sm_count=16, tasks_per_warp=2)
+    big = engine.plan(b, sm_count=148, tasks_per_warp=8)
+    assert len(big) > len(small)
+    coverage(b, small); coverage(b, big)
+
+
+def test_rejects_malformed_jobs(built):
+    from acc_genomics_b200 import engine
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    good = Batch.from_lists([(acgt, acgt, acgt, acgt, acgt)], [acgt])
+    empty_read = Batch(np.array([0, 0, 4], dtype=np.int32), acgt, acgt, acgt, acgt, acgt, good.hap_off, good.hap)
+    with pytest.raises(engine.PmmError):
+        engine.plan(empty_read)
+    empty_hap = Batch(good.read_off, acgt, acgt, acgt, acgt, acgt, np.array([0, 4, 4], dtype=np.int32), acgt)
+    with pytest.raises(engine.PmmError):
+        engine.plan(empty_hap)
+    assert len(engine.plan(good)) == 1
