@@ -367,8 +367,10 @@ int pmm_set_option(pmm_ctx* c, const char* key, const char* value)
     if (!c || !key || !value) return PMM_ERR_INVALID;
     const std::string k(key);
     if (k == "stream") {
-        const unsigned long long v = strtoull(value, nullptr, 0);
-        c->stream = v ? reinterpret_cast<cudaStream_t>(v) : c->own_stream;
+        const std::string sv(value);
+        if (sv == "own") c->stream = c->own_stream;
+        else if (sv == "default") c->stream = nullptr;                       // the legacy default stream
+        else c->stream = reinterpret_cast<cudaStream_t>(strtoull(value, nullptr, 0));
         return PMM_OK;
     }
     if (k == "tasks_per_warp") {

@@ -67,7 +67,8 @@ const char* pmm_last_error(const pmm_ctx* ctx);     /* ctx may be NULL: last err
 int  pmm_device_count(void);
 
 /* Options (strings, like the task's get_conf(key, value), task/xlnx/PairHMMTask.h:73-77):
- *   "stream"          = decimal value of a cudaStream_t to run on instead of the context's own stream
+ *   "stream"          = value of a cudaStream_t (decimal or 0x..) to run on, "default" for the legacy default
+ *                       stream, "own" for the context's own non-blocking stream (the initial setting)
  *   "tasks_per_warp"  = target queue depth per resident warp used when cutting regions into warp-tasks        */
 int  pmm_set_option(pmm_ctx* ctx, const char* key, const char* value);
 
