@@ -547,6 +547,35 @@ int pmm_fetch_log10(pmm_ctx* c, double* out, uint64_t cap, uint64_t* n_fallback)
     return PMM_OK;
 }
 
+int pmm_fetch_fallback(pmm_ctx* c, uint32_t* index, double* value, uint64_t cap, uint64_t* count)
+{
+    if (!c || !count) return PMM_ERR_INVALID;
+    uint32_t nfb = 0;
+    int rc = fetch_common(c, true, &nfb, nullptr);
+    if (rc) return rc;
+    *count = nfb;
+    if (!index && !value) return PMM_OK;
+    if (!index || !value || cap < nfb) return c->fail(PMM_ERR_INVALID, "fallback buffers too small");
+    const char* ho = static_cast<const char*>(c->h_out.p);
+    const uint32_t* hidx = reinterpret_cast<const uint32_t*>(ho + 256 + align_up(sizeof(float) * c->pairs));
+    const double* hd = reinterpret_cast<const double*>(reinterpret_cast<const char*>(hidx) + align_up(sizeof(uint32_t) * c->pairs));
+    memcpy(index, hidx, sizeof(uint32_t) * nfb);
+    memcpy(value, hd, sizeof(double) * nfb);
+    return PMM_OK;
+}
+
+int pmm_stage_serialized(pmm_ctx* c, const void* reads_ser, uint64_t reads_bytes, const void* haps_ser,
+                         uint64_t haps_bytes, int* num_read, int* num_hap)
+{
+    if (!c) return PMM_ERR_INVALID;
+    cudaSetDevice(c->device);
+    int rc = flatten_serialized(c, reads_ser, reads_bytes, haps_ser, haps_bytes);
+    if (rc) return rc;
+    if (num_read) *num_read = (int)c->tmp_roff.size() - 1;
+    if (num_hap) *num_hap = (int)c->tmp_hoff.size() - 1;
+    return stage_tmp_single_region(c);
+}
+
 int pmm_get_stats(const pmm_ctx* c, pmm_stats_t* out)
 {
     if (!c || !out) return PMM_ERR_INVALID;

@@ -21,7 +21,7 @@ PMM_OK, PMM_ERR_INVALID, PMM_ERR_CUDA, PMM_ERR_NO_DEVICE, PMM_ERR_STATE = 0, 1, 
 EXPORTS = [
     "pmm_create", "pmm_destroy", "pmm_last_error", "pmm_device_count", "pmm_set_option",
     "pmm_forward_raw_serialized", "pmm_forward_log10", "pmm_forward_log10_serialized",
-    "pmm_stage_flat", "pmm_launch", "pmm_sync", "pmm_fetch_raw", "pmm_fetch_log10", "pmm_fetch_fallback_mask",
+    "pmm_stage_flat", "pmm_stage_serialized", "pmm_fetch_fallback", "pmm_launch", "pmm_sync", "pmm_fetch_raw", "pmm_fetch_log10", "pmm_fetch_fallback_mask",
     "pmm_get_stats", "pmm_measure_fp32_peak", "pmm_plan_flat", "pmm_host_table",
 ]
 
@@ -78,6 +78,8 @@ def load_library() -> C.CDLL:
         L.pmm_forward_log10_serialized.argtypes = [vp, vp, u64, vp, u64, vp, u64, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(u64)]
         L.pmm_forward_log10.argtypes = [vp, C.POINTER(PmmRead), C.c_int, C.POINTER(PmmHap), C.c_int, vp, C.POINTER(u64)]
         L.pmm_stage_flat.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp, u32, vp, vp, u32, vp]
+        L.pmm_stage_serialized.argtypes = [vp, vp, u64, vp, u64, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.pmm_fetch_fallback.argtypes = [vp, vp, vp, u64, C.POINTER(u64)]
         L.pmm_launch.argtypes = [vp]; L.pmm_sync.argtypes = [vp]
         L.pmm_fetch_raw.argtypes = [vp, vp, u64]
         L.pmm_fetch_log10.argtypes = [vp, vp, u64, C.POINTER(u64)]

@@ -103,10 +103,17 @@ int  pmm_stage_flat(pmm_ctx* ctx, uint32_t num_read, const uint32_t* read_off,
                     const uint8_t* bases, const uint8_t* q, const uint8_t* i, const uint8_t* d, const uint8_t* c,
                     uint32_t num_hap, const uint32_t* hap_off, const uint8_t* hap_bases,
                     uint32_t num_region, const pmm_region_t* regions);
+/* Same, from the task's serialized input blocks (what PairHMM::prepare() receives, task/xlnx/PairHMMTask.cpp:35-38). */
+int  pmm_stage_serialized(pmm_ctx* ctx, const void* reads_ser, uint64_t reads_bytes,
+                          const void* haps_ser, uint64_t haps_bytes, int* num_read, int* num_hap);
 int  pmm_launch(pmm_ctx* ctx);
 int  pmm_sync(pmm_ctx* ctx);
 int  pmm_fetch_raw(pmm_ctx* ctx, float* out_raw, uint64_t out_capacity);
 int  pmm_fetch_log10(pmm_ctx* ctx, double* out, uint64_t out_capacity, uint64_t* n_fallback);
+/* The pairs that took the double re-run: index[k] = position in the read-major result, value[k] = the double
+ * likelihood scaled by 2^1020 (what compute_fp_avxd returns, client/PairHMMWorker.cpp:182).  With index == value ==
+ * NULL only the count is returned. */
+int  pmm_fetch_fallback(pmm_ctx* ctx, uint32_t* index, double* value, uint64_t capacity, uint64_t* count);
 /* The fallback decision of the last launched job: mask[k] = 1 where raw[k] < 1e-28f. */
 int  pmm_fetch_fallback_mask(pmm_ctx* ctx, uint8_t* mask, uint64_t capacity);
 
