@@ -69,7 +69,8 @@ struct pmm_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string err;
-    int tasks_per_warp = 6;
+    int tasks_per_warp = 16;
+    Variant force{0, 0, false};         // "force_variant" option (tuning sweeps): K,W of the float kernel
 
     // device-resident tables
     DevBuf tables;
@@ -77,9 +78,10 @@ struct pmm_ctx {
 
     // job state
     PinBuf h_in;  DevBuf d_in;          // one arena: read blob | descs | hap blob | descs | spos | tasks | regions
-    DevBuf d_stream, d_iyf, d_iyd, d_raw, d_fb_tasks, d_fb_idx, d_tiny_tasks, d_dres, d_ctrl, d_scratch, d_probe;
+    DevBuf d_params, d_stream, d_iyf, d_iyd, d_raw, d_fb_tasks, d_fb_idx, d_tiny_tasks, d_dres, d_ctrl, d_scratch, d_probe;
     PinBuf h_out;                       // raw floats | fb idx | dres
-    size_t off_rblob = 0, off_rdesc = 0, off_hblob = 0, off_hdesc = 0, off_spos = 0, off_tasks = 0, off_regions = 0;
+    size_t off_rblob = 0, off_rdesc = 0, off_hblob = 0, off_hdesc = 0, off_spos = 0, off_tasks = 0, off_regions = 0, off_groups = 0;
+    uint32_t num_groups = 0;
     uint32_t num_read = 0, num_hap = 0, num_region = 0, num_tasks = 0;
     uint64_t pairs = 0, cells = 0;
     uint32_t max_hap_len = 0;
@@ -141,7 +143,8 @@ int stage_common(pmm_ctx* c, uint32_t num_read, const uint32_t* read_off, const 
     Plan plan;
     {
         std::string perr;
-        rc = plan_job(num_read, read_off, num_hap, hap_off, num_region, regions, c->sm_count, c->tasks_per_warp, plan, perr);
+        rc = plan_job(num_read, read_off, num_hap, hap_off, num_region, regions, c->sm_count, c->tasks_per_warp, plan, perr,
+                      c->force.K ? &c->force : nullptr);
         if (rc) return c->fail(rc, perr);
     }
     const uint64_t total_bases = read_off[num_read] - read_off[0];
@@ -158,6 +161,7 @@ int stage_common(pmm_ctx* c, uint32_t num_read, const uint32_t* read_off, const 
     const size_t sz_hblob = total_hap, sz_hdesc = sizeof(HapDesc) * num_hap;
     const size_t sz_spos = sizeof(uint32_t) * (num_hap + 1), sz_tasks = sizeof(Task) * tasks.size();
     const size_t sz_regions = sizeof(RegionDesc) * num_region;
+    const size_t sz_groups = sizeof(GroupDesc) * plan.groups.size();
     size_t off = 0;
     c->off_rblob = off; off = align_up(off + sz_rblob);
     c->off_rdesc = off; off = align_up(off + sz_rdesc);
@@ -166,6 +170,7 @@ int stage_common(pmm_ctx* c, uint32_t num_read, const uint32_t* read_off, const 
     c->off_spos = off; off = align_up(off + sz_spos);
     c->off_tasks = off; off = align_up(off + sz_tasks);
     c->off_regions = off; off = align_up(off + sz_regions);
+    c->off_groups = off; off = align_up(off + sz_groups);
     const size_t arena = off;
     PMM_CUDA(c, c->h_in.reserve(arena));
     PMM_CUDA(c, c->d_in.reserve(arena));
@@ -187,10 +192,13 @@ int stage_common(pmm_ctx* c, uint32_t num_read, const uint32_t* read_off, const 
     spos[num_hap] = pos;                           // final separator
     memcpy(hb + c->off_tasks, tasks.data(), sz_tasks);
     memcpy(hb + c->off_regions, rdesc.data(), sz_regions);
+    memcpy(hb + c->off_groups, plan.groups.data(), sz_groups);
+    c->num_groups = (uint32_t)plan.groups.size();
 
     // ---- device buffers -------------------------------------------------------------------------------------
     const size_t stream_bytes = kStreamFrontPad + (size_t)pos + 1 + kStreamTailPad;
     PMM_CUDA(c, c->d_stream.reserve(stream_bytes));
+    PMM_CUDA(c, c->d_params.reserve(sizeof(float) * plan.param_floats));
     PMM_CUDA(c, c->d_iyf.reserve(sizeof(float) * num_hap));
     PMM_CUDA(c, c->d_iyd.reserve(sizeof(double) * num_hap));
     PMM_CUDA(c, c->d_raw.reserve(sizeof(float) * pairs));
@@ -352,7 +360,7 @@ void pmm_destroy(pmm_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (DevBuf* b : {&c->tables, &c->d_in, &c->d_stream, &c->d_iyf, &c->d_iyd, &c->d_raw, &c->d_fb_tasks, &c->d_fb_idx,
+    for (DevBuf* b : {&c->tables, &c->d_in, &c->d_params, &c->d_stream, &c->d_iyf, &c->d_iyd, &c->d_raw, &c->d_fb_tasks, &c->d_fb_idx,
                       &c->d_tiny_tasks, &c->d_dres, &c->d_ctrl, &c->d_scratch, &c->d_probe}) b->release();
     c->h_in.release(); c->h_out.release();
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
@@ -377,6 +385,13 @@ int pmm_set_option(pmm_ctx* c, const char* key, const char* value)
         const int v = atoi(value);
         if (v < 1 || v > 64) return c->fail(PMM_ERR_INVALID, "tasks_per_warp out of range");
         c->tasks_per_warp = v;
+        return PMM_OK;
+    }
+    if (k == "force_variant") {
+        int K = 0, W = 0;
+        if (sscanf(value, "%d,%d", &K, &W) != 2 || (K && !forward_f32_has_variant(K, W)))
+            return c->fail(PMM_ERR_INVALID, "force_variant wants \"K,W\" of an instantiated float kernel, or \"0,0\"");
+        c->force = Variant{K, W, false};
         return PMM_OK;
     }
     return c->fail(PMM_ERR_INVALID, "unknown option " + k);
@@ -414,6 +429,12 @@ int pmm_launch(pmm_ctx* c)
     a.tab = c->dtab;
     a.scratch = c->d_scratch.p;
     a.scratch_stride = c->max_hap_len + 8;
+
+    // ---- row parameters, once per read (the reference recomputes them per pair) --------------------------------
+    a.params = static_cast<float*>(c->d_params.p);
+    PMM_CUDA(c, launch_read_params(a.read_blob, a.reads, reinterpret_cast<GroupDesc*>(db + c->off_groups), c->num_groups,
+                                   c->dtab, static_cast<float*>(c->d_params.p), s));
+    ++launches;
 
     // ---- float pass, one launch per (K, W) variant present in the job -----------------------------------------
     if (c->segs.size() > 200) return c->fail(PMM_ERR_INVALID, "too many kernel variants in one job");

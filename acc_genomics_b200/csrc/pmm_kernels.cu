@@ -28,6 +28,7 @@
 #include "pmm_kernels.cuh"
 
 #include <cfloat>
+#include <type_traits>
 
 namespace pmm {
 namespace {
@@ -77,8 +78,15 @@ __host__ __device__ constexpr int wtab_elems() { return 5 * ((K + Arith<T>::kVec
 // ---------------------------------------------------------------------------------------------------------
 // The forward kernel.
 // ---------------------------------------------------------------------------------------------------------
+// Resident CTAs per SM the register allocator must leave room for: the state of a lane is 8 registers per row
+// (5 parameters + M, X, Y), so K decides the occupancy step (64K registers / 128 threads).
+template <typename T, int K> __host__ __device__ constexpr int min_ctas()
+{
+    return sizeof(T) == 8 ? 3 : K <= 11 ? 4 : K <= 16 ? 3 : 2;
+}
+
 template <typename T, int K, int W, bool STRIPED, bool FLUSH>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) pmm_forward_kernel(const ForwardArgs a)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, min_ctas<T, K>()) pmm_forward_kernel(const ForwardArgs a)
 {
     using A = Arith<T>;
     constexpr int VEC = A::kVec;
@@ -128,39 +136,63 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) pmm_forward_kernel(const Fo
         #pragma unroll 1
         for (int stripe = 0; stripe < nstripes; ++stripe) {
             // ---- per-row parameters (avx-pairhmm-template.h:108-127, :155-158) --------------------------
-            T pMM[K], pG[K], pMX[K], pXX[K], pMY[K], pYY[K];
+            T pMM[K], pG[K], pMX[K], pMY[K], pC[K];       // pXX == pYY == ph2pr[c] (:119-121)
+            T pX0 = (T)0;                                                // pC[0] as the X update of row 0 sees it
             unsigned padmask = 0;
             __syncwarp();                                                // previous task / stripe done with wtab
-            #pragma unroll
-            for (int j = 0; j < K; ++j) {
-                const int r0 = stripe * W * K + l * K + j - pad;          // 0-based read base of this row
-                T mw = (T)0, xw = (T)0;
-                int cls = 0;
-                if (r0 >= 0 && valid) {
-                    const uint8_t* b = a.read_blob + rd.off + r0;
-                    cls = base_class(b[0]);
-                    const int q_ = b[rd.stride] & 127, i_ = b[2 * rd.stride] & 127;
-                    const int d_ = b[3 * rd.stride] & 127, c_ = b[4 * rd.stride] & 127;
-                    const int mx = max(i_, d_), mn = min(i_, d_);
-                    pMM[j] = A::m2m(a.tab, ((mx * (mx + 1)) >> 1) + mn);
-                    const T pc = A::ph2pr(a.tab, c_);
-                    pG[j] = A::sub((T)1.0, pc);
-                    pMX[j] = A::ph2pr(a.tab, i_);
-                    pXX[j] = pc;
-                    pMY[j] = A::ph2pr(a.tab, d_);
-                    pYY[j] = pc;
-                    const T dm = A::ph2pr(a.tab, q_);
-                    mw = A::sub((T)1.0, dm);
-                    xw = A::div(dm, (T)3.0);
-                } else {
-                    // boundary row: M = X = 0, Y keeps its value
-                    pMM[j] = (T)0; pG[j] = (T)0; pMX[j] = (T)0; pXX[j] = (T)0; pMY[j] = (T)0; pYY[j] = (T)1.0;
-                    padmask |= 1u << j;
-                }
+            if constexpr (std::is_same<T, float>::value) {
+                // float pass: the rows were prepared once per read by read_params_kernel; W consecutive lanes read
+                // consecutive floats, all 8K loads are independent
+                constexpr int KW = K * W;
+                const float* pb = a.params + tk->param_off + ((size_t)(STRIPED ? 0 : g) * nstripes + stripe) * (kParamPlanes * KW) + l;
                 #pragma unroll
-                for (int h = 0; h < 5; ++h) {
-                    const bool match = (cls == h) || cls == 4 || h == 4;
-                    wlane[h * CLS_STRIDE + (j / VEC) * 32 * VEC + (j % VEC)] = match ? mw : xw;
+                for (int j = 0; j < K; ++j) {
+                    const float* pj = pb + j * W;
+                    pMM[j] = __ldg(pj + 0 * KW); pG[j] = __ldg(pj + 1 * KW); pMX[j] = __ldg(pj + 2 * KW);
+                    pMY[j] = __ldg(pj + 3 * KW); pC[j] = __ldg(pj + 4 * KW);
+                    const float mw = __ldg(pj + 5 * KW), xw = __ldg(pj + 6 * KW);
+                    const unsigned cls = __float_as_uint(__ldg(pj + 7 * KW));
+                    if (cls == kPadClass) padmask |= 1u << j;
+                    if (j == 0) pX0 = cls == kPadClass ? 0.0f : pC[0];
+                    #pragma unroll
+                    for (int h = 0; h < 5; ++h) {
+                        const bool match = (cls == (unsigned)h) || cls == 4 || h == 4;
+                        wlane[h * CLS_STRIDE + (j / VEC) * 32 * VEC + (j % VEC)] = match ? mw : xw;
+                    }
+                }
+            } else {
+                #pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    const int r0 = stripe * W * K + l * K + j - pad;          // 0-based read base of this row
+                    T mw = (T)0, xw = (T)0;
+                    int cls = 0;
+                    if (r0 >= 0 && valid) {
+                        const uint8_t* b = a.read_blob + rd.off + r0;
+                        cls = base_class(b[0]);
+                        const int q_ = b[rd.stride] & 127, i_ = b[2 * rd.stride] & 127;
+                        const int d_ = b[3 * rd.stride] & 127, c_ = b[4 * rd.stride] & 127;
+                        const int mx = max(i_, d_), mn = min(i_, d_);
+                        pMM[j] = A::m2m(a.tab, ((mx * (mx + 1)) >> 1) + mn);
+                        const T pc = A::ph2pr(a.tab, c_);
+                        pG[j] = A::sub((T)1.0, pc);
+                        pMX[j] = A::ph2pr(a.tab, i_);
+                        pMY[j] = A::ph2pr(a.tab, d_);
+                        pC[j] = pc;
+                        if (j == 0) pX0 = pc;
+                        const T dm = A::ph2pr(a.tab, q_);
+                        mw = A::sub((T)1.0, dm);
+                        xw = A::div(dm, (T)3.0);
+                    } else {
+                        // boundary row: M = 0, Y keeps its value, X copies the row above; a boundary row 0 ignores the
+                        // row above (pX0 = 0: whatever the shuffle delivers, lane 0's own value included) so X stays 0
+                        pMM[j] = (T)0; pG[j] = (T)0; pMX[j] = (T)0; pMY[j] = (T)0; pC[j] = (T)1.0;
+                        padmask |= 1u << j;
+                    }
+                    #pragma unroll
+                    for (int h = 0; h < 5; ++h) {
+                        const bool match = (cls == h) || cls == 4 || h == 4;
+                        wlane[h * CLS_STRIDE + (j / VEC) * 32 * VEC + (j % VEC)] = match ? mw : xw;
+                    }
                 }
             }
             __syncwarp();
@@ -199,13 +231,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) pmm_forward_kernel(const Fo
                     const T t5 = A::add(t3, flush<FLUSH>(A::mul(yd, pG[j])));
                     Mn[j] = flush<FLUSH>(A::mul(t5, w[j]));
                     // Y = Mleft*pMY + Yleft*pYY                        (:197)
-                    Yn[j] = A::add(flush<FLUSH>(A::mul(M[j], pMY[j])), flush<FLUSH>(A::mul(Y[j], pYY[j])));
+                    Yn[j] = A::add(flush<FLUSH>(A::mul(M[j], pMY[j])), flush<FLUSH>(A::mul(Y[j], pC[j])));
                 }
                 #pragma unroll
                 for (int j = 0; j < K; ++j) {
                     const T mu = j ? Mn[j - 1] : inM, xu = j ? Xn[j - 1] : inX;
                     // X = Mup*pMX + Xup*pXX                             (:194)
-                    Xn[j] = A::add(flush<FLUSH>(A::mul(mu, pMX[j])), flush<FLUSH>(A::mul(xu, pXX[j])));
+                    Xn[j] = A::add(flush<FLUSH>(A::mul(mu, pMX[j])), flush<FLUSH>(A::mul(xu, j ? pC[j] : pX0)));
                 }
                 #pragma unroll
                 for (int j = 0; j < K; ++j) { M[j] = Mn[j]; X[j] = Xn[j]; Y[j] = Yn[j]; }
@@ -270,13 +302,69 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) pmm_forward_kernel(const Fo
                 ++hn;
                 next_sep = hn <= nhaps ? (int)(a.spos[hap_first + hn] - s0) : Tsteps + W;
                 int send = next_sep < Tsteps ? next_sep : Tsteps;
-                #pragma unroll 2
+                // four steps per trip: the element loads use one pointer with immediate offsets
+                const uint8_t* q = sp + t;
+                #pragma unroll 1
+                for (; t + 4 <= send; t += 4, q += 4) {
+                    const unsigned e1 = q[1], e2 = q[2], e3 = q[3], e4 = q[4];
+                    steady_step(t, e);
+                    steady_step(t + 1, e1);
+                    steady_step(t + 2, e2);
+                    steady_step(t + 3, e3);
+                    e = e4;
+                }
+                #pragma unroll 1
                 for (; t < send; ++t) {
                     const unsigned en = sp[t + 1];
                     steady_step(t, e);
                     e = en;
                 }
             }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Row parameters of the float pass: one CTA per read group, see GroupDesc in pmm_types.h for the layout.
+// What the reference recomputes for every pair (initializeVectors, avx-pairhmm-template.h:108-127, and the
+// 1 - distm, distm / 3 of stripeINITIALIZATION, :155-158) is done here once per read.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) read_params_kernel(const uint8_t* __restrict__ blob, const ReadDesc* __restrict__ reads,
+                                                          const GroupDesc* __restrict__ groups, uint32_t ngroups,
+                                                          DeviceTables tab, float* __restrict__ params)
+{
+    if (blockIdx.x >= ngroups) return;
+    const GroupDesc gd = groups[blockIdx.x];
+    const uint32_t K = gd.K, W = gd.W, KW = K * W, rows = gd.nstripes * KW;
+    const uint32_t slots = gd.nstripes > 1 ? 1u : 32u / W;
+    for (uint32_t slot = 0; slot < slots; ++slot) {
+        const bool valid = slot < gd.nreads;
+        ReadDesc rd = {0u, 0u, 0u};
+        if (valid) rd = reads[gd.read[slot]];
+        const int pad = (int)rows - (int)rd.len;                 // boundary rows above the read (all rows if unused)
+        float* base = params + gd.param_off + (size_t)slot * gd.nstripes * kParamPlanes * KW;
+        for (uint32_t x = threadIdx.x; x < rows; x += blockDim.x) {
+            const uint32_t s = x / KW, idx = x % KW, j = idx / W, l = idx % W;
+            const int r0 = (int)(s * KW + l * K + j) - pad;      // 0-based read base of row j of lane l
+            float v[kParamPlanes] = {0.f, 0.f, 0.f, 0.f, 1.0f, 0.f, 0.f, __uint_as_float(kPadClass)};
+            if (valid && r0 >= 0) {
+                const uint8_t* b = blob + rd.off + r0;
+                const int q_ = b[rd.stride] & 127, i_ = b[2 * rd.stride] & 127;
+                const int d_ = b[3 * rd.stride] & 127, c_ = b[4 * rd.stride] & 127;
+                const int mx = max(i_, d_), mn = min(i_, d_);
+                const float pc = __ldg(tab.ph2pr_f + c_), dm = __ldg(tab.ph2pr_f + q_);
+                v[0] = __ldg(tab.m2m_f + ((mx * (mx + 1)) >> 1) + mn);
+                v[1] = __fsub_rn(1.0f, pc);
+                v[2] = __ldg(tab.ph2pr_f + i_);
+                v[3] = __ldg(tab.ph2pr_f + d_);
+                v[4] = pc;
+                v[5] = __fsub_rn(1.0f, dm);
+                v[6] = __fdiv_rn(dm, 3.0f);
+                v[7] = __uint_as_float((unsigned)base_class(b[0]));
+            }
+            float* o = base + (size_t)s * kParamPlanes * KW + idx;
+            #pragma unroll
+            for (int p = 0; p < kParamPlanes; ++p) o[(size_t)p * KW] = v[p];
         }
     }
 }
@@ -327,7 +415,7 @@ __global__ void compact_fallback_kernel(const float* __restrict__ raw, const Reg
     t.read[0] = r.read_first + local / r.nhaps; t.read[1] = t.read[2] = t.read[3] = 0;
     t.out_base[0] = slot; t.out_base[1] = t.out_base[2] = t.out_base[3] = 0;
     t.hap_first = r.hap_first + local % r.nhaps;
-    t.nhaps = 1; t.nreads = 1; t.reserved = 0;
+    t.nhaps = 1; t.nreads = 1; t.param_off = 0;
     fb_tasks[slot] = t;
     fb_out_index[slot] = idx;
 }
@@ -434,6 +522,14 @@ cudaError_t launch_build_stream(const uint8_t* hap_blob, const HapDesc* haps, co
 {
     if (num_hap == 0) return cudaSuccess;
     build_stream_kernel<<<num_hap, 128, 0, s>>>(hap_blob, haps, spos, num_hap, stream, inity_f, inity_d, ic_f, ic_d);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_read_params(const uint8_t* read_blob, const ReadDesc* reads, const GroupDesc* groups, uint32_t ngroups,
+                               const DeviceTables& tab, float* params, cudaStream_t s)
+{
+    if (ngroups == 0) return cudaSuccess;
+    read_params_kernel<<<ngroups, 128, 0, s>>>(read_blob, reads, groups, ngroups, tab, params);
     return cudaGetLastError();
 }
 

@@ -38,6 +38,7 @@ struct DeviceTables {
 struct ForwardArgs {
     const uint8_t*  read_blob;
     const ReadDesc* reads;
+    const float*    params;        // float pass: row parameters written by read_params_kernel (GroupDesc layout)
     const uint8_t*  stream;        // points at stream[0]; kStreamFrontPad readable bytes precede it
     const uint32_t* spos;          // [num_hap + 1]; spos[num_hap] = position of the final SEP
     const void*     inity;         // float* or double* [num_hap]
@@ -65,6 +66,10 @@ int forward_f64_ctas_per_sm(bool flush);
 cudaError_t launch_build_stream(const uint8_t* hap_blob, const HapDesc* haps, const uint32_t* spos, uint32_t num_hap,
                                 uint8_t* stream, float* inity_f, double* inity_d, float ic_f, double ic_d,
                                 cudaStream_t s);
+
+// Row parameters of the float pass, one CTA per read group (layout: GroupDesc in pmm_types.h).
+cudaError_t launch_read_params(const uint8_t* read_blob, const ReadDesc* reads, const GroupDesc* groups, uint32_t ngroups,
+                               const DeviceTables& tab, float* params, cudaStream_t s);
 
 // Scan raw[] for values below 1e-28f and append one single-pair Task per hit (read, hap, slot) to fb_tasks.
 cudaError_t launch_compact_fallback(const float* raw, const RegionDesc* regions, uint32_t nregions,

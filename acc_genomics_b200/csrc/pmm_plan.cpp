@@ -19,7 +19,7 @@ Variant pick_variant(int R)
     Variant best{kStripedK, 32, true};
     double best_eff = -1.0;
     for (int W = 8; W <= 32; W *= 2)
-        for (int K = 4; K <= 16; ++K) {
+        for (int K = 4; K <= kMaxK; ++K) {
             if (!forward_f32_has_variant(K, W) || R + 1 > K * W) continue;
             double eff = 12.0 * R / (W * step_cost(K));
             if (K > 12) eff *= 0.97;
@@ -30,7 +30,7 @@ Variant pick_variant(int R)
 
 int plan_job(uint32_t num_read, const uint32_t* read_off, uint32_t num_hap, const uint32_t* hap_off,
              uint32_t num_region, const pmm_region_t* regions, int sm_count, int tasks_per_warp,
-             Plan& plan, std::string& err)
+             Plan& plan, std::string& err, const Variant* force)
 {
     plan = Plan();
     if (!num_read || !num_hap || !num_region || !read_off || !hap_off || !regions) { err = "empty job"; return PMM_ERR_INVALID; }
@@ -76,7 +76,9 @@ int plan_job(uint32_t num_read, const uint32_t* read_off, uint32_t num_hap, cons
             return read_off[x + 1] - read_off[x] > read_off[y + 1] - read_off[y]; });
         for (uint32_t k = 0; k < r.num_read;) {
             const int R = (int)(read_off[order[k] + 1] - read_off[order[k]]);
-            Group gr; gr.v = pick_variant(R); gr.region = g; gr.n = 0;
+            Group gr; gr.region = g; gr.n = 0;
+            gr.v = (force && !force->striped && forward_f32_has_variant(force->K, force->W) && R + 1 <= force->K * force->W)
+                       ? *force : pick_variant(R);
             const uint32_t G = gr.v.striped ? 1u : (uint32_t)(32 / gr.v.W);
             for (; gr.n < G && k < r.num_read; ++k) gr.reads[gr.n++] = order[k];
             for (uint32_t z = gr.n; z < (uint32_t)kMaxGroups; ++z) gr.reads[z] = 0;
@@ -99,6 +101,19 @@ int plan_job(uint32_t num_read, const uint32_t* read_off, uint32_t num_hap, cons
     for (uint32_t gi : gorder) {
         const Group& gr = groups[gi];
         const RegionDesc& r = plan.regions[gr.region];
+        // row-parameter block of the group: every slot of the warp gets one, used or not
+        GroupDesc gd{};
+        for (uint32_t z = 0; z < (uint32_t)kMaxGroups; ++z) gd.read[z] = gr.reads[z];
+        gd.nreads = gr.n; gd.K = (uint32_t)gr.v.K; gd.W = (uint32_t)gr.v.W;
+        const uint32_t kw = gd.K * gd.W;
+        gd.nstripes = gr.v.striped ? (read_off[gr.reads[0] + 1] - read_off[gr.reads[0]] + kw) / kw : 1u;
+        const uint64_t slots = gr.v.striped ? 1u : 32u / gd.W;
+        if (plan.param_floats + slots * gd.nstripes * kParamPlanes * kw >= (1ull << 32)) {
+            err = "row parameters of one job exceed 16 GiB: split it"; return PMM_ERR_INVALID;
+        }
+        gd.param_off = (uint32_t)plan.param_floats;
+        plan.param_floats += slots * gd.nstripes * kParamPlanes * kw;
+        plan.groups.push_back(gd);
         const uint32_t hpt = gr.v.striped ? 1u : std::min(plan.haps_per_task, r.nhaps);
         if (plan.segs.empty() || !(plan.segs.back().v == gr.v)) plan.segs.push_back(LaunchSeg{gr.v, (uint32_t)plan.tasks.size(), 0});
         const uint32_t nruns = (r.nhaps + hpt - 1) / hpt;          // runs of near-equal length
@@ -109,7 +124,7 @@ int plan_job(uint32_t num_read, const uint32_t* read_off, uint32_t num_hap, cons
                 t.read[z] = gr.reads[z];
                 t.out_base[z] = z < gr.n ? r.out_first + (gr.reads[z] - r.read_first) * r.nhaps + h0 : 0;
             }
-            t.hap_first = r.hap_first + h0; t.nhaps = h1 - h0; t.nreads = gr.n; t.reserved = 0;
+            t.hap_first = r.hap_first + h0; t.nhaps = h1 - h0; t.nreads = gr.n; t.param_off = gd.param_off;
             plan.tasks.push_back(t);
             plan.segs.back().task_count++;
         }

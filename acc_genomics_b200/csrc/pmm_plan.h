@@ -13,6 +13,8 @@ struct LaunchSeg { Variant v; uint32_t task_first, task_count; };
 
 struct Plan {
     std::vector<RegionDesc> regions;
+    std::vector<GroupDesc> groups;      // read groups (reads sharing a warp) and where their row parameters live
+    uint64_t param_floats = 0;          // size of the row-parameter buffer
     std::vector<Task> tasks;            // grouped by variant, see segs
     std::vector<LaunchSeg> segs;        // one kernel launch each, largest footprint first
     uint64_t pairs = 0, cells = 0;
@@ -30,6 +32,6 @@ Variant pick_variant(int R);
 // Returns PMM_OK or PMM_ERR_INVALID with a message.
 int plan_job(uint32_t num_read, const uint32_t* read_off, uint32_t num_hap, const uint32_t* hap_off,
              uint32_t num_region, const pmm_region_t* regions, int sm_count, int tasks_per_warp,
-             Plan& plan, std::string& err);
+             Plan& plan, std::string& err, const Variant* force = nullptr);   // force: tuning sweeps only
 
 }  // namespace pmm

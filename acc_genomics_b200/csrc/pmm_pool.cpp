@@ -1,0 +1,223 @@
+// pmm_pool.cpp -- host-side work queue over the GPUs of one box.
+//
+// Read x haplotype pairs are independent and nothing is reduced, so multi-GPU is a partition of whole regions with
+// no collective: the pool owns `contexts_per_device` engine contexts (pmm_ctx, each with its own stream and pinned
+// staging buffers) on every device it was given and one feeder thread per context.  Jobs go into one queue ordered
+// by cell count, largest first (the skewed length distribution of configs 4/5 leaves the small jobs to fill the
+// tail); a feeder takes the next job, stages it, launches and fetches it through the same C ABI a single-GPU caller
+// uses.  Two or three contexts per GPU keep the copy engines and the host-side packing of job i+1 busy while the
+// kernels of job i run.  This is the piece that stands where the reference has Blaze's per-accelerator task queue
+// and the FPGA processing-unit balancer (/root/reference/pairhmm/interface/PairHMMFpgaInterface.cpp:67-170).
+#include "../../include/pairhmm_cuda.h"
+
+#include <atomic>
+#include <condition_variable>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <queue>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+struct Job {
+    uint64_t ticket = 0, cells = 0;
+    // flat layout, borrowed from the caller until pmm_pool_wait returns
+    uint32_t num_read = 0, num_hap = 0, num_region = 0;
+    const uint32_t* read_off = nullptr; const uint8_t* tr[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    const uint32_t* hap_off = nullptr; const uint8_t* hap = nullptr;
+    const pmm_region_t* regions = nullptr;
+    pmm_region_t one_region{};
+    double* out = nullptr; uint64_t out_capacity = 0;
+    // completion
+    int rc = PMM_OK; std::string err; uint64_t n_fallback = 0; int device = -1; bool done = false;
+};
+
+struct JobOrder {
+    bool operator()(const Job* a, const Job* b) const
+    {
+        if (a->cells != b->cells) return a->cells < b->cells;      // priority_queue: largest on top
+        return a->ticket > b->ticket;
+    }
+};
+
+}  // namespace
+
+struct pmm_pool {
+    std::vector<pmm_ctx*> ctxs;
+    std::vector<int> ctx_device;
+    std::vector<std::thread> feeders;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::priority_queue<Job*, std::vector<Job*>, JobOrder> queue;
+    std::map<uint64_t, Job*> jobs;                 // every submitted, not yet collected job
+    uint64_t next_ticket = 1;
+    bool stopping = false;
+    std::string err;
+    std::vector<uint64_t> cells_per_device, jobs_per_device;
+    int n_devices = 0;
+    std::vector<int> devices;
+};
+
+static std::string g_pool_error;
+
+static void feeder_main(pmm_pool* p, size_t slot)
+{
+    pmm_ctx* c = p->ctxs[slot];
+    for (;;) {
+        Job* j = nullptr;
+        {
+            std::unique_lock<std::mutex> lk(p->mu);
+            p->cv_work.wait(lk, [&] { return p->stopping || !p->queue.empty(); });
+            if (p->queue.empty()) return;          // stopping and drained
+            j = p->queue.top(); p->queue.pop();
+        }
+        int rc = pmm_stage_flat(c, j->num_read, j->read_off, j->tr[0], j->tr[1], j->tr[2], j->tr[3], j->tr[4],
+                                j->num_hap, j->hap_off, j->hap, j->num_region, j->regions);
+        if (rc == PMM_OK) rc = pmm_launch(c);
+        uint64_t nfb = 0;
+        if (rc == PMM_OK) rc = pmm_fetch_log10(c, j->out, j->out_capacity, &nfb);
+        std::string err = rc == PMM_OK ? std::string() : std::string(pmm_last_error(c));
+        {
+            std::lock_guard<std::mutex> lk(p->mu);
+            j->rc = rc; j->err = err; j->n_fallback = nfb; j->device = p->ctx_device[slot]; j->done = true;
+            for (int d = 0; d < p->n_devices; ++d)
+                if (p->devices[d] == j->device) { p->cells_per_device[d] += j->cells; p->jobs_per_device[d]++; }
+        }
+        p->cv_done.notify_all();
+    }
+}
+
+extern "C" {
+
+int pmm_pool_create(const int* devices, int n_devices, int contexts_per_device, pmm_pool** out)
+{
+    if (!out) return PMM_ERR_INVALID;
+    *out = nullptr;
+    const int visible = pmm_device_count();
+    if (visible == 0) { g_pool_error = "no CUDA device visible; the pool has no CPU path"; return PMM_ERR_NO_DEVICE; }
+    if (contexts_per_device < 1 || contexts_per_device > 8) { g_pool_error = "contexts_per_device must be 1..8"; return PMM_ERR_INVALID; }
+    std::vector<int> devs;
+    if (!devices || n_devices <= 0) {
+        for (int d = 0; d < visible; ++d) devs.push_back(d);        // all GPUs of the box
+    } else {
+        for (int k = 0; k < n_devices; ++k) {
+            if (devices[k] < 0 || devices[k] >= visible) { g_pool_error = "device index out of range"; return PMM_ERR_INVALID; }
+            devs.push_back(devices[k]);
+        }
+    }
+    pmm_pool* p = new pmm_pool();
+    p->devices = devs; p->n_devices = (int)devs.size();
+    p->cells_per_device.assign(devs.size(), 0); p->jobs_per_device.assign(devs.size(), 0);
+    for (int rep = 0; rep < contexts_per_device; ++rep)
+        for (int d : devs) {
+            pmm_ctx* c = nullptr;
+            int rc = pmm_create(d, &c);
+            if (rc != PMM_OK) {
+                g_pool_error = pmm_last_error(nullptr);
+                for (pmm_ctx* x : p->ctxs) pmm_destroy(x);
+                delete p;
+                return rc;
+            }
+            p->ctxs.push_back(c); p->ctx_device.push_back(d);
+        }
+    for (size_t s = 0; s < p->ctxs.size(); ++s) p->feeders.emplace_back(feeder_main, p, s);
+    *out = p;
+    return PMM_OK;
+}
+
+void pmm_pool_destroy(pmm_pool* p)
+{
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(p->mu);
+        p->stopping = true;
+    }
+    p->cv_work.notify_all();
+    for (auto& t : p->feeders) t.join();
+    for (pmm_ctx* c : p->ctxs) pmm_destroy(c);
+    for (auto& kv : p->jobs) delete kv.second;
+    delete p;
+}
+
+const char* pmm_pool_last_error(const pmm_pool* p) { return p ? p->err.c_str() : g_pool_error.c_str(); }
+
+int pmm_pool_num_devices(const pmm_pool* p) { return p ? p->n_devices : 0; }
+
+int pmm_pool_submit_flat(pmm_pool* p, uint32_t num_read, const uint32_t* read_off,
+                         const uint8_t* bases, const uint8_t* q, const uint8_t* i, const uint8_t* d, const uint8_t* c,
+                         uint32_t num_hap, const uint32_t* hap_off, const uint8_t* hap_bases,
+                         uint32_t num_region, const pmm_region_t* regions,
+                         double* out_log10, uint64_t out_capacity, uint64_t* ticket)
+{
+    if (!p || !ticket) return PMM_ERR_INVALID;
+    if (!read_off || !hap_off || !bases || !q || !i || !d || !c || !hap_bases || !out_log10 || !num_read || !num_hap) {
+        std::lock_guard<std::mutex> lk(p->mu);
+        p->err = "null or empty input"; return PMM_ERR_INVALID;
+    }
+    Job* j = new Job();
+    j->num_read = num_read; j->num_hap = num_hap;
+    j->read_off = read_off; j->tr[0] = bases; j->tr[1] = q; j->tr[2] = i; j->tr[3] = d; j->tr[4] = c;
+    j->hap_off = hap_off; j->hap = hap_bases;
+    if (regions && num_region) { j->regions = regions; j->num_region = num_region; }
+    else { j->one_region = pmm_region_t{0, num_read, 0, num_hap}; j->regions = &j->one_region; j->num_region = 1; }
+    uint64_t pairs = 0;
+    for (uint32_t g = 0; g < j->num_region; ++g) {
+        const pmm_region_t& r = j->regions[g];
+        if ((uint64_t)r.read_first + r.num_read > num_read || (uint64_t)r.hap_first + r.num_hap > num_hap) {
+            delete j;
+            std::lock_guard<std::mutex> lk(p->mu);
+            p->err = "region out of range"; return PMM_ERR_INVALID;
+        }
+        pairs += (uint64_t)r.num_read * r.num_hap;
+        j->cells += (uint64_t)(read_off[r.read_first + r.num_read] - read_off[r.read_first]) *
+                    (uint64_t)(hap_off[r.hap_first + r.num_hap] - hap_off[r.hap_first]);
+    }
+    if (out_capacity < pairs) {
+        delete j;
+        std::lock_guard<std::mutex> lk(p->mu);
+        p->err = "output buffer too small"; return PMM_ERR_INVALID;
+    }
+    j->out = out_log10; j->out_capacity = out_capacity;
+    {
+        std::lock_guard<std::mutex> lk(p->mu);
+        if (p->stopping) { delete j; p->err = "pool is shutting down"; return PMM_ERR_STATE; }
+        j->ticket = p->next_ticket++;
+        p->jobs[j->ticket] = j;
+        p->queue.push(j);
+        *ticket = j->ticket;
+    }
+    p->cv_work.notify_one();
+    return PMM_OK;
+}
+
+int pmm_pool_wait(pmm_pool* p, uint64_t ticket, uint64_t* n_fallback, int* device)
+{
+    if (!p) return PMM_ERR_INVALID;
+    std::unique_lock<std::mutex> lk(p->mu);
+    auto it = p->jobs.find(ticket);
+    if (it == p->jobs.end()) { p->err = "unknown ticket"; return PMM_ERR_STATE; }
+    Job* j = it->second;
+    p->cv_done.wait(lk, [&] { return j->done; });
+    const int rc = j->rc;
+    if (rc != PMM_OK) p->err = j->err;
+    if (n_fallback) *n_fallback = j->n_fallback;
+    if (device) *device = j->device;
+    p->jobs.erase(it);
+    delete j;
+    return rc;
+}
+
+int pmm_pool_device_load(const pmm_pool* p, int slot, int* device, uint64_t* jobs, uint64_t* cells)
+{
+    if (!p || slot < 0 || slot >= p->n_devices) return PMM_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(const_cast<pmm_pool*>(p)->mu);
+    if (device) *device = p->devices[slot];
+    if (jobs) *jobs = p->jobs_per_device[slot];
+    if (cells) *cells = p->cells_per_device[slot];
+    return PMM_OK;
+}
+
+}  // extern "C"

@@ -7,6 +7,7 @@ namespace pmm {
 constexpr int kMaxGroups = 4;           // reads per warp: 32 / W, W >= 8
 constexpr int kWarpsPerCta = 4;
 constexpr int kF64K = 6;                // rows per lane of the double kernel (W = 32): 191-base reads in one stripe
+constexpr int kMaxK = 20;               // most rows per lane of any float variant
 constexpr int kStripedK = 8;            // rows per lane of the striped float kernel (W = 32)
 
 struct ReadDesc { uint32_t off, stride, len; };
@@ -21,13 +22,32 @@ struct Task {
     uint32_t hap_first;
     uint32_t nhaps;
     uint32_t nreads;
-    uint32_t reserved;
+    uint32_t param_off;                 // float pass: index (in floats) of the group's row parameters, see GroupDesc
 };
 static_assert(sizeof(Task) == 48, "Task layout");
 
+// Row parameters per read are computed once per job (not once per pair like the reference's initializeVectors,
+// avx-pairhmm-template.h:83-128) by read_params_kernel and stored per read group in the order the forward kernel's
+// lanes consume them.  A group is the set of up to 32/W reads that share a warp.  Slot g of the group owns
+// nstripes * kParamPlanes * K * W floats starting at param_off + g * nstripes * kParamPlanes * K * W, laid out
+// [stripe][plane][j][l]: plane p of the row that is row j of lane l -- consecutive lanes read consecutive addresses.
+// Planes: 0 pMM, 1 pGAPM, 2 pMX, 3 pMY, 4 pXX = pYY, 5 match weight 1 - e, 6 mismatch weight e / 3, 7 base class
+// as an integer (0..4, kPadClass for a boundary row above the read or an unused slot).
+constexpr int kParamPlanes = 8;
+constexpr uint32_t kPadClass = 5;
+struct GroupDesc {
+    uint32_t read[kMaxGroups];
+    uint32_t nreads;
+    uint32_t K, W, nstripes;            // nstripes > 1 only for the striped variant (one read per group)
+    uint32_t param_off;
+    uint32_t reserved[3];
+};
+static_assert(sizeof(GroupDesc) == 48, "GroupDesc layout");
+
 // (K rows per lane, W lanes per read) instantiations of the float kernel.
 #define PMM_F32_VARIANTS(X) \
-    X(4, 8) X(5, 8) X(6, 8) X(7, 8) X(8, 8) X(10, 8) X(12, 8) X(13, 8) X(14, 8) X(16, 8) \
+    X(4, 8) X(5, 8) X(6, 8) X(7, 8) X(8, 8) X(9, 8) X(10, 8) X(11, 8) X(12, 8) X(13, 8) X(14, 8) X(15, 8) X(16, 8) \
+    X(17, 8) X(18, 8) X(19, 8) X(20, 8) \
     X(4, 16) X(5, 16) X(6, 16) X(7, 16) X(8, 16) X(9, 16) X(10, 16) X(11, 16) X(12, 16) X(14, 16) X(16, 16) \
     X(4, 32) X(5, 32) X(6, 32) X(7, 32) X(8, 32) X(9, 32) X(10, 32) X(12, 32) X(14, 32) X(16, 32)
 

@@ -23,6 +23,8 @@ EXPORTS = [
     "pmm_forward_raw_serialized", "pmm_forward_log10", "pmm_forward_log10_serialized",
     "pmm_stage_flat", "pmm_stage_serialized", "pmm_fetch_fallback", "pmm_launch", "pmm_sync", "pmm_fetch_raw", "pmm_fetch_log10", "pmm_fetch_fallback_mask",
     "pmm_get_stats", "pmm_measure_fp32_peak", "pmm_plan_flat", "pmm_host_table",
+    "pmm_pool_create", "pmm_pool_destroy", "pmm_pool_last_error", "pmm_pool_num_devices", "pmm_pool_submit_flat",
+    "pmm_pool_wait", "pmm_pool_device_load",
 ]
 
 
@@ -88,8 +90,15 @@ def load_library() -> C.CDLL:
         L.pmm_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.pmm_plan_flat.argtypes = [u32, vp, u32, vp, u32, vp, C.c_int, C.c_int, vp, u64, C.POINTER(u64)]
         L.pmm_host_table.argtypes = [C.c_int, vp, u64]
+        L.pmm_pool_create.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
+        L.pmm_pool_destroy.argtypes = [vp]; L.pmm_pool_destroy.restype = None
+        L.pmm_pool_last_error.argtypes = [vp]; L.pmm_pool_last_error.restype = C.c_char_p
+        L.pmm_pool_num_devices.argtypes = [vp]
+        L.pmm_pool_submit_flat.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp, u32, vp, vp, u32, vp, vp, u64, C.POINTER(u64)]
+        L.pmm_pool_wait.argtypes = [vp, u64, C.POINTER(u64), C.POINTER(C.c_int)]
+        L.pmm_pool_device_load.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(u64), C.POINTER(u64)]
         for n in EXPORTS:
-            if n not in ("pmm_destroy", "pmm_last_error"):
+            if n not in ("pmm_destroy", "pmm_last_error", "pmm_pool_destroy", "pmm_pool_last_error"):
                 getattr(L, n).restype = C.c_int
         _lib = L
     return _lib
@@ -125,7 +134,7 @@ def host_table(which: int) -> np.ndarray:
     return out
 
 
-def plan(batches: Sequence[Batch] | Batch, sm_count: int = 148, tasks_per_warp: int = 6):
+def plan(batches: Sequence[Batch] | Batch, sm_count: int = 148, tasks_per_warp: int = 16):
     """Host-only: the warp-tasks pmm_stage_flat would build.  Returns a list of dicts.  No GPU needed."""
     if isinstance(batches, Batch):
         batches = [batches]
@@ -266,3 +275,70 @@ class PairHMMEngine:
         nfb = C.c_uint64()
         self._ck(self.lib.pmm_forward_log10(self.h, reads, b.num_read, haps, b.num_hap, out.ctypes.data, C.byref(nfb)))
         return out.reshape(b.num_read, b.num_hap), int(nfb.value)
+
+
+class PairHMMPool:
+    """The multi-GPU work queue (pmm_pool_*): regions in, log10 likelihoods out, whole regions per GPU, no collective."""
+
+    def __init__(self, devices: Sequence[int] | None = None, contexts_per_device: int = 2):
+        self.lib = load_library()
+        h = C.c_void_p()
+        if devices:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = self.lib.pmm_pool_create(C.cast(arr, C.c_void_p), len(devices), contexts_per_device, C.byref(h))
+        else:
+            rc = self.lib.pmm_pool_create(None, 0, contexts_per_device, C.byref(h))
+        if rc != PMM_OK:
+            raise PmmError(rc, self.lib.pmm_pool_last_error(None).decode())
+        self.h = h
+        self._live = {}
+
+    @property
+    def num_devices(self) -> int:
+        return self.lib.pmm_pool_num_devices(self.h)
+
+    def submit(self, batches: Sequence[Batch] | Batch, out: np.ndarray | None = None, job: dict | None = None) -> int:
+        """Queue one job (a list of regions).  Returns a ticket; the result array is returned by wait()."""
+        if job is None:
+            if isinstance(batches, Batch):
+                batches = [batches]
+            job = concat_regions(batches)
+        if out is None:
+            out = np.empty(job["pairs"], dtype=np.float64)
+        t = C.c_uint64()
+        rc = self.lib.pmm_pool_submit_flat(self.h, job["num_read"], job["read_off"].ctypes.data, job["rs"].ctypes.data,
+                                           job["q"].ctypes.data, job["i"].ctypes.data, job["d"].ctypes.data,
+                                           job["c"].ctypes.data, job["num_hap"], job["hap_off"].ctypes.data,
+                                           job["hap"].ctypes.data, job["num_region"], C.cast(job["regions"], C.c_void_p),
+                                           out.ctypes.data, out.size, C.byref(t))
+        if rc != PMM_OK:
+            raise PmmError(rc, self.lib.pmm_pool_last_error(self.h).decode())
+        self._live[t.value] = (job, out)          # the library borrows these until wait()
+        return t.value
+
+    def wait(self, ticket: int):
+        """-> (log10 likelihoods [pairs], number of fallback pairs, device index)."""
+        nfb, dev = C.c_uint64(), C.c_int()
+        rc = self.lib.pmm_pool_wait(self.h, ticket, C.byref(nfb), C.byref(dev))
+        _, out = self._live.pop(ticket)
+        if rc != PMM_OK:
+            raise PmmError(rc, self.lib.pmm_pool_last_error(self.h).decode())
+        return out, int(nfb.value), int(dev.value)
+
+    def device_load(self):
+        res = []
+        for s in range(self.num_devices):
+            d, j, c = C.c_int(), C.c_uint64(), C.c_uint64()
+            self.lib.pmm_pool_device_load(self.h, s, C.byref(d), C.byref(j), C.byref(c))
+            res.append(dict(device=d.value, jobs=j.value, cells=c.value))
+        return res
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pmm_pool_destroy(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -69,7 +69,9 @@ int  pmm_device_count(void);
 /* Options (strings, like the task's get_conf(key, value), task/xlnx/PairHMMTask.h:73-77):
  *   "stream"          = value of a cudaStream_t (decimal or 0x..) to run on, "default" for the legacy default
  *                       stream, "own" for the context's own non-blocking stream (the initial setting)
- *   "tasks_per_warp"  = target queue depth per resident warp used when cutting regions into warp-tasks        */
+ *   "tasks_per_warp"  = target queue depth per resident warp used when cutting regions into warp-tasks
+ *   "force_variant"   = "K,W": rows per lane and lanes per read of the float kernel for every read that fits
+ *                       (tuning sweeps, tools/sweep_variants.py); "0,0" gives the choice back to the planner   */
 int  pmm_set_option(pmm_ctx* ctx, const char* key, const char* value);
 
 /* ---- one-shot calls, host buffers in, host buffers out --------------------------------------------------
@@ -118,6 +120,30 @@ int  pmm_fetch_fallback(pmm_ctx* ctx, uint32_t* index, double* value, uint64_t c
 int  pmm_fetch_fallback_mask(pmm_ctx* ctx, uint8_t* mask, uint64_t capacity);
 
 int  pmm_get_stats(const pmm_ctx* ctx, pmm_stats_t* out);
+
+/* ---- multi-GPU work queue --------------------------------------------------------------------------------
+ * Independent read x haplotype regions are partitioned across the GPUs of one box by a host-side queue; nothing is
+ * reduced, so there is no collective.  The pool owns contexts_per_device contexts on each of
+ * the given devices (NULL / 0 = every visible GPU) and one feeder thread per context; jobs are taken largest first.
+ * This is what stands where the reference has Blaze's accelerator queue (client/PairHMMWorker.cpp:217-251 hands
+ * tiles to client_->start() one after another) and the per-PU balancer (interface/PairHMMFpgaInterface.cpp:67-170).
+ *   pmm_pool_submit_flat : same layout as pmm_stage_flat (regions == NULL: one region of everything); the input
+ *                          arrays and out_log10 are borrowed until pmm_pool_wait(ticket) returns.  Thread-safe.
+ *   pmm_pool_wait        : blocks until that job is done; returns the job's status, the number of pairs that took
+ *                          the double re-run and the device that ran it.  Each ticket is waited for exactly once. */
+typedef struct pmm_pool pmm_pool;
+int  pmm_pool_create(const int* devices, int n_devices, int contexts_per_device, pmm_pool** out);
+void pmm_pool_destroy(pmm_pool* pool);
+const char* pmm_pool_last_error(const pmm_pool* pool);      /* pool may be NULL: last error of pmm_pool_create */
+int  pmm_pool_num_devices(const pmm_pool* pool);
+int  pmm_pool_submit_flat(pmm_pool* pool, uint32_t num_read, const uint32_t* read_off,
+                          const uint8_t* bases, const uint8_t* q, const uint8_t* i, const uint8_t* d, const uint8_t* c,
+                          uint32_t num_hap, const uint32_t* hap_off, const uint8_t* hap_bases,
+                          uint32_t num_region, const pmm_region_t* regions,
+                          double* out_log10, uint64_t out_capacity, uint64_t* ticket);
+int  pmm_pool_wait(pmm_pool* pool, uint64_t ticket, uint64_t* n_fallback, int* device);
+/* Jobs and cells completed so far by the slot-th device of the pool (0 <= slot < pmm_pool_num_devices). */
+int  pmm_pool_device_load(const pmm_pool* pool, int slot, int* device, uint64_t* jobs, uint64_t* cells);
 
 /* ---- host-only entry points (no GPU needed) -------------------------------------------------------------
  * pmm_plan_flat: how pmm_stage_flat would cut a job into warp-tasks on a GPU with sm_count SMs.  This is the

@@ -45,7 +45,7 @@ def test_variant_choice(built):
         b = synth.region(np.random.Generator(np.random.PCG64(1)), [length] * 8, [length + 50] * 2)
         t = engine.plan(b)[0]
         return t["K"], t["W"], t["striped"]
-    assert variant(151) == (10, 16, False)       # 2 reads per warp, 152 of 160 rows used
+    assert variant(151) == (19, 8, False)        # 4 reads per warp, 151 + 1 boundary row = all 152 rows used
     k, w, s = variant(250)
     assert not s and 251 <= k * w <= 256
     k, w, s = variant(101)
