@@ -320,7 +320,7 @@ class PairHMMPool:
         """-> (log10 likelihoods [pairs], number of fallback pairs, device index)."""
         nfb, dev = C.c_uint64(), C.c_int()
         rc = self.lib.pmm_pool_wait(self.h, ticket, C.byref(nfb), C.byref(dev))
-        _, out = self._live.pop(ticket)
+        _, out = self._live.pop(ticket, (None, None))
         if rc != PMM_OK:
             raise PmmError(rc, self.lib.pmm_pool_last_error(self.h).decode())
         return out, int(nfb.value), int(dev.value)

@@ -1,0 +1,53 @@
+// PairHMMWorker.h -- one batch of reads x haplotypes through a PairHMMClient, returning the final log10
+// likelihoods.  Same class and method names as the reference (/root/reference/pairhmm/client/PairHMMWorker.h:9-49):
+// construct per batch, run(), getOutput(double*).
+//
+// What changed against the reference's worker (client/PairHMMWorker.cpp):
+//   * there is no CPU routing: the reference keeps small batches (< 32 reads, < 2 haplotypes or < 5e6 cells,
+//     :57-66) and everything beyond the FPGA's length limits (:70-93) on the host's AVX code and runs it on a side
+//     thread (:214); the GPU has no limits and this build has no CPU compute path at all;
+//   * a batch is only tiled when it would exceed the engine's 2 GiB / 2^31-pair job limit, not at 2048 x 128;
+//   * the double-precision re-run of underflowed pairs already happened on the GPU; getOutput() takes those values
+//     from the task's fallback list instead of calling compute_fp_avxd (:176-184) and applies the same two log10
+//     formulas with the host libm.
+#ifndef PAIRHMMWORKER_H
+#define PAIRHMMWORKER_H
+
+#include <cstdint>
+#include <unordered_map>
+#include <vector>
+
+#include "PairHMMClient.h"
+
+class PairHMMWorker {
+ public:
+  PairHMMWorker(PairHMMClient* client,
+      int num_read, int num_hap,
+      read_t* reads, hap_t* haps);
+
+  ~PairHMMWorker();
+
+  // perform all computation
+  void run();
+
+  // NOTE: output must hold num_read * num_hap doubles, read-major
+  void getOutput(double* output);
+
+  // the reference's CPU fallback entry; throws in this build
+  void compute();
+
+  int numRecalculated() const { return (int)fallback_.size(); }
+
+ private:
+  PairHMMClient* client_;
+  int num_read_;
+  int num_hap_;
+  read_t* host_reads_;
+  hap_t*  host_haps_;
+  bool ran_;
+
+  std::vector<float> output_;                       // raw float likelihoods, read-major
+  std::unordered_map<uint64_t, double> fallback_;   // index in output_ -> double likelihood (scaled by 2^1020)
+};
+
+#endif

@@ -1,0 +1,89 @@
+// PairHMMTask.cpp -- see PairHMMTask.h.
+#include "PairHMMTask.h"
+
+#include <cstring>
+#include <stdexcept>
+
+PairHMMEngine::PairHMMEngine(int device) : ctx(nullptr) {
+  const int rc = pmm_create(device, &ctx);
+  if (rc != PMM_OK)
+    throw std::runtime_error(std::string("PairHMM CUDA engine unavailable: ") + pmm_last_error(nullptr));
+}
+
+PairHMMEngine::~PairHMMEngine() { pmm_destroy(ctx); }
+
+PairHMM::PairHMM() : blaze::Task(3), env(nullptr), num_cell(0), num_read(0), num_hap(0) {}
+
+PairHMM::~PairHMM() {
+  if (env) {
+    // hand the engine and the output block back for the next task on this device
+    env->putScratch("engine", engine_);
+    env->putScratch("output", output_);
+  }
+}
+
+bool PairHMM::conf_flag(const std::string& key, bool dflt) {
+  std::string v;
+  if (!get_conf(key, v)) return dflt;
+  return !(v == "0" || v == "false" || v == "no" || v == "off");
+}
+
+void PairHMM::check(int rc, const char* what) {
+  if (rc == PMM_OK) return;
+  const std::string msg = std::string(what) + ": " + pmm_last_error(engine_ ? engine_->ctx : nullptr);
+  if (rc == PMM_ERR_INVALID) throw blaze::invalidParam(msg);
+  throw std::runtime_error(msg);
+}
+
+void PairHMM::prepare() {
+  env = dynamic_cast<blaze::CudaEnv*>(getEnv());
+  if (!env) throw blaze::invalidParam("PairHMM task needs a CudaEnv");
+
+  num_cell = *static_cast<uint64_t*>(getInput(0));
+
+  if (!env->getScratch("engine", engine_)) engine_.reset(new PairHMMEngine(env->getDevice()));
+
+  std::string v;
+  if (get_conf("tasks_per_warp", v)) check(pmm_set_option(engine_->ctx, "tasks_per_warp", v.c_str()), "tasks_per_warp");
+
+  // parse the two wire-format blocks, pack into pinned memory, copy to the GPU, build the haplotype stream
+  check(pmm_stage_serialized(engine_->ctx, getInput(1), getInputLength(1), getInput(2), getInputLength(2),
+                             &num_read, &num_hap), "stage");
+
+  const uint64_t pairs = (uint64_t)num_read * (uint64_t)num_hap;
+  if (!env->getScratch("output", output_) || output_->getSize() < pairs * sizeof(float)) {
+    // grow-only; a recycled block may be larger than this batch needs, exactly like the reference's fixed
+    // 2048 x 128 block (task/xlnx/PairHMMTask.cpp:69-76)
+    const uint64_t cap = pairs + pairs / 4 + 1024;
+    output_ = env->create_block(1, (int)std::min<uint64_t>(cap, 0x7fffffff), cap * sizeof(float), 4096, blaze::DataBlock::OWNED);
+  }
+  setOutput(0, output_);
+}
+
+void PairHMM::compute() {
+  if (!engine_) throw std::runtime_error("PairHMM::compute() before prepare()");
+  const uint64_t pairs = (uint64_t)num_read * (uint64_t)num_hap;
+
+  check(pmm_launch(engine_->ctx), "launch");
+  check(pmm_fetch_raw(engine_->ctx, reinterpret_cast<float*>(output_->getData()), output_->getSize() / sizeof(float)), "fetch");
+
+  if (conf_flag("emit_fallback", true)) {
+    uint64_t n = 0;
+    check(pmm_fetch_fallback(engine_->ctx, nullptr, nullptr, 0, &n), "fallback count");
+    const size_t idx_bytes = (n * sizeof(uint32_t) + 7) / 8 * 8;
+    const size_t bytes = sizeof(uint64_t) + idx_bytes + n * sizeof(double);
+    blaze::DataBlock_ptr fb = env->create_block(1, (int)std::min<size_t>(bytes, 0x7fffffff), bytes, 8, blaze::DataBlock::OWNED);
+    char* p = fb->getData();
+    memcpy(p, &n, sizeof n);
+    if (n) {
+      check(pmm_fetch_fallback(engine_->ctx, reinterpret_cast<uint32_t*>(p + sizeof(uint64_t)),
+                               reinterpret_cast<double*>(p + sizeof(uint64_t) + idx_bytes), n, &n), "fallback list");
+    }
+    setOutput(1, fb);
+  }
+  (void)pairs;
+}
+
+extern "C" blaze::Task* create() { return new PairHMM(); }
+
+extern "C" void destroy(blaze::Task* p) { delete p; }

@@ -1,0 +1,44 @@
+"""The multi-GPU work queue (pmm_pool_*): many regions in flight over every visible GPU, results identical to the
+single-context path and to the oracle.  Runs on one GPU too (the feeders then share it)."""
+import numpy as np
+import pytest
+
+from acc_genomics_b200 import synth
+from conftest import assert_bits_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def test_pool_matches_oracle_and_spreads_jobs(built, checker):
+    from acc_genomics_b200.engine import PairHMMPool
+    pool = PairHMMPool(contexts_per_device=2)
+    regions = synth.config(5, scale=0.008, seed=11)                     # 20 ragged regions
+    jobs = [regions[k:k + 2] for k in range(0, len(regions), 2)]        # 10 jobs of 2 regions
+    tickets = [pool.submit(j) for j in jobs]
+    for j, t in zip(jobs, tickets):
+        out, nfb, dev = pool.wait(t)
+        want = np.concatenate([checker.batch(b, threads=8)[1].ravel() for b in j])
+        assert_bits_equal(out, want, "pool job")
+        assert 0 <= dev
+    load = pool.device_load()
+    assert sum(d["jobs"] for d in load) == len(jobs)
+    assert sum(d["cells"] for d in load) == sum(b.num_cells for b in regions)
+    if pool.num_devices > 1:
+        assert all(d["jobs"] > 0 for d in load), load
+    pool.close()
+
+
+def test_pool_rejects_bad_jobs(built):
+    from acc_genomics_b200.engine import PairHMMPool, PmmError
+    pool = PairHMMPool(devices=[0], contexts_per_device=1)
+    b = synth.config(1, scale=0.1)[0]
+    with pytest.raises(PmmError):
+        pool.submit(b, out=np.empty(3, dtype=np.float64))                # output too small
+    with pytest.raises(PmmError):
+        pool.wait(12345)                                                 # unknown ticket
+    t = pool.submit(b)
+    out, _, _ = pool.wait(t)
+    assert np.isfinite(out).all()
+    pool.close()
+    with pytest.raises(PmmError):
+        PairHMMPool(devices=[99])
