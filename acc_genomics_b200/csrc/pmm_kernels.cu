@@ -33,6 +33,11 @@
 namespace pmm {
 namespace {
 
+#ifndef PMM_STEADY_UNROLL
+#define PMM_STEADY_UNROLL 4
+#endif
+constexpr int kSteadyUnroll = PMM_STEADY_UNROLL;     // steps per trip of the branch-free loop
+
 __device__ __forceinline__ int base_class(unsigned ch)
 {
     // A,C,T,G,N -> 0..4, everything else 0 (ConvertChar's zero-initialised table, host_type.h:123-143)
@@ -302,16 +307,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, min_ctas<T, K>()) pmm_forwa
                 ++hn;
                 next_sep = hn <= nhaps ? (int)(a.spos[hap_first + hn] - s0) : Tsteps + W;
                 int send = next_sep < Tsteps ? next_sep : Tsteps;
-                // four steps per trip: the element loads use one pointer with immediate offsets
+                // kSteadyUnroll steps per trip: the element loads use one pointer with immediate offsets
                 const uint8_t* q = sp + t;
                 #pragma unroll 1
-                for (; t + 4 <= send; t += 4, q += 4) {
-                    const unsigned e1 = q[1], e2 = q[2], e3 = q[3], e4 = q[4];
+                for (; t + kSteadyUnroll <= send; t += kSteadyUnroll, q += kSteadyUnroll) {
+                    unsigned en[kSteadyUnroll];
+                    #pragma unroll
+                    for (int u = 0; u < kSteadyUnroll; ++u) en[u] = q[u + 1];
                     steady_step(t, e);
-                    steady_step(t + 1, e1);
-                    steady_step(t + 2, e2);
-                    steady_step(t + 3, e3);
-                    e = e4;
+                    #pragma unroll
+                    for (int u = 1; u < kSteadyUnroll; ++u) steady_step(t + u, en[u - 1]);
+                    e = en[kSteadyUnroll - 1];
                 }
                 #pragma unroll 1
                 for (; t < send; ++t) {

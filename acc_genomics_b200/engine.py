@@ -14,7 +14,7 @@ import numpy as np
 from .batch import Batch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpairhmm_b200.so")
+LIB_PATH = os.environ.get("PAIRHMM_B200_LIB") or os.path.join(_HERE, "libpairhmm_b200.so")   # override: tuning builds only
 
 PMM_OK, PMM_ERR_INVALID, PMM_ERR_CUDA, PMM_ERR_NO_DEVICE, PMM_ERR_STATE = 0, 1, 2, 3, 4
 

@@ -13,8 +13,10 @@ used only for the barrier and for the max over ranks of the device time.
 Numbers in the JSON line
   value        whole-job GCUPS (cells = sum(read_len) * sum(hap_len), /root/reference/pairhmm/host/main.cpp:305-313)
                with inputs resident in HBM, device time from CUDA events, L2 flushed between steps
-  e2e          the same metric through the public C ABI with HOST buffers: pmm_stage_flat (pack into pinned memory,
-               H2D, haplotype stream) + pmm_launch + pmm_fetch_log10 (D2H, host log10) per step, wall clock
+  e2e          the same metric through the public C ABI with HOST buffers, wall clock: every step packs its inputs into
+               pinned memory, copies them to the GPU, builds the haplotype stream, runs the kernels, copies the results
+               back and takes log10 on the host.  `value` runs the steps through the work queue (pmm_pool_*, three
+               contexts on the GPU, so neighbouring steps overlap); `serial_value` runs them one at a time on one context
   roofline     the float forward kernel against the measured FP32 instruction-issue rate of this GPU
                (12 FP32 instructions per cell: 8 FMUL + 4 FADD)
   cpu_baseline the reference's own AVX implementation (oracle/_ref, built from /root/reference with pinned flags) on
@@ -236,6 +238,7 @@ def main():
     assert np.isfinite(raw).all() and not np.isnan(out).any()
 
     # ---- end to end through the C ABI with host buffers -----------------------------------------------------------
+    # (a) one job at a time on one context: stage (pack, H2D) -> launch -> fetch (D2H, host log10), nothing overlapped
     res = np.empty(st["pairs"], dtype=np.float64)
     for _ in range(3):
         eng.restage(); eng.launch(); eng.fetch_log10(res)
@@ -244,15 +247,40 @@ def main():
     for _ in range(args.steps):
         eng.restage(); eng.launch(); eng.fetch_log10(res)
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    e2e_serial_s = time.perf_counter() - t0
     st2 = eng.stats()
+    # (b) the same steps through the work queue a host application uses (pmm_pool_*): every step still packs its
+    # inputs from host memory, copies them to the GPU, runs, copies the results back and takes log10 on the host, but
+    # three contexts keep the copies and the host work of neighbouring steps under the kernels
+    from acc_genomics_b200.engine import PairHMMPool
+    from collections import deque
+    depth = 3
+    pool = PairHMMPool(devices=[local], contexts_per_device=depth)
+    outs = [np.empty(st["pairs"], dtype=np.float64) for _ in range(depth + 1)]
+
+    def run_pool(n):
+        live = deque()
+        for k in range(n):
+            if len(live) > depth:
+                pool.wait(live.popleft())
+            live.append(pool.submit(None, out=outs[k % (depth + 1)], job=eng._job))
+        while live:
+            pool.wait(live.popleft())
+    run_pool(2 * depth)
+    barrier()
+    t0 = time.perf_counter()
+    run_pool(args.steps)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    assert np.array_equal(outs[0].view(np.uint64), out.view(np.uint64)), "pool result differs from the single-context result"
+    pool.close()
     log("e2e done")
 
     # ---- FP32 issue peak, measured on this GPU ----------------------------------------------------------------------
     peak_lane_instr, _ = eng.measure_fp32_peak()
 
     # ---- max over ranks -----------------------------------------------------------------------------------------------
-    times = torch.tensor([dev_s, e2e_s], dtype=torch.float64, device="cuda")
+    times = torch.tensor([dev_s, e2e_s, e2e_serial_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         total_cells = torch.tensor([float(cells)], dtype=torch.float64, device="cuda")
@@ -260,7 +288,7 @@ def main():
         job_cells = float(total_cells.item())
     else:
         job_cells = float(cells)
-    dev_s, e2e_s = float(times[0].item()), float(times[1].item())
+    dev_s, e2e_s, e2e_serial_s = float(times[0].item()), float(times[1].item()), float(times[2].item())
 
     if rank == 0:
         value = job_cells * args.steps / dev_s * 1e-9
@@ -279,7 +307,11 @@ def main():
                        "parallelism": f"{world} x independent region batches, no collective"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(st2["h2d_bytes"]), "d2h_bytes_per_step": int(st2["d2h_bytes"]),
                     "ms_per_step": e2e_s / args.steps * 1e3,
-                    "path": "pmm_stage_flat + pmm_launch + pmm_fetch_log10, host numpy buffers in, float64 log10 out"},
+                    "path": "pmm_pool_submit_flat / pmm_pool_wait, 3 contexts on the GPU: per step pack + H2D + kernels + D2H + "
+                            "host log10, host numpy buffers in, float64 log10 out, steps overlapped by the queue",
+                    "serial_value": job_cells * args.steps / e2e_serial_s * 1e-9,
+                    "serial_ms_per_step": e2e_serial_s / args.steps * 1e3,
+                    "serial_path": "pmm_stage_flat + pmm_launch + pmm_fetch_log10 on one context, nothing overlapped"},
             "gpu_launches": int(st["kernel_launches"]) * args.steps,
             "clocks": clocks,
             "roofline": {"bound": "fp32_issue", "kernel": "pmm_forward_kernel<float,K,W> (float pass)", "achieved": achieved, "peak": peak,
