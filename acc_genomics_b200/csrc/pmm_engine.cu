@@ -27,6 +27,7 @@ namespace {
 std::string g_create_error;
 
 constexpr size_t kAlign = 256;
+constexpr uint32_t kCtrlCursors = 64, kCtrlWords = 64 + 32 * 104;
 inline size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
 
 struct DevBuf {
@@ -70,6 +71,7 @@ struct pmm_ctx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string err;
     int tasks_per_warp = 16;
+    int f64_rows = kF64K;               // rows per lane of the double kernel for the staged job (pick_f64_rows)
     Variant force{0, 0, false};         // "force_variant" option (tuning sweeps): K,W of the float kernel
 
     // device-resident tables
@@ -154,6 +156,7 @@ int stage_common(pmm_ctx* c, uint32_t num_read, const uint32_t* read_off, const 
     const std::vector<Task>& tasks = plan.tasks;
     const std::vector<RegionDesc>& rdesc = plan.regions;
     c->max_hap_len = max_hap;
+    c->f64_rows = pick_f64_rows(plan.max_read_len);
     c->segs = plan.segs;
 
     // ---- pack the input arena ---------------------------------------------------------------------------------
@@ -206,12 +209,13 @@ int stage_common(pmm_ctx* c, uint32_t num_read, const uint32_t* read_off, const 
     PMM_CUDA(c, c->d_tiny_tasks.reserve(sizeof(Task) * pairs));
     PMM_CUDA(c, c->d_fb_idx.reserve(sizeof(uint32_t) * pairs));
     PMM_CUDA(c, c->d_dres.reserve(sizeof(double) * pairs));
-    PMM_CUDA(c, c->d_ctrl.reserve(sizeof(uint32_t) * 256));
+    PMM_CUDA(c, c->d_ctrl.reserve(sizeof(uint32_t) * kCtrlWords));
     PMM_CUDA(c, c->h_out.reserve(256 + align_up(sizeof(float) * pairs) + align_up(sizeof(uint32_t) * pairs) + sizeof(double) * pairs + 256));
     // carry rows of the striped kernels: one haplotype (+2 separators) per warp, three rows of doubles
     {
-        const int ctas64 = std::max(forward_f64_ctas_per_sm(false), forward_f64_ctas_per_sm(true));
-        const int ctas32 = forward_f32_ctas_per_sm(8, 32, true);
+        const int ctas64 = std::max(std::max(forward_f64_ctas_per_sm(5, false), forward_f64_ctas_per_sm(5, true)),
+                                    std::max(forward_f64_ctas_per_sm(6, false), forward_f64_ctas_per_sm(6, true)));
+        const int ctas32 = forward_f32_ctas_per_sm(kStripedK, 32, true);
         const size_t warps = (size_t)c->sm_count * std::max(ctas64, ctas32) * kWarpsPerCta;
         PMM_CUDA(c, c->d_scratch.reserve(warps * 3 * (size_t)(max_hap + 8) * sizeof(double)));
     }
@@ -416,10 +420,12 @@ int pmm_launch(pmm_ctx* c)
     cudaSetDevice(c->device);
     cudaStream_t s = c->stream;
     char* db = static_cast<char*>(c->d_in.p);
-    uint32_t* ctrl = static_cast<uint32_t*>(c->d_ctrl.p);       // [0] fallback count, [1] flush count, [2..] queue cursors
+    // control words, hot ones on their own 128-byte lines: [0] fallback count, [1] flush count,
+    // [kCtrlCursors + 32 k] work-queue cursor of launch k
+    uint32_t* ctrl = static_cast<uint32_t*>(c->d_ctrl.p);
     uint32_t launches = 0;
     PMM_CUDA(c, cudaEventRecord(c->ev[0], s));
-    PMM_CUDA(c, cudaMemsetAsync(ctrl, 0, sizeof(uint32_t) * 256, s));
+    PMM_CUDA(c, cudaMemsetAsync(ctrl, 0, sizeof(uint32_t) * kCtrlWords, s));
 
     ForwardArgs a{};
     a.read_blob = reinterpret_cast<uint8_t*>(db + c->off_rblob);
@@ -436,32 +442,30 @@ int pmm_launch(pmm_ctx* c)
                                    c->dtab, static_cast<float*>(c->d_params.p), s));
     ++launches;
 
-    // ---- float pass, one launch per (K, W) variant present in the job -----------------------------------------
-    if (c->segs.size() > 200) return c->fail(PMM_ERR_INVALID, "too many kernel variants in one job");
-    uint32_t cursor = 2;
+    // ---- float pass, one launch per (K, W) variant present in the job; results below 1e-28f are appended to the
+    //      fallback list by the kernel itself (PairHMMWorker.cpp:176) ----------------------------------------------
+    if (c->segs.size() > 100) return c->fail(PMM_ERR_INVALID, "too many kernel variants in one job");
+    const FallbackQueue fq{static_cast<Task*>(c->d_fb_tasks.p), static_cast<uint32_t*>(c->d_fb_idx.p), ctrl + 0, (uint32_t)c->pairs};
+    uint32_t cursor = kCtrlCursors;
     for (const LaunchSeg& seg : c->segs) {
         a.inity = c->d_iyf.p;
         a.tasks = reinterpret_cast<Task*>(db + c->off_tasks) + seg.task_first;
         a.ntasks = seg.task_count; a.ntasks_dev = nullptr;
-        a.counter = ctrl + cursor++;
+        a.counter = ctrl + cursor; cursor += 32;
         a.out = c->d_raw.p;
         const int per_sm = forward_f32_ctas_per_sm(seg.v.K, seg.v.W, seg.v.striped);
         if (per_sm <= 0) return c->fail(PMM_ERR_INVALID, "kernel variant unavailable");
         const int ctas = (int)std::min<uint64_t>((seg.task_count + kWarpsPerCta - 1) / kWarpsPerCta, (uint64_t)c->sm_count * per_sm);
-        PMM_CUDA(c, launch_forward_f32(seg.v.K, seg.v.W, seg.v.striped, a, ctas, s));
+        PMM_CUDA(c, launch_forward_f32(seg.v.K, seg.v.W, seg.v.striped, a, fq, ctas, s));
         ++launches;
     }
     PMM_CUDA(c, cudaEventRecord(c->ev[1], s));
 
-    // ---- fallback: compaction, double re-run, flush-to-zero re-run of the tiny ones ---------------------------
-    PMM_CUDA(c, launch_compact_fallback(static_cast<float*>(c->d_raw.p), reinterpret_cast<RegionDesc*>(db + c->off_regions),
-                                        c->num_region, (uint32_t)c->pairs, static_cast<Task*>(c->d_fb_tasks.p),
-                                        static_cast<uint32_t*>(c->d_fb_idx.p), ctrl + 0, (uint32_t)c->pairs, s));
-    ++launches;
-    a.inity = c->d_iyd.p;
-    a.out = c->d_dres.p;
-    a.tasks = static_cast<Task*>(c->d_fb_tasks.p); a.ntasks = 0; a.ntasks_dev = ctrl + 0; a.counter = ctrl + cursor++;
-    PMM_CUDA(c, launch_forward_f64(false, a, c->sm_count * std::max(1, forward_f64_ctas_per_sm(false)), s));
+    // ---- double re-run of the fallback list (count read from device memory) -----------------------------------------
+    a.inity = c->d_iyd.p; a.out = c->d_dres.p; a.tasks = static_cast<Task*>(c->d_fb_tasks.p);
+    a.ntasks = 0; a.ntasks_dev = ctrl + 0; a.counter = ctrl + cursor; cursor += 32;
+    const int KD = c->f64_rows;
+    PMM_CUDA(c, launch_forward_f64(KD, false, a, c->sm_count * std::max(1, forward_f64_ctas_per_sm(KD, false)), s));
     ++launches;
     // Intermediate products below DBL_MIN are flushed to zero on the reference's x86 (FTZ on); they can only
     // influence results that are themselves tiny.  Everything below 2^-800 (scaled by 2^1020) is recomputed with
@@ -469,8 +473,8 @@ int pmm_launch(pmm_ctx* c)
     PMM_CUDA(c, launch_compact_tiny(static_cast<double*>(c->d_dres.p), static_cast<Task*>(c->d_fb_tasks.p), ctrl + 0,
                                     ldexp(1.0, -800), static_cast<Task*>(c->d_tiny_tasks.p), ctrl + 1, s));
     ++launches;
-    a.tasks = static_cast<Task*>(c->d_tiny_tasks.p); a.ntasks_dev = ctrl + 1; a.counter = ctrl + cursor++;
-    PMM_CUDA(c, launch_forward_f64(true, a, c->sm_count * std::max(1, forward_f64_ctas_per_sm(true)), s));
+    a.tasks = static_cast<Task*>(c->d_tiny_tasks.p); a.ntasks_dev = ctrl + 1; a.counter = ctrl + cursor;
+    PMM_CUDA(c, launch_forward_f64(KD, true, a, c->sm_count * std::max(1, forward_f64_ctas_per_sm(KD, true)), s));
     ++launches;
     PMM_CUDA(c, cudaEventRecord(c->ev[2], s));
     c->stats.kernel_launches = launches;

@@ -90,8 +90,28 @@ template <typename T, int K> __host__ __device__ constexpr int min_ctas()
     return sizeof(T) == 8 ? 3 : K <= 11 ? 4 : K <= 16 ? 3 : 2;
 }
 
-template <typename T, int K, int W, bool STRIPED, bool FLUSH>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, min_ctas<T, K>()) pmm_forward_kernel(const ForwardArgs a)
+// ---- fallback list: the float pass appends the pairs whose result is below 1e-28f the moment the result exists ----
+// (Tried and measured on B200, see DESIGN.md section 4.4: also *consuming* the list inside the float kernel, so that the
+// double re-run overlaps the float pass, is slower than a separate double launch -- the two loop bodies evict each
+// other from the instruction caches and the double tasks run at the float kernel's lower occupancy.)
+__device__ __forceinline__ void push_fallback(const FallbackQueue& fq, uint32_t read, uint32_t hap, uint32_t out_index)
+{
+    const uint32_t slot = atomicAdd(fq.reserve, 1u);
+    if (slot >= fq.capacity) return;              // cannot happen: capacity = pairs of the job
+    Task t;
+    t.read[0] = read; t.read[1] = t.read[2] = t.read[3] = 0;
+    t.out_base[0] = slot; t.out_base[1] = t.out_base[2] = t.out_base[3] = 0;
+    t.hap_first = hap; t.nhaps = 1; t.nreads = 1; t.param_off = 0;
+    fq.tasks[slot] = t;
+    fq.out_index[slot] = out_index;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// One warp-task: the reads of one group against a run of haplotypes.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T, int K, int W, bool STRIPED, bool FLUSH, bool PUSH>
+__device__ __forceinline__ void run_task(const ForwardArgs& a, const Task* tk, T* wtab, const int lane,
+                                         const uint32_t gwarp, const FallbackQueue& fq)
 {
     using A = Arith<T>;
     constexpr int VEC = A::kVec;
@@ -99,234 +119,243 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, min_ctas<T, K>()) pmm_forwa
     constexpr int CLS_STRIDE = KQ * 32 * VEC;         // elements between the tables of two haplotype classes
     static_assert(W == 8 || W == 16 || W == 32, "W");
     static_assert(!STRIPED || W == 32, "striped variant handles one read per warp");
-
-    extern __shared__ uint4 smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane / W, l = lane % W;
-    T* wtab = reinterpret_cast<T*>(smem_raw) + warp * wtab_elems<T, K>();
     T* wlane = wtab + lane * VEC;
-
-    const uint32_t ntasks = a.ntasks_dev ? *a.ntasks_dev : a.ntasks;
     const T* inity = static_cast<const T*>(a.inity);
     T* out = static_cast<T*>(a.out);
-    const uint32_t gwarp = blockIdx.x * kWarpsPerCta + warp;
 
+    const uint32_t hap_first = tk->hap_first, nhaps = tk->nhaps;
+    const bool valid = (uint32_t)g < tk->nreads;
+    ReadDesc rd = {0u, 0u, 0u};
+    uint32_t out_base = 0;
+    if (valid) { rd = a.reads[tk->read[g]]; out_base = tk->out_base[g]; }
+    const int R = (int)rd.len;
+    const int nstripes = STRIPED ? (R + W * K) / (W * K) : 1;       // ceil((R + 1) / (W*K))
+    const int pad = nstripes * W * K - R;                            // >= 1 boundary rows at the top
+
+    const uint32_t s0 = a.spos[hap_first];
+    const int Lc = (int)(a.spos[hap_first + nhaps] - s0) + 1;        // elements incl. the terminal separator
+    const int Tsteps = Lc + W - 1;
+    const uint8_t* sp = a.stream + s0 - l;                           // this lane's element at step t is sp[t]
+
+    T* scM = nullptr; T* scX = nullptr; T* scY = nullptr;
+    if (STRIPED) {
+        scM = static_cast<T*>(a.scratch) + (size_t)gwarp * 3 * a.scratch_stride;
+        scX = scM + a.scratch_stride; scY = scX + a.scratch_stride;
+    }
+
+    #pragma unroll 1
+    for (int stripe = 0; stripe < nstripes; ++stripe) {
+        // ---- per-row parameters (avx-pairhmm-template.h:108-127, :155-158) --------------------------
+        T pMM[K], pG[K], pMX[K], pMY[K], pC[K];       // pXX == pYY == ph2pr[c] (:119-121)
+        T pX0 = (T)0;                                                // pC[0] as the X update of row 0 sees it
+        unsigned padmask = 0;
+        __syncwarp();                                                // previous task / stripe done with wtab
+        if constexpr (std::is_same<T, float>::value) {
+            // float pass: the rows were prepared once per read by read_params_kernel; W consecutive lanes read
+            // consecutive floats, all 8K loads are independent
+            constexpr int KW = K * W;
+            const float* pb = a.params + tk->param_off + ((size_t)(STRIPED ? 0 : g) * nstripes + stripe) * (kParamPlanes * KW) + l;
+            #pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const float* pj = pb + j * W;
+                pMM[j] = __ldg(pj + 0 * KW); pG[j] = __ldg(pj + 1 * KW); pMX[j] = __ldg(pj + 2 * KW);
+                pMY[j] = __ldg(pj + 3 * KW); pC[j] = __ldg(pj + 4 * KW);
+                const float mw = __ldg(pj + 5 * KW), xw = __ldg(pj + 6 * KW);
+                const unsigned cls = __float_as_uint(__ldg(pj + 7 * KW));
+                if (cls == kPadClass) padmask |= 1u << j;
+                if (j == 0) pX0 = cls == kPadClass ? 0.0f : pC[0];
+                #pragma unroll
+                for (int h = 0; h < 5; ++h) {
+                    const bool match = (cls == (unsigned)h) || cls == 4 || h == 4;
+                    wlane[h * CLS_STRIDE + (j / VEC) * 32 * VEC + (j % VEC)] = match ? mw : xw;
+                }
+            }
+        } else {
+            #pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const int r0 = stripe * W * K + l * K + j - pad;          // 0-based read base of this row
+                T mw = (T)0, xw = (T)0;
+                int cls = 0;
+                if (r0 >= 0 && valid) {
+                    const uint8_t* b = a.read_blob + rd.off + r0;
+                    cls = base_class(b[0]);
+                    const int q_ = b[rd.stride] & 127, i_ = b[2 * rd.stride] & 127;
+                    const int d_ = b[3 * rd.stride] & 127, c_ = b[4 * rd.stride] & 127;
+                    const int mx = max(i_, d_), mn = min(i_, d_);
+                    pMM[j] = A::m2m(a.tab, ((mx * (mx + 1)) >> 1) + mn);
+                    const T pc = A::ph2pr(a.tab, c_);
+                    pG[j] = A::sub((T)1.0, pc);
+                    pMX[j] = A::ph2pr(a.tab, i_);
+                    pMY[j] = A::ph2pr(a.tab, d_);
+                    pC[j] = pc;
+                    if (j == 0) pX0 = pc;
+                    const T dm = A::ph2pr(a.tab, q_);
+                    mw = A::sub((T)1.0, dm);
+                    xw = A::div(dm, (T)3.0);
+                } else {
+                    // boundary row: M = 0, Y keeps its value, X copies the row above; a boundary row 0 ignores the
+                    // row above (pX0 = 0: whatever the shuffle delivers, lane 0's own value included) so X stays 0
+                    pMM[j] = (T)0; pG[j] = (T)0; pMX[j] = (T)0; pMY[j] = (T)0; pC[j] = (T)1.0;
+                    padmask |= 1u << j;
+                }
+                #pragma unroll
+                for (int h = 0; h < 5; ++h) {
+                    const bool match = (cls == h) || cls == 4 || h == 4;
+                    wlane[h * CLS_STRIDE + (j / VEC) * 32 * VEC + (j % VEC)] = match ? mw : xw;
+                }
+            }
+        }
+        __syncwarp();
+
+        T M[K], X[K], Y[K];
+        #pragma unroll
+        for (int j = 0; j < K; ++j) { M[j] = (T)0; X[j] = (T)0; Y[j] = (T)0; }
+        T dM = (T)0, dX = (T)0, dY = (T)0;        // last row of the lane above, previous column (diagonal)
+        T sM = (T)0, sX = (T)0;                   // running sums of the read's last row
+        int nsep = 0;
+        bool done = false;
+        const bool last_stripe = stripe == nstripes - 1;
+        const bool carry_in = STRIPED && stripe > 0 && l == 0;
+        const bool carry_out = STRIPED && !last_stripe && l == W - 1;
+
+        // One column of K cells.  inM/inX/inY: last row of the lane above at this column.
+        auto cells = [&](unsigned e, T inM, T inX, T inY) {
+            const T* wp = wlane + e * CLS_STRIDE;
+            T w[KQ * VEC];
+            #pragma unroll
+            for (int m = 0; m < KQ; ++m) {
+                if (VEC == 4) {
+                    const float4 v = *reinterpret_cast<const float4*>(wp + m * 32 * VEC);
+                    w[m * VEC + 0] = v.x; w[m * VEC + 1] = v.y; w[m * VEC + 2] = v.z; w[m * VEC + 3] = v.w;
+                } else {
+                    const double2 v = *reinterpret_cast<const double2*>(wp + m * 32 * VEC);
+                    w[m * VEC + 0] = v.x; w[m * VEC + 1] = v.y;
+                }
+            }
+            T Mn[K], Xn[K], Yn[K];
+            #pragma unroll
+            for (int j = K - 1; j >= 0; --j) {
+                const T md = j ? M[j - 1] : dM, xd = j ? X[j - 1] : dX, yd = j ? Y[j - 1] : dY;
+                // M = ((Md*pMM + Xd*pGAPM) + Yd*pGAPM) * w        (avx-pairhmm-template.h:188)
+                const T t3 = A::add(flush<FLUSH>(A::mul(md, pMM[j])), flush<FLUSH>(A::mul(xd, pG[j])));
+                const T t5 = A::add(t3, flush<FLUSH>(A::mul(yd, pG[j])));
+                Mn[j] = flush<FLUSH>(A::mul(t5, w[j]));
+                // Y = Mleft*pMY + Yleft*pYY                        (:197)
+                Yn[j] = A::add(flush<FLUSH>(A::mul(M[j], pMY[j])), flush<FLUSH>(A::mul(Y[j], pC[j])));
+            }
+            #pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const T mu = j ? Mn[j - 1] : inM, xu = j ? Xn[j - 1] : inX;
+                // X = Mup*pMX + Xup*pXX                             (:194)
+                Xn[j] = A::add(flush<FLUSH>(A::mul(mu, pMX[j])), flush<FLUSH>(A::mul(xu, j ? pC[j] : pX0)));
+            }
+            #pragma unroll
+            for (int j = 0; j < K; ++j) { M[j] = Mn[j]; X[j] = Xn[j]; Y[j] = Yn[j]; }
+            sM = A::add(sM, M[K - 1]);          // (:328,:331) two sums, left to right
+            sX = A::add(sX, X[K - 1]);
+            dM = inM; dX = inX; dY = inY;
+        };
+
+        // Step with every check: separators, fill/drain, stripe carries.
+        auto checked_step = [&](int t, unsigned e) {
+            T inM = __shfl_up_sync(0xffffffffu, M[K - 1], 1, W);
+            T inX = __shfl_up_sync(0xffffffffu, X[K - 1], 1, W);
+            T inY = __shfl_up_sync(0xffffffffu, Y[K - 1], 1, W);
+            const int p = t - l;
+            const bool active = p >= 0 && !done;
+            if (carry_in && active) { inM = ld_cg(scM + p); inX = ld_cg(scX + p); inY = ld_cg(scY + p); }
+            if (active) {
+                if (e == kSep) {
+                    if (nsep > 0 && l == W - 1 && valid && last_stripe) {
+                            const T res = A::add(sM, sX);
+                            out[out_base + nsep - 1] = res;
+                            if constexpr (PUSH) {
+                                // the reference's test, a float compare (PairHMMWorker.cpp:176); NaN -> false
+                                if (res < 1e-28f) push_fallback(fq, tk->read[g], hap_first + nsep - 1, out_base + nsep - 1);
+                            }
+                        }
+                    done = nsep == (int)nhaps;
+                    const T iy = done ? (T)0 : inity[hap_first + nsep];
+                    ++nsep;
+                    #pragma unroll
+                    for (int j = 0; j < K; ++j) { M[j] = (T)0; X[j] = (T)0; Y[j] = (padmask >> j) & 1 ? iy : (T)0; }
+                    sM = (T)0; sX = (T)0;
+                    dM = inM; dX = inX; dY = inY;
+                } else {
+                    cells(e, inM, inX, inY);
+                }
+                if (carry_out) { scM[p] = M[K - 1]; scX[p] = X[K - 1]; scY[p] = Y[K - 1]; }
+            }
+        };
+
+        // Branch-free step: every lane is inside the bases of a haplotype.
+        auto steady_step = [&](int t, unsigned e) {
+            T inM = __shfl_up_sync(0xffffffffu, M[K - 1], 1, W);
+            T inX = __shfl_up_sync(0xffffffffu, X[K - 1], 1, W);
+            T inY = __shfl_up_sync(0xffffffffu, Y[K - 1], 1, W);
+            if (STRIPED) {
+                const int p = t - l;
+                if (carry_in) { inM = ld_cg(scM + p); inX = ld_cg(scX + p); inY = ld_cg(scY + p); }
+                cells(e, inM, inX, inY);
+                if (carry_out) { scM[p] = M[K - 1]; scX[p] = X[K - 1]; scY[p] = Y[K - 1]; }
+            } else {
+                cells(e, inM, inX, inY);
+            }
+        };
+
+        int t = 0;
+        uint32_t hn = 0;                      // index (within the task) of the next separator lane 0 will meet
+        int next_sep = 0;                     // step at which lane 0 meets it
+        unsigned e = sp[0];
+        while (t < Tsteps) {
+            // checked window: lane l meets the separator at step next_sep + l
+            int wend = next_sep + W;
+            if (wend > Tsteps) wend = Tsteps;
+            for (; t < wend; ++t) {
+                const unsigned en = sp[t + 1];
+                checked_step(t, e);
+                e = en;
+            }
+            ++hn;
+            next_sep = hn <= nhaps ? (int)(a.spos[hap_first + hn] - s0) : Tsteps + W;
+            int send = next_sep < Tsteps ? next_sep : Tsteps;
+            // kSteadyUnroll steps per trip: the element loads use one pointer with immediate offsets
+            const uint8_t* q = sp + t;
+            #pragma unroll 1
+            for (; t + kSteadyUnroll <= send; t += kSteadyUnroll, q += kSteadyUnroll) {
+                unsigned en[kSteadyUnroll];
+                #pragma unroll
+                for (int u = 0; u < kSteadyUnroll; ++u) en[u] = q[u + 1];
+                steady_step(t, e);
+                #pragma unroll
+                for (int u = 1; u < kSteadyUnroll; ++u) steady_step(t + u, en[u - 1]);
+                e = en[kSteadyUnroll - 1];
+            }
+            #pragma unroll 1
+            for (; t < send; ++t) {
+                const unsigned en = sp[t + 1];
+                steady_step(t, e);
+                e = en;
+            }
+        }
+    }
+}
+
+template <typename T, int K, int W, bool STRIPED, bool FLUSH, bool PUSH>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, min_ctas<T, K>()) pmm_forward_kernel(const ForwardArgs a, const FallbackQueue fq)
+{
+    extern __shared__ uint4 smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    T* wtab = reinterpret_cast<T*>(smem_raw) + warp * wtab_elems<T, K>();
+    const uint32_t ntasks = a.ntasks_dev ? *a.ntasks_dev : a.ntasks;
+    const uint32_t gwarp = blockIdx.x * kWarpsPerCta + warp;
     for (;;) {
         uint32_t ti = 0;
         if (lane == 0) ti = atomicAdd(a.counter, 1u);
         ti = __shfl_sync(0xffffffffu, ti, 0);
         if (ti >= ntasks) break;
-
-        const Task* tk = a.tasks + ti;
-        const uint32_t hap_first = tk->hap_first, nhaps = tk->nhaps;
-        const bool valid = (uint32_t)g < tk->nreads;
-        ReadDesc rd = {0u, 0u, 0u};
-        uint32_t out_base = 0;
-        if (valid) { rd = a.reads[tk->read[g]]; out_base = tk->out_base[g]; }
-        const int R = (int)rd.len;
-        const int nstripes = STRIPED ? (R + W * K) / (W * K) : 1;       // ceil((R + 1) / (W*K))
-        const int pad = nstripes * W * K - R;                            // >= 1 boundary rows at the top
-
-        const uint32_t s0 = a.spos[hap_first];
-        const int Lc = (int)(a.spos[hap_first + nhaps] - s0) + 1;        // elements incl. the terminal separator
-        const int Tsteps = Lc + W - 1;
-        const uint8_t* sp = a.stream + s0 - l;                           // this lane's element at step t is sp[t]
-
-        T* scM = nullptr; T* scX = nullptr; T* scY = nullptr;
-        if (STRIPED) {
-            scM = static_cast<T*>(a.scratch) + (size_t)gwarp * 3 * a.scratch_stride;
-            scX = scM + a.scratch_stride; scY = scX + a.scratch_stride;
-        }
-
-        #pragma unroll 1
-        for (int stripe = 0; stripe < nstripes; ++stripe) {
-            // ---- per-row parameters (avx-pairhmm-template.h:108-127, :155-158) --------------------------
-            T pMM[K], pG[K], pMX[K], pMY[K], pC[K];       // pXX == pYY == ph2pr[c] (:119-121)
-            T pX0 = (T)0;                                                // pC[0] as the X update of row 0 sees it
-            unsigned padmask = 0;
-            __syncwarp();                                                // previous task / stripe done with wtab
-            if constexpr (std::is_same<T, float>::value) {
-                // float pass: the rows were prepared once per read by read_params_kernel; W consecutive lanes read
-                // consecutive floats, all 8K loads are independent
-                constexpr int KW = K * W;
-                const float* pb = a.params + tk->param_off + ((size_t)(STRIPED ? 0 : g) * nstripes + stripe) * (kParamPlanes * KW) + l;
-                #pragma unroll
-                for (int j = 0; j < K; ++j) {
-                    const float* pj = pb + j * W;
-                    pMM[j] = __ldg(pj + 0 * KW); pG[j] = __ldg(pj + 1 * KW); pMX[j] = __ldg(pj + 2 * KW);
-                    pMY[j] = __ldg(pj + 3 * KW); pC[j] = __ldg(pj + 4 * KW);
-                    const float mw = __ldg(pj + 5 * KW), xw = __ldg(pj + 6 * KW);
-                    const unsigned cls = __float_as_uint(__ldg(pj + 7 * KW));
-                    if (cls == kPadClass) padmask |= 1u << j;
-                    if (j == 0) pX0 = cls == kPadClass ? 0.0f : pC[0];
-                    #pragma unroll
-                    for (int h = 0; h < 5; ++h) {
-                        const bool match = (cls == (unsigned)h) || cls == 4 || h == 4;
-                        wlane[h * CLS_STRIDE + (j / VEC) * 32 * VEC + (j % VEC)] = match ? mw : xw;
-                    }
-                }
-            } else {
-                #pragma unroll
-                for (int j = 0; j < K; ++j) {
-                    const int r0 = stripe * W * K + l * K + j - pad;          // 0-based read base of this row
-                    T mw = (T)0, xw = (T)0;
-                    int cls = 0;
-                    if (r0 >= 0 && valid) {
-                        const uint8_t* b = a.read_blob + rd.off + r0;
-                        cls = base_class(b[0]);
-                        const int q_ = b[rd.stride] & 127, i_ = b[2 * rd.stride] & 127;
-                        const int d_ = b[3 * rd.stride] & 127, c_ = b[4 * rd.stride] & 127;
-                        const int mx = max(i_, d_), mn = min(i_, d_);
-                        pMM[j] = A::m2m(a.tab, ((mx * (mx + 1)) >> 1) + mn);
-                        const T pc = A::ph2pr(a.tab, c_);
-                        pG[j] = A::sub((T)1.0, pc);
-                        pMX[j] = A::ph2pr(a.tab, i_);
-                        pMY[j] = A::ph2pr(a.tab, d_);
-                        pC[j] = pc;
-                        if (j == 0) pX0 = pc;
-                        const T dm = A::ph2pr(a.tab, q_);
-                        mw = A::sub((T)1.0, dm);
-                        xw = A::div(dm, (T)3.0);
-                    } else {
-                        // boundary row: M = 0, Y keeps its value, X copies the row above; a boundary row 0 ignores the
-                        // row above (pX0 = 0: whatever the shuffle delivers, lane 0's own value included) so X stays 0
-                        pMM[j] = (T)0; pG[j] = (T)0; pMX[j] = (T)0; pMY[j] = (T)0; pC[j] = (T)1.0;
-                        padmask |= 1u << j;
-                    }
-                    #pragma unroll
-                    for (int h = 0; h < 5; ++h) {
-                        const bool match = (cls == h) || cls == 4 || h == 4;
-                        wlane[h * CLS_STRIDE + (j / VEC) * 32 * VEC + (j % VEC)] = match ? mw : xw;
-                    }
-                }
-            }
-            __syncwarp();
-
-            T M[K], X[K], Y[K];
-            #pragma unroll
-            for (int j = 0; j < K; ++j) { M[j] = (T)0; X[j] = (T)0; Y[j] = (T)0; }
-            T dM = (T)0, dX = (T)0, dY = (T)0;        // last row of the lane above, previous column (diagonal)
-            T sM = (T)0, sX = (T)0;                   // running sums of the read's last row
-            int nsep = 0;
-            bool done = false;
-            const bool last_stripe = stripe == nstripes - 1;
-            const bool carry_in = STRIPED && stripe > 0 && l == 0;
-            const bool carry_out = STRIPED && !last_stripe && l == W - 1;
-
-            // One column of K cells.  inM/inX/inY: last row of the lane above at this column.
-            auto cells = [&](unsigned e, T inM, T inX, T inY) {
-                const T* wp = wlane + e * CLS_STRIDE;
-                T w[KQ * VEC];
-                #pragma unroll
-                for (int m = 0; m < KQ; ++m) {
-                    if (VEC == 4) {
-                        const float4 v = *reinterpret_cast<const float4*>(wp + m * 32 * VEC);
-                        w[m * VEC + 0] = v.x; w[m * VEC + 1] = v.y; w[m * VEC + 2] = v.z; w[m * VEC + 3] = v.w;
-                    } else {
-                        const double2 v = *reinterpret_cast<const double2*>(wp + m * 32 * VEC);
-                        w[m * VEC + 0] = v.x; w[m * VEC + 1] = v.y;
-                    }
-                }
-                T Mn[K], Xn[K], Yn[K];
-                #pragma unroll
-                for (int j = K - 1; j >= 0; --j) {
-                    const T md = j ? M[j - 1] : dM, xd = j ? X[j - 1] : dX, yd = j ? Y[j - 1] : dY;
-                    // M = ((Md*pMM + Xd*pGAPM) + Yd*pGAPM) * w        (avx-pairhmm-template.h:188)
-                    const T t3 = A::add(flush<FLUSH>(A::mul(md, pMM[j])), flush<FLUSH>(A::mul(xd, pG[j])));
-                    const T t5 = A::add(t3, flush<FLUSH>(A::mul(yd, pG[j])));
-                    Mn[j] = flush<FLUSH>(A::mul(t5, w[j]));
-                    // Y = Mleft*pMY + Yleft*pYY                        (:197)
-                    Yn[j] = A::add(flush<FLUSH>(A::mul(M[j], pMY[j])), flush<FLUSH>(A::mul(Y[j], pC[j])));
-                }
-                #pragma unroll
-                for (int j = 0; j < K; ++j) {
-                    const T mu = j ? Mn[j - 1] : inM, xu = j ? Xn[j - 1] : inX;
-                    // X = Mup*pMX + Xup*pXX                             (:194)
-                    Xn[j] = A::add(flush<FLUSH>(A::mul(mu, pMX[j])), flush<FLUSH>(A::mul(xu, j ? pC[j] : pX0)));
-                }
-                #pragma unroll
-                for (int j = 0; j < K; ++j) { M[j] = Mn[j]; X[j] = Xn[j]; Y[j] = Yn[j]; }
-                sM = A::add(sM, M[K - 1]);          // (:328,:331) two sums, left to right
-                sX = A::add(sX, X[K - 1]);
-                dM = inM; dX = inX; dY = inY;
-            };
-
-            // Step with every check: separators, fill/drain, stripe carries.
-            auto checked_step = [&](int t, unsigned e) {
-                T inM = __shfl_up_sync(0xffffffffu, M[K - 1], 1, W);
-                T inX = __shfl_up_sync(0xffffffffu, X[K - 1], 1, W);
-                T inY = __shfl_up_sync(0xffffffffu, Y[K - 1], 1, W);
-                const int p = t - l;
-                const bool active = p >= 0 && !done;
-                if (carry_in && active) { inM = ld_cg(scM + p); inX = ld_cg(scX + p); inY = ld_cg(scY + p); }
-                if (active) {
-                    if (e == kSep) {
-                        if (nsep > 0 && l == W - 1 && valid && last_stripe) out[out_base + nsep - 1] = A::add(sM, sX);
-                        done = nsep == (int)nhaps;
-                        const T iy = done ? (T)0 : inity[hap_first + nsep];
-                        ++nsep;
-                        #pragma unroll
-                        for (int j = 0; j < K; ++j) { M[j] = (T)0; X[j] = (T)0; Y[j] = (padmask >> j) & 1 ? iy : (T)0; }
-                        sM = (T)0; sX = (T)0;
-                        dM = inM; dX = inX; dY = inY;
-                    } else {
-                        cells(e, inM, inX, inY);
-                    }
-                    if (carry_out) { scM[p] = M[K - 1]; scX[p] = X[K - 1]; scY[p] = Y[K - 1]; }
-                }
-            };
-
-            // Branch-free step: every lane is inside the bases of a haplotype.
-            auto steady_step = [&](int t, unsigned e) {
-                T inM = __shfl_up_sync(0xffffffffu, M[K - 1], 1, W);
-                T inX = __shfl_up_sync(0xffffffffu, X[K - 1], 1, W);
-                T inY = __shfl_up_sync(0xffffffffu, Y[K - 1], 1, W);
-                if (STRIPED) {
-                    const int p = t - l;
-                    if (carry_in) { inM = ld_cg(scM + p); inX = ld_cg(scX + p); inY = ld_cg(scY + p); }
-                    cells(e, inM, inX, inY);
-                    if (carry_out) { scM[p] = M[K - 1]; scX[p] = X[K - 1]; scY[p] = Y[K - 1]; }
-                } else {
-                    cells(e, inM, inX, inY);
-                }
-            };
-
-            int t = 0;
-            uint32_t hn = 0;                      // index (within the task) of the next separator lane 0 will meet
-            int next_sep = 0;                     // step at which lane 0 meets it
-            unsigned e = sp[0];
-            while (t < Tsteps) {
-                // checked window: lane l meets the separator at step next_sep + l
-                int wend = next_sep + W;
-                if (wend > Tsteps) wend = Tsteps;
-                for (; t < wend; ++t) {
-                    const unsigned en = sp[t + 1];
-                    checked_step(t, e);
-                    e = en;
-                }
-                ++hn;
-                next_sep = hn <= nhaps ? (int)(a.spos[hap_first + hn] - s0) : Tsteps + W;
-                int send = next_sep < Tsteps ? next_sep : Tsteps;
-                // kSteadyUnroll steps per trip: the element loads use one pointer with immediate offsets
-                const uint8_t* q = sp + t;
-                #pragma unroll 1
-                for (; t + kSteadyUnroll <= send; t += kSteadyUnroll, q += kSteadyUnroll) {
-                    unsigned en[kSteadyUnroll];
-                    #pragma unroll
-                    for (int u = 0; u < kSteadyUnroll; ++u) en[u] = q[u + 1];
-                    steady_step(t, e);
-                    #pragma unroll
-                    for (int u = 1; u < kSteadyUnroll; ++u) steady_step(t + u, en[u - 1]);
-                    e = en[kSteadyUnroll - 1];
-                }
-                #pragma unroll 1
-                for (; t < send; ++t) {
-                    const unsigned en = sp[t + 1];
-                    steady_step(t, e);
-                    e = en;
-                }
-            }
-        }
+        run_task<T, K, W, STRIPED, FLUSH, PUSH>(a, a.tasks + ti, wtab, lane, gwarp, fq);
     }
 }
 
@@ -464,23 +493,23 @@ __global__ void __launch_bounds__(256) fp32_probe_kernel(float* sink, int iters)
 // ---------------------------------------------------------------------------------------------------------
 // Variant table
 // ---------------------------------------------------------------------------------------------------------
-template <typename T, int K, int W, bool STRIPED, bool FLUSH>
-cudaError_t launch_variant(const ForwardArgs& a, int ctas, cudaStream_t s)
+template <typename T, int K, int W, bool STRIPED, bool FLUSH, bool PUSH>
+cudaError_t launch_variant(const ForwardArgs& a, const FallbackQueue& fq, int ctas, cudaStream_t s)
 {
     constexpr int smem = kWarpsPerCta * wtab_elems<T, K>() * (int)sizeof(T);
-    auto kern = pmm_forward_kernel<T, K, W, STRIPED, FLUSH>;
+    auto kern = pmm_forward_kernel<T, K, W, STRIPED, FLUSH, PUSH>;
     // per device, cheap: the context may live on any GPU of the box
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    kern<<<ctas, kWarpsPerCta * 32, smem, s>>>(a);
+    kern<<<ctas, kWarpsPerCta * 32, smem, s>>>(a, fq);
     return cudaGetLastError();
 }
 
-template <typename T, int K, int W, bool STRIPED, bool FLUSH>
+template <typename T, int K, int W, bool STRIPED, bool FLUSH, bool PUSH>
 int variant_ctas_per_sm()
 {
     constexpr int smem = kWarpsPerCta * wtab_elems<T, K>() * (int)sizeof(T);
-    auto kern = pmm_forward_kernel<T, K, W, STRIPED, FLUSH>;
+    auto kern = pmm_forward_kernel<T, K, W, STRIPED, FLUSH, PUSH>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     int n = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kWarpsPerCta * 32, smem) != cudaSuccess) return 0;
@@ -489,13 +518,13 @@ int variant_ctas_per_sm()
 
 }  // namespace
 
-cudaError_t launch_forward_f32(int K, int W, bool striped, const ForwardArgs& a, int ctas, cudaStream_t s)
+cudaError_t launch_forward_f32(int K, int W, bool striped, const ForwardArgs& a, const FallbackQueue& fq, int ctas, cudaStream_t s)
 {
     if (striped) {
-        if (K == kStripedK && W == 32) return launch_variant<float, kStripedK, 32, true, false>(a, ctas, s);
+        if (K == kStripedK && W == 32) return launch_variant<float, kStripedK, 32, true, false, true>(a, fq, ctas, s);
         return cudaErrorInvalidValue;
     }
-#define X(k, w) if (K == k && W == w) return launch_variant<float, k, w, false, false>(a, ctas, s);
+#define X(k, w) if (K == k && W == w) return launch_variant<float, k, w, false, false, true>(a, fq, ctas, s);
     PMM_F32_VARIANTS(X)
 #undef X
     return cudaErrorInvalidValue;
@@ -503,23 +532,38 @@ cudaError_t launch_forward_f32(int K, int W, bool striped, const ForwardArgs& a,
 
 int forward_f32_ctas_per_sm(int K, int W, bool striped)
 {
-    if (striped) return (K == kStripedK && W == 32) ? variant_ctas_per_sm<float, kStripedK, 32, true, false>() : 0;
-#define X(k, w) if (K == k && W == w) return variant_ctas_per_sm<float, k, w, false, false>();
+    if (striped) return (K == kStripedK && W == 32) ? variant_ctas_per_sm<float, kStripedK, 32, true, false, true>() : 0;
+#define X(k, w) if (K == k && W == w) return variant_ctas_per_sm<float, k, w, false, false, true>();
     PMM_F32_VARIANTS(X)
 #undef X
     return 0;
 }
 
-cudaError_t launch_forward_f64(bool flush, const ForwardArgs& a, int ctas, cudaStream_t s)
+// Double re-run: rows per lane K in {5, 6} (W = 32, multi-stripe capable); see pick_f64_rows().
+cudaError_t launch_forward_f64(int K, bool flush, const ForwardArgs& a, int ctas, cudaStream_t s)
 {
-    return flush ? launch_variant<double, kF64K, 32, true, true>(a, ctas, s)
-                 : launch_variant<double, kF64K, 32, true, false>(a, ctas, s);
+    const FallbackQueue none{};
+    if (K == 5) return flush ? launch_variant<double, 5, 32, true, true, false>(a, none, ctas, s)
+                             : launch_variant<double, 5, 32, true, false, false>(a, none, ctas, s);
+    if (K == 6) return flush ? launch_variant<double, 6, 32, true, true, false>(a, none, ctas, s)
+                             : launch_variant<double, 6, 32, true, false, false>(a, none, ctas, s);
+    return cudaErrorInvalidValue;
 }
 
-int forward_f64_ctas_per_sm(bool flush)
+int forward_f64_ctas_per_sm(int K, bool flush)
 {
-    return flush ? variant_ctas_per_sm<double, kF64K, 32, true, true>()
-                 : variant_ctas_per_sm<double, kF64K, 32, true, false>();
+    if (K == 5) return flush ? variant_ctas_per_sm<double, 5, 32, true, true, false>() : variant_ctas_per_sm<double, 5, 32, true, false, false>();
+    if (K == 6) return flush ? variant_ctas_per_sm<double, 6, 32, true, true, false>() : variant_ctas_per_sm<double, 6, 32, true, false, false>();
+    return 0;
+}
+
+// Rows per lane of the double kernel for a job whose longest read has max_read_len bases: the block (160 or 192
+// rows per stripe) that wastes the fewest rows on it.
+int pick_f64_rows(uint32_t max_read_len)
+{
+    const uint32_t rows = max_read_len + 1;
+    const uint32_t p5 = (rows + 159) / 160 * 160, p6 = (rows + 191) / 192 * 192;
+    return p5 <= p6 ? 5 : 6;
 }
 
 cudaError_t launch_build_stream(const uint8_t* hap_blob, const HapDesc* haps, const uint32_t* spos, uint32_t num_hap,

@@ -52,16 +52,26 @@ struct ForwardArgs {
     DeviceTables    tab;
 };
 
+// Fallback list: the float pass appends one single-pair task per result below 1e-28f (PairHMMWorker.cpp:176).
+struct FallbackQueue {
+    Task*     tasks;
+    uint32_t* out_index;     // position of the pair in the job's result
+    uint32_t* reserve;       // entries appended so far (== fallback count when the float pass is done)
+    uint32_t  capacity;
+};
+
 // Launch helpers implemented in pmm_kernels.cu -------------------------------------------------------------
 
 // Float pass.  (K rows per lane) x (W lanes per read); W in {8,16,32}.  Returns cudaErrorInvalidValue for an
-// uninstantiated (K, W).  `striped` selects the multi-stripe variant for reads longer than W*K - 1 bases.
-cudaError_t launch_forward_f32(int K, int W, bool striped, const ForwardArgs& a, int ctas, cudaStream_t s);
-// Double re-run (fallback list).  flush = emulate x86 flush-to-zero on every product.
-cudaError_t launch_forward_f64(bool flush, const ForwardArgs& a, int ctas, cudaStream_t s);
-// Shared memory one CTA of the given variant needs (bytes) and CTAs per SM it reaches.
+// uninstantiated (K, W).  `striped` selects the multi-stripe variant for reads longer than W*K - 1 bases.  Results
+// below 1e-28f are appended to fq as they are produced.
+cudaError_t launch_forward_f32(int K, int W, bool striped, const ForwardArgs& a, const FallbackQueue& fq, int ctas, cudaStream_t s);
+// Double re-run (fallback list), K rows per lane from pick_f64_rows().  flush = emulate x86 flush-to-zero on every product.
+cudaError_t launch_forward_f64(int K, bool flush, const ForwardArgs& a, int ctas, cudaStream_t s);
+int pick_f64_rows(uint32_t max_read_len);
+// CTAs per SM the given variant reaches.
 int forward_f32_ctas_per_sm(int K, int W, bool striped);
-int forward_f64_ctas_per_sm(bool flush);
+int forward_f64_ctas_per_sm(int K, bool flush);
 
 cudaError_t launch_build_stream(const uint8_t* hap_blob, const HapDesc* haps, const uint32_t* spos, uint32_t num_hap,
                                 uint8_t* stream, float* inity_f, double* inity_d, float ic_f, double ic_d,
@@ -72,6 +82,7 @@ cudaError_t launch_read_params(const uint8_t* read_blob, const ReadDesc* reads, 
                                const DeviceTables& tab, float* params, cudaStream_t s);
 
 // Scan raw[] for values below 1e-28f and append one single-pair Task per hit (read, hap, slot) to fb_tasks.
+// (Not used by the engine any more -- the float kernel appends inline -- kept for the standalone tests/tools.)
 cudaError_t launch_compact_fallback(const float* raw, const RegionDesc* regions, uint32_t nregions,
                                     uint32_t total_pairs, Task* fb_tasks, uint32_t* fb_out_index,
                                     uint32_t* fb_count, uint32_t fb_capacity, cudaStream_t s);

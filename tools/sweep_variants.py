@@ -10,6 +10,8 @@ from acc_genomics_b200.engine import PairHMMEngine, PmmError
 VARIANTS = [(k, 8) for k in range(4, 21)] + [(k, 16) for k in (4, 5, 6, 7, 8, 9, 10, 11, 12, 14, 16)] + \
            [(k, 32) for k in (4, 5, 6, 7, 8, 9, 10, 12, 14, 16)]
 eng = PairHMMEngine(0)
+for kv in os.environ.get("PMM_OPTS", "").split():
+    eng.set_option(*kv.split("="))
 os.makedirs("gpurun_out", exist_ok=True)
 out = open("gpurun_out/sweep_variants.jsonl", "a")
 cfgs = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [2, 1, 4]
