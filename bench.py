@@ -3,7 +3,8 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2] [--impl ours|reference]
 
-One "step" = one pass of the hot path over one batch: float forward kernels, fallback compaction, double re-run
+One "step" = one pass of the hot path over one batch: row parameters, float forward kernels (which also build the
+fallback list), double re-run of the fallback list
 (pmm_launch of include/pairhmm_cuda.h).  At N = 1 the workload is configs[1] of BASELINE.json (config 2, the
 GATK-HaplotypeCaller-like active region: 1000 reads x 151 bp against 64 haplotypes of 300-600 bp, ~4.4e9 cells).
 With N > 1 (launched by torch.distributed.run, one rank per GPU) every rank runs a batch of the same shape with its
@@ -126,7 +127,7 @@ def cpu_reference_pass(lib, batches, threads: int):
     return time.perf_counter() - t0, nfb
 
 
-def run_reference(args, rank: int, world: int):
+def run_reference(args, rank: int, world: int, out=sys.stdout):
     """--impl reference: the reference's own CPU implementation on the host cores (rank 0 only)."""
     if rank != 0:
         return
@@ -154,7 +155,7 @@ def run_reference(args, rank: int, world: int):
                          "sample": "the full workload per step, all host threads, static split over reads"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    }), file=out, flush=True)
 
 
 _T0 = time.perf_counter()
@@ -166,11 +167,23 @@ def log(msg: str):
 
 def main():
     args = parse()
+    # Libraries (NCCL's version banner, for one) write to fd 1; the contract is ONE JSON line on stdout.  Keep the real
+    # stdout aside and point fd 1 at stderr until the line is printed.
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+    try:
+        _main(args, real_stdout)
+    finally:
+        real_stdout.flush()
+
+
+def _main(args, real_stdout):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, real_stdout)
         return
 
     import torch
@@ -227,11 +240,11 @@ def main():
     dev_s = sum(step_ms) * 1e-3
 
     # per-kernel time of the float forward kernel(s), from the engine's own events on the same stream
-    f32_ms = []
+    f32_ms, fb_ms = [], []
     for _ in range(min(args.steps, 10)):
         flush.fill_(1)
         eng.launch(); eng.sync()
-        f32_ms.append(eng.stats()["ms_f32"])
+        f32_ms.append(eng.stats()["ms_f32"]); fb_ms.append(eng.stats()["ms_fallback"])
     f32_ms_avg = float(np.mean(f32_ms))
     raw = eng.fetch_raw()
     out, nfb = eng.fetch_log10()
@@ -317,6 +330,8 @@ def main():
             "roofline": {"bound": "fp32_issue", "kernel": "pmm_forward_kernel<float,K,W> (float pass)", "achieved": achieved, "peak": peak,
                          "unit": "T FP32 lane-instr/s", "frac": achieved / peak, "traffic": None,
                          "kernel_ms": f32_ms_avg, "kernel_gcups": f32_cells_per_s * 1e-9,
+                         "kernel_ms_note": "CUDA events around read_params_kernel + the float forward launch(es) on the engine's stream",
+                         "fallback_pass_ms": float(np.mean(fb_ms)),
                          "algorithmic": "12 FP32 instr per cell (8 FMUL + 4 FADD) x cells per launch",
                          "peak_source": "measured live: independent FMUL/FADD streams (pmm_measure_fp32_peak); "
                                         "MEASURED_PEAKS.json has no FP32 figure",
@@ -340,7 +355,7 @@ def main():
             except Exception as e:  # the baseline is a report, never a reason to lose the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)}
         log("cpu baseline done")
-        print(json.dumps(line))
+        print(json.dumps(line), file=real_stdout, flush=True)
     eng.close()
     if world > 1:
         dist.barrier()
