@@ -71,6 +71,8 @@ struct pmm_ctx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string err;
     int tasks_per_warp = 16;
+    bool fast = false;                  // "mode" option: fast = contracted float kernels + exact re-check near the threshold
+    float guard = 0.0078125f;           // "guard" option: relative half-width of the re-check band around 1e-28f (2^-7)
     int f64_rows = kF64K;               // rows per lane of the double kernel for the staged job (pick_f64_rows)
     Variant force{0, 0, false};         // "force_variant" option (tuning sweeps): K,W of the float kernel
 
@@ -215,7 +217,8 @@ int stage_common(pmm_ctx* c, uint32_t num_read, const uint32_t* read_off, const 
     {
         const int ctas64 = std::max(std::max(forward_f64_ctas_per_sm(5, false), forward_f64_ctas_per_sm(5, true)),
                                     std::max(forward_f64_ctas_per_sm(6, false), forward_f64_ctas_per_sm(6, true)));
-        const int ctas32 = forward_f32_ctas_per_sm(kStripedK, 32, true);
+        const int ctas32 = std::max(std::max(forward_f32_ctas_per_sm(kStripedK, 32, true, false), forward_f32_ctas_per_sm(kStripedK, 32, true, true)),
+                                    recheck_f32_ctas_per_sm());
         const size_t warps = (size_t)c->sm_count * std::max(ctas64, ctas32) * kWarpsPerCta;
         PMM_CUDA(c, c->d_scratch.reserve(warps * 3 * (size_t)(max_hap + 8) * sizeof(double)));
     }
@@ -391,6 +394,18 @@ int pmm_set_option(pmm_ctx* c, const char* key, const char* value)
         c->tasks_per_warp = v;
         return PMM_OK;
     }
+    if (k == "mode") {
+        const std::string v(value);
+        if (v != "exact" && v != "fast") return c->fail(PMM_ERR_INVALID, "mode is \"exact\" or \"fast\"");
+        c->fast = v == "fast";
+        return PMM_OK;
+    }
+    if (k == "guard") {
+        const float g = (float)atof(value);
+        if (!(g >= 0.0f && g < 1.0f)) return c->fail(PMM_ERR_INVALID, "guard must be in [0, 1)");
+        c->guard = g;
+        return PMM_OK;
+    }
     if (k == "force_variant") {
         int K = 0, W = 0;
         if (sscanf(value, "%d,%d", &K, &W) != 2 || (K && !forward_f32_has_variant(K, W)))
@@ -445,7 +460,12 @@ int pmm_launch(pmm_ctx* c)
     // ---- float pass, one launch per (K, W) variant present in the job; results below 1e-28f are appended to the
     //      fallback list by the kernel itself (PairHMMWorker.cpp:176) ----------------------------------------------
     if (c->segs.size() > 100) return c->fail(PMM_ERR_INVALID, "too many kernel variants in one job");
-    const FallbackQueue fq{static_cast<Task*>(c->d_fb_tasks.p), static_cast<uint32_t*>(c->d_fb_idx.p), ctrl + 0, (uint32_t)c->pairs};
+    // fast mode: results within the guard band around the threshold are re-run by an exact kernel before the decision
+    // is taken, so the decision (and the float value of those pairs) is the reference's, bit for bit
+    const float thr = 1e-28f;
+    FallbackQueue fq{static_cast<Task*>(c->d_fb_tasks.p), static_cast<uint32_t*>(c->d_fb_idx.p), ctrl + 0, (uint32_t)c->pairs,
+                     c->fast ? thr * (1.0f - c->guard) : thr, c->fast ? thr * (1.0f + c->guard) : thr,
+                     static_cast<Task*>(c->d_tiny_tasks.p) /* free until the double pass is over */, ctrl + 2};
     uint32_t cursor = kCtrlCursors;
     for (const LaunchSeg& seg : c->segs) {
         a.inity = c->d_iyf.p;
@@ -453,10 +473,18 @@ int pmm_launch(pmm_ctx* c)
         a.ntasks = seg.task_count; a.ntasks_dev = nullptr;
         a.counter = ctrl + cursor; cursor += 32;
         a.out = c->d_raw.p;
-        const int per_sm = forward_f32_ctas_per_sm(seg.v.K, seg.v.W, seg.v.striped);
+        const int per_sm = forward_f32_ctas_per_sm(seg.v.K, seg.v.W, seg.v.striped, c->fast);
         if (per_sm <= 0) return c->fail(PMM_ERR_INVALID, "kernel variant unavailable");
         const int ctas = (int)std::min<uint64_t>((seg.task_count + kWarpsPerCta - 1) / kWarpsPerCta, (uint64_t)c->sm_count * per_sm);
-        PMM_CUDA(c, launch_forward_f32(seg.v.K, seg.v.W, seg.v.striped, a, fq, ctas, s));
+        PMM_CUDA(c, launch_forward_f32(seg.v.K, seg.v.W, seg.v.striped, c->fast, a, fq, ctas, s));
+        ++launches;
+    }
+    if (c->fast) {
+        // ---- exact re-check of the guard band (normally a handful of pairs, often none) -----------------------------
+        a.tasks = static_cast<Task*>(c->d_tiny_tasks.p); a.ntasks = 0; a.ntasks_dev = ctrl + 2;
+        a.counter = ctrl + cursor; cursor += 32;
+        fq.lo = fq.hi = thr;
+        PMM_CUDA(c, launch_recheck_f32(a, fq, c->sm_count * std::max(1, recheck_f32_ctas_per_sm()), s));
         ++launches;
     }
     PMM_CUDA(c, cudaEventRecord(c->ev[1], s));
@@ -502,11 +530,11 @@ static int fetch_common(pmm_ctx* c, bool want_lists, uint32_t* nfb_out, uint32_t
     char* ho = static_cast<char*>(c->h_out.p);
     uint32_t* hctrl = reinterpret_cast<uint32_t*>(ho);                          // 256 B header
     float* hraw = reinterpret_cast<float*>(ho + 256);
-    PMM_CUDA(c, cudaMemcpyAsync(hctrl, c->d_ctrl.p, 8, cudaMemcpyDeviceToHost, s));
+    PMM_CUDA(c, cudaMemcpyAsync(hctrl, c->d_ctrl.p, 12, cudaMemcpyDeviceToHost, s));
     PMM_CUDA(c, cudaMemcpyAsync(hraw, c->d_raw.p, sizeof(float) * c->pairs, cudaMemcpyDeviceToHost, s));
     PMM_CUDA(c, cudaStreamSynchronize(s));
     const uint32_t nfb = hctrl[0], ntiny = hctrl[1];
-    uint64_t d2h = 8 + sizeof(float) * c->pairs;
+    uint64_t d2h = 12 + sizeof(float) * c->pairs;
     if (want_lists && nfb) {
         uint32_t* hidx = reinterpret_cast<uint32_t*>(ho + 256 + align_up(sizeof(float) * c->pairs));
         double* hd = reinterpret_cast<double*>(reinterpret_cast<char*>(hidx) + align_up(sizeof(uint32_t) * c->pairs));
@@ -515,7 +543,7 @@ static int fetch_common(pmm_ctx* c, bool want_lists, uint32_t* nfb_out, uint32_t
         PMM_CUDA(c, cudaStreamSynchronize(s));
         d2h += (sizeof(uint32_t) + sizeof(double)) * nfb;
     }
-    c->stats.fallback_pairs = nfb; c->stats.flush_pairs = ntiny; c->stats.d2h_bytes = d2h;
+    c->stats.fallback_pairs = nfb; c->stats.flush_pairs = ntiny; c->stats.recheck_pairs = hctrl[2]; c->stats.d2h_bytes = d2h;
     cudaEventElapsedTime(&c->stats.ms_f32, c->ev[0], c->ev[1]);
     cudaEventElapsedTime(&c->stats.ms_fallback, c->ev[1], c->ev[2]);
     if (nfb_out) *nfb_out = nfb;

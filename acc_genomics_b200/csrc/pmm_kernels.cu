@@ -106,14 +106,38 @@ __device__ __forceinline__ void push_fallback(const FallbackQueue& fq, uint32_t 
     fq.out_index[slot] = out_index;
 }
 
+// Fast mode: a result too close to 1e-28f to trust the decision.  The re-check task writes the exact float result
+// over the fast one (out_base = the pair's own result index) and, being an exact kernel with kPush, appends the
+// pair to the fallback list if that is what the reference would do.
+__device__ __forceinline__ void push_recheck(const FallbackQueue& fq, uint32_t read, uint32_t hap, uint32_t out_index)
+{
+    const uint32_t slot = atomicAdd(fq.recheck_count, 1u);
+    if (slot >= fq.capacity) return;
+    Task t;
+    t.read[0] = read; t.read[1] = t.read[2] = t.read[3] = 0;
+    t.out_base[0] = out_index; t.out_base[1] = t.out_base[2] = t.out_base[3] = 0;
+    t.hap_first = hap; t.nhaps = 1; t.nreads = 1; t.param_off = 0;
+    fq.recheck_tasks[slot] = t;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // One warp-task: the reads of one group against a run of haplotypes.
 // ---------------------------------------------------------------------------------------------------------
-template <typename T, int K, int W, bool STRIPED, bool FLUSH, bool PUSH>
+// F: bit flags.  kFlush: emulate x86 flush-to-zero after every double product.  kPush: append results below the
+// fallback threshold to the fallback list (float).  kFast: contract the float cell update to 4 FMUL + 4 FFMA (results
+// within a few ulp of the exact order; the engine re-checks everything near the threshold with an exact kernel).
+// kInline: compute the float row parameters in the kernel instead of reading read_params_kernel's planes (single-pair
+// re-check tasks have no parameter block).
+constexpr int kFlush = 1, kPush = 2, kFast = 4, kInline = 8;
+
+template <typename T, int K, int W, bool STRIPED, int F>
 __device__ __forceinline__ void run_task(const ForwardArgs& a, const Task* tk, T* wtab, const int lane,
                                          const uint32_t gwarp, const FallbackQueue& fq)
 {
     using A = Arith<T>;
+    constexpr bool FLUSH = (F & kFlush) != 0, PUSH = (F & kPush) != 0, FAST = (F & kFast) != 0, INLINE = (F & kInline) != 0;
+    constexpr bool kIsFloat = std::is_same<T, float>::value;
+    static_assert(kIsFloat || !(FAST || PUSH || INLINE), "float-only flags");
     constexpr int VEC = A::kVec;
     constexpr int KQ = (K + VEC - 1) / VEC;           // 16-byte weight vectors per lane and class
     constexpr int CLS_STRIDE = KQ * 32 * VEC;         // elements between the tables of two haplotype classes
@@ -151,7 +175,7 @@ __device__ __forceinline__ void run_task(const ForwardArgs& a, const Task* tk, T
         T pX0 = (T)0;                                                // pC[0] as the X update of row 0 sees it
         unsigned padmask = 0;
         __syncwarp();                                                // previous task / stripe done with wtab
-        if constexpr (std::is_same<T, float>::value) {
+        if constexpr (kIsFloat && !INLINE) {
             // float pass: the rows were prepared once per read by read_params_kernel; W consecutive lanes read
             // consecutive floats, all 8K loads are independent
             constexpr int KW = K * W;
@@ -237,18 +261,26 @@ __device__ __forceinline__ void run_task(const ForwardArgs& a, const Task* tk, T
             #pragma unroll
             for (int j = K - 1; j >= 0; --j) {
                 const T md = j ? M[j - 1] : dM, xd = j ? X[j - 1] : dX, yd = j ? Y[j - 1] : dY;
-                // M = ((Md*pMM + Xd*pGAPM) + Yd*pGAPM) * w        (avx-pairhmm-template.h:188)
-                const T t3 = A::add(flush<FLUSH>(A::mul(md, pMM[j])), flush<FLUSH>(A::mul(xd, pG[j])));
-                const T t5 = A::add(t3, flush<FLUSH>(A::mul(yd, pG[j])));
-                Mn[j] = flush<FLUSH>(A::mul(t5, w[j]));
-                // Y = Mleft*pMY + Yleft*pYY                        (:197)
-                Yn[j] = A::add(flush<FLUSH>(A::mul(M[j], pMY[j])), flush<FLUSH>(A::mul(Y[j], pC[j])));
+                if constexpr (FAST) {
+                    // same formulas, each multiply-add pair contracted: FMUL + 2 FFMA + FMUL, and FMUL + FFMA
+                    const float t5 = __fmaf_rn(yd, pG[j], __fmaf_rn(xd, pG[j], __fmul_rn(md, pMM[j])));
+                    Mn[j] = __fmul_rn(t5, w[j]);
+                    Yn[j] = __fmaf_rn(Y[j], pC[j], __fmul_rn(M[j], pMY[j]));
+                } else {
+                    // M = ((Md*pMM + Xd*pGAPM) + Yd*pGAPM) * w        (avx-pairhmm-template.h:188)
+                    const T t3 = A::add(flush<FLUSH>(A::mul(md, pMM[j])), flush<FLUSH>(A::mul(xd, pG[j])));
+                    const T t5 = A::add(t3, flush<FLUSH>(A::mul(yd, pG[j])));
+                    Mn[j] = flush<FLUSH>(A::mul(t5, w[j]));
+                    // Y = Mleft*pMY + Yleft*pYY                        (:197)
+                    Yn[j] = A::add(flush<FLUSH>(A::mul(M[j], pMY[j])), flush<FLUSH>(A::mul(Y[j], pC[j])));
+                }
             }
             #pragma unroll
             for (int j = 0; j < K; ++j) {
                 const T mu = j ? Mn[j - 1] : inM, xu = j ? Xn[j - 1] : inX;
                 // X = Mup*pMX + Xup*pXX                             (:194)
-                Xn[j] = A::add(flush<FLUSH>(A::mul(mu, pMX[j])), flush<FLUSH>(A::mul(xu, j ? pC[j] : pX0)));
+                if constexpr (FAST) Xn[j] = __fmaf_rn(xu, j ? pC[j] : pX0, __fmul_rn(mu, pMX[j]));
+                else Xn[j] = A::add(flush<FLUSH>(A::mul(mu, pMX[j])), flush<FLUSH>(A::mul(xu, j ? pC[j] : pX0)));
             }
             #pragma unroll
             for (int j = 0; j < K; ++j) { M[j] = Mn[j]; X[j] = Xn[j]; Y[j] = Yn[j]; }
@@ -271,8 +303,13 @@ __device__ __forceinline__ void run_task(const ForwardArgs& a, const Task* tk, T
                             const T res = A::add(sM, sX);
                             out[out_base + nsep - 1] = res;
                             if constexpr (PUSH) {
-                                // the reference's test, a float compare (PairHMMWorker.cpp:176); NaN -> false
-                                if (res < 1e-28f) push_fallback(fq, tk->read[g], hap_first + nsep - 1, out_base + nsep - 1);
+                                // exact kernels: lo == hi == 1e-28f, the reference's test, a float compare
+                                // (PairHMMWorker.cpp:176; NaN -> false).  Fast kernels: results in [lo, hi) are too close
+                                // to the threshold to decide and go to the exact re-check list instead.
+                                if (res < fq.hi) {
+                                    if (res < fq.lo) push_fallback(fq, tk->read[g], hap_first + nsep - 1, out_base + nsep - 1);
+                                    else push_recheck(fq, tk->read[g], hap_first + nsep - 1, out_base + nsep - 1);
+                                }
                             }
                         }
                     done = nsep == (int)nhaps;
@@ -342,7 +379,7 @@ __device__ __forceinline__ void run_task(const ForwardArgs& a, const Task* tk, T
     }
 }
 
-template <typename T, int K, int W, bool STRIPED, bool FLUSH, bool PUSH>
+template <typename T, int K, int W, bool STRIPED, int F>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, min_ctas<T, K>()) pmm_forward_kernel(const ForwardArgs a, const FallbackQueue fq)
 {
     extern __shared__ uint4 smem_raw[];
@@ -355,7 +392,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, min_ctas<T, K>()) pmm_forwa
         if (lane == 0) ti = atomicAdd(a.counter, 1u);
         ti = __shfl_sync(0xffffffffu, ti, 0);
         if (ti >= ntasks) break;
-        run_task<T, K, W, STRIPED, FLUSH, PUSH>(a, a.tasks + ti, wtab, lane, gwarp, fq);
+        run_task<T, K, W, STRIPED, F>(a, a.tasks + ti, wtab, lane, gwarp, fq);
     }
 }
 
@@ -493,11 +530,11 @@ __global__ void __launch_bounds__(256) fp32_probe_kernel(float* sink, int iters)
 // ---------------------------------------------------------------------------------------------------------
 // Variant table
 // ---------------------------------------------------------------------------------------------------------
-template <typename T, int K, int W, bool STRIPED, bool FLUSH, bool PUSH>
+template <typename T, int K, int W, bool STRIPED, int F>
 cudaError_t launch_variant(const ForwardArgs& a, const FallbackQueue& fq, int ctas, cudaStream_t s)
 {
     constexpr int smem = kWarpsPerCta * wtab_elems<T, K>() * (int)sizeof(T);
-    auto kern = pmm_forward_kernel<T, K, W, STRIPED, FLUSH, PUSH>;
+    auto kern = pmm_forward_kernel<T, K, W, STRIPED, F>;
     // per device, cheap: the context may live on any GPU of the box
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
@@ -505,11 +542,11 @@ cudaError_t launch_variant(const ForwardArgs& a, const FallbackQueue& fq, int ct
     return cudaGetLastError();
 }
 
-template <typename T, int K, int W, bool STRIPED, bool FLUSH, bool PUSH>
+template <typename T, int K, int W, bool STRIPED, int F>
 int variant_ctas_per_sm()
 {
     constexpr int smem = kWarpsPerCta * wtab_elems<T, K>() * (int)sizeof(T);
-    auto kern = pmm_forward_kernel<T, K, W, STRIPED, FLUSH, PUSH>;
+    auto kern = pmm_forward_kernel<T, K, W, STRIPED, F>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     int n = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kWarpsPerCta * 32, smem) != cudaSuccess) return 0;
@@ -518,42 +555,56 @@ int variant_ctas_per_sm()
 
 }  // namespace
 
-cudaError_t launch_forward_f32(int K, int W, bool striped, const ForwardArgs& a, const FallbackQueue& fq, int ctas, cudaStream_t s)
+cudaError_t launch_forward_f32(int K, int W, bool striped, bool fast, const ForwardArgs& a, const FallbackQueue& fq, int ctas, cudaStream_t s)
 {
     if (striped) {
-        if (K == kStripedK && W == 32) return launch_variant<float, kStripedK, 32, true, false, true>(a, fq, ctas, s);
-        return cudaErrorInvalidValue;
+        if (K != kStripedK || W != 32) return cudaErrorInvalidValue;
+        return fast ? launch_variant<float, kStripedK, 32, true, kPush | kFast>(a, fq, ctas, s)
+                    : launch_variant<float, kStripedK, 32, true, kPush>(a, fq, ctas, s);
     }
-#define X(k, w) if (K == k && W == w) return launch_variant<float, k, w, false, false, true>(a, fq, ctas, s);
+#define X(k, w) if (K == k && W == w) return fast ? launch_variant<float, k, w, false, kPush | kFast>(a, fq, ctas, s) \
+                                                   : launch_variant<float, k, w, false, kPush>(a, fq, ctas, s);
     PMM_F32_VARIANTS(X)
 #undef X
     return cudaErrorInvalidValue;
 }
 
-int forward_f32_ctas_per_sm(int K, int W, bool striped)
+int forward_f32_ctas_per_sm(int K, int W, bool striped, bool fast)
 {
-    if (striped) return (K == kStripedK && W == 32) ? variant_ctas_per_sm<float, kStripedK, 32, true, false, true>() : 0;
-#define X(k, w) if (K == k && W == w) return variant_ctas_per_sm<float, k, w, false, false, true>();
+    if (striped) {
+        if (K != kStripedK || W != 32) return 0;
+        return fast ? variant_ctas_per_sm<float, kStripedK, 32, true, kPush | kFast>() : variant_ctas_per_sm<float, kStripedK, 32, true, kPush>();
+    }
+#define X(k, w) if (K == k && W == w) return fast ? variant_ctas_per_sm<float, k, w, false, kPush | kFast>() \
+                                                   : variant_ctas_per_sm<float, k, w, false, kPush>();
     PMM_F32_VARIANTS(X)
 #undef X
     return 0;
 }
 
+// Exact float re-check of single pairs (fast mode's guard band): one read per warp, any length, parameters inline.
+cudaError_t launch_recheck_f32(const ForwardArgs& a, const FallbackQueue& fq, int ctas, cudaStream_t s)
+{
+    return launch_variant<float, kStripedK, 32, true, kPush | kInline>(a, fq, ctas, s);
+}
+
+int recheck_f32_ctas_per_sm() { return variant_ctas_per_sm<float, kStripedK, 32, true, kPush | kInline>(); }
+
 // Double re-run: rows per lane K in {5, 6} (W = 32, multi-stripe capable); see pick_f64_rows().
 cudaError_t launch_forward_f64(int K, bool flush, const ForwardArgs& a, int ctas, cudaStream_t s)
 {
     const FallbackQueue none{};
-    if (K == 5) return flush ? launch_variant<double, 5, 32, true, true, false>(a, none, ctas, s)
-                             : launch_variant<double, 5, 32, true, false, false>(a, none, ctas, s);
-    if (K == 6) return flush ? launch_variant<double, 6, 32, true, true, false>(a, none, ctas, s)
-                             : launch_variant<double, 6, 32, true, false, false>(a, none, ctas, s);
+    if (K == 5) return flush ? launch_variant<double, 5, 32, true, kFlush>(a, none, ctas, s)
+                             : launch_variant<double, 5, 32, true, 0>(a, none, ctas, s);
+    if (K == 6) return flush ? launch_variant<double, 6, 32, true, kFlush>(a, none, ctas, s)
+                             : launch_variant<double, 6, 32, true, 0>(a, none, ctas, s);
     return cudaErrorInvalidValue;
 }
 
 int forward_f64_ctas_per_sm(int K, bool flush)
 {
-    if (K == 5) return flush ? variant_ctas_per_sm<double, 5, 32, true, true, false>() : variant_ctas_per_sm<double, 5, 32, true, false, false>();
-    if (K == 6) return flush ? variant_ctas_per_sm<double, 6, 32, true, true, false>() : variant_ctas_per_sm<double, 6, 32, true, false, false>();
+    if (K == 5) return flush ? variant_ctas_per_sm<double, 5, 32, true, kFlush>() : variant_ctas_per_sm<double, 5, 32, true, 0>();
+    if (K == 6) return flush ? variant_ctas_per_sm<double, 6, 32, true, kFlush>() : variant_ctas_per_sm<double, 6, 32, true, 0>();
     return 0;
 }
 

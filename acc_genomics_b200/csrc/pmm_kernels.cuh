@@ -58,6 +58,11 @@ struct FallbackQueue {
     uint32_t* out_index;     // position of the pair in the job's result
     uint32_t* reserve;       // entries appended so far (== fallback count when the float pass is done)
     uint32_t  capacity;
+    // Thresholds of the float pass: result < lo -> fallback list; lo <= result < hi -> exact re-check list.  Exact
+    // kernels run with lo == hi == 1e-28f (the reference's test, PairHMMWorker.cpp:176); fast kernels with a guard band.
+    float     lo, hi;
+    Task*     recheck_tasks;
+    uint32_t* recheck_count;
 };
 
 // Launch helpers implemented in pmm_kernels.cu -------------------------------------------------------------
@@ -65,12 +70,15 @@ struct FallbackQueue {
 // Float pass.  (K rows per lane) x (W lanes per read); W in {8,16,32}.  Returns cudaErrorInvalidValue for an
 // uninstantiated (K, W).  `striped` selects the multi-stripe variant for reads longer than W*K - 1 bases.  Results
 // below 1e-28f are appended to fq as they are produced.
-cudaError_t launch_forward_f32(int K, int W, bool striped, const ForwardArgs& a, const FallbackQueue& fq, int ctas, cudaStream_t s);
+cudaError_t launch_forward_f32(int K, int W, bool striped, bool fast, const ForwardArgs& a, const FallbackQueue& fq, int ctas, cudaStream_t s);
+// Exact float re-run of the single-pair tasks on the re-check list (fast mode), overwriting their results.
+cudaError_t launch_recheck_f32(const ForwardArgs& a, const FallbackQueue& fq, int ctas, cudaStream_t s);
+int recheck_f32_ctas_per_sm();
 // Double re-run (fallback list), K rows per lane from pick_f64_rows().  flush = emulate x86 flush-to-zero on every product.
 cudaError_t launch_forward_f64(int K, bool flush, const ForwardArgs& a, int ctas, cudaStream_t s);
 int pick_f64_rows(uint32_t max_read_len);
 // CTAs per SM the given variant reaches.
-int forward_f32_ctas_per_sm(int K, int W, bool striped);
+int forward_f32_ctas_per_sm(int K, int W, bool striped, bool fast = false);
 int forward_f64_ctas_per_sm(int K, bool flush);
 
 cudaError_t launch_build_stream(const uint8_t* hap_blob, const HapDesc* haps, const uint32_t* spos, uint32_t num_hap,

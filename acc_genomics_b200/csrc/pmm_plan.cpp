@@ -129,6 +129,28 @@ int plan_job(uint32_t num_read, const uint32_t* read_off, uint32_t num_hap, cons
             plan.segs.back().task_count++;
         }
     }
+
+    // ---- longest tasks first inside each launch: warps pull tasks in order, so the kernel's tail is made of the
+    //      shortest ones.  Cost = steps of the wavefront = haplotype bases + separators of the run.  A counting sort
+    //      on 64 cost classes keeps the planner linear in the number of tasks. ---------------------------------------
+    std::vector<Task> sorted;
+    std::vector<uint32_t> cost;
+    for (const LaunchSeg& seg : plan.segs) {
+        if (seg.task_count < 2) continue;
+        Task* first = plan.tasks.data() + seg.task_first;
+        cost.resize(seg.task_count);
+        uint32_t cmax = 1;
+        for (uint32_t k = 0; k < seg.task_count; ++k) {
+            cost[k] = hap_off[first[k].hap_first + first[k].nhaps] - hap_off[first[k].hap_first] + first[k].nhaps;
+            cmax = std::max(cmax, cost[k]);
+        }
+        uint32_t start[65] = {0};
+        for (uint32_t k = 0; k < seg.task_count; ++k) start[63 - (uint32_t)((uint64_t)cost[k] * 63 / cmax) + 1]++;
+        for (int b = 0; b < 64; ++b) start[b + 1] += start[b];
+        sorted.resize(seg.task_count);
+        for (uint32_t k = 0; k < seg.task_count; ++k) sorted[start[63 - (uint32_t)((uint64_t)cost[k] * 63 / cmax)]++] = first[k];
+        std::copy(sorted.begin(), sorted.end(), first);
+    }
     return PMM_OK;
 }
 

@@ -36,7 +36,7 @@ class PmmStats(C.Structure):
     _fields_ = [("pairs", C.c_uint64), ("cells", C.c_uint64), ("fallback_pairs", C.c_uint64), ("flush_pairs", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("kernel_launches", C.c_uint32),
                 ("f32_tasks", C.c_uint32), ("ms_stage", C.c_float), ("ms_f32", C.c_float), ("ms_fallback", C.c_float),
-                ("ms_fetch", C.c_float)]
+                ("ms_fetch", C.c_float), ("recheck_pairs", C.c_uint64)]
 
 
 class PmmTaskInfo(C.Structure):

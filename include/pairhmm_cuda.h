@@ -56,6 +56,7 @@ typedef struct {
     uint32_t kernel_launches;         /* kernels launched by the last pmm_launch                             */
     uint32_t f32_tasks;               /* warp-tasks of the float pass                                        */
     float    ms_stage, ms_f32, ms_fallback, ms_fetch;   /* CUDA-event / host timings of the last job          */
+    uint64_t recheck_pairs;           /* fast mode: pairs re-run by the exact float kernel (guard band)      */
 } pmm_stats_t;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------
@@ -70,6 +71,13 @@ int  pmm_device_count(void);
  *   "stream"          = value of a cudaStream_t (decimal or 0x..) to run on, "default" for the legacy default
  *                       stream, "own" for the context's own non-blocking stream (the initial setting)
  *   "tasks_per_warp"  = target queue depth per resident warp used when cutting regions into warp-tasks
+ *   "mode"            = "exact" (default): every multiply and add of the float pass is rounded on its own, results are
+ *                       bit-identical to the reference's AVX code.  "fast": the float cell update is contracted to
+ *                       4 FMUL + 4 FFMA per cell (12 -> 8 instructions); results agree with the reference to a few
+ *                       float ulp (<= 1e-5 relative in log10, typically 1e-7), and every pair whose float result lies
+ *                       within the guard band around 1e-28f is re-run by the exact kernel before the float-versus-
+ *                       double decision is taken, so that decision stays identical to the reference's
+ *   "guard"           = relative half-width of that band (default 0.0078125 = 2^-7)
  *   "force_variant"   = "K,W": rows per lane and lanes per read of the float kernel for every read that fits
  *                       (tuning sweeps, tools/sweep_variants.py); "0,0" gives the choice back to the planner   */
 int  pmm_set_option(pmm_ctx* ctx, const char* key, const char* value);
