@@ -9,6 +9,9 @@
 #include "pmm_tables.h"
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -96,7 +99,8 @@ struct pmm_ctx {
 
     // scratch reused by the one-shot calls
     std::vector<uint32_t> tmp_roff, tmp_hoff;
-    std::vector<uint8_t> tmp_tracks[5], tmp_hap;
+    std::vector<ReadDesc> tmp_rdesc;
+    std::vector<HapDesc> tmp_hdesc;
     std::vector<float> tmp_raw;
 
     int fail_cuda(cudaError_t e, const char* what)
@@ -129,15 +133,20 @@ int ensure_tables(pmm_ctx* c)
     return PMM_OK;
 }
 
-struct ReadSrc {
-    // track t of read r lives at base[t] + off[r]
-    const uint8_t* base[5];
+// Where the bytes of a job come from.  The device-side blobs are the concatenation of `parts`; the descriptors give
+// every read's five tracks (off, stride, len) and every haplotype (off, len) inside those blobs.  Two producers:
+// five flat track arrays (stride = total bases) and the reference's wire format taken as it is (stride = len,
+// interface/PairHMMHostInterface.cpp:175-207) -- the latter makes staging a serialized block one memcpy.
+struct BlobPart { const uint8_t* p; size_t n; };
+struct JobSource {
+    std::vector<BlobPart> read_parts, hap_parts;
+    const ReadDesc* rdesc = nullptr;
+    const HapDesc* hdesc = nullptr;
 };
 
 // Common staging: reads are given as (offset, length) into five tracks, haplotypes likewise into one.
-int stage_common(pmm_ctx* c, uint32_t num_read, const uint32_t* read_off, const ReadSrc& rs,
-                 uint32_t num_hap, const uint32_t* hap_off, const uint8_t* hap_bases,
-                 uint32_t num_region, const pmm_region_t* regions)
+int stage_common(pmm_ctx* c, uint32_t num_read, const uint32_t* read_off, uint32_t num_hap, const uint32_t* hap_off,
+                 const JobSource& src, uint32_t num_region, const pmm_region_t* regions)
 {
     auto t0 = std::chrono::steady_clock::now();
     c->staged = false; c->launched = false;
@@ -151,8 +160,9 @@ int stage_common(pmm_ctx* c, uint32_t num_read, const uint32_t* read_off, const 
                       c->force.K ? &c->force : nullptr);
         if (rc) return c->fail(rc, perr);
     }
-    const uint64_t total_bases = read_off[num_read] - read_off[0];
-    const uint64_t total_hap = hap_off[num_hap] - hap_off[0];
+    size_t sz_rblob = 0, sz_hblob = 0;
+    for (const BlobPart& bp : src.read_parts) sz_rblob += bp.n;
+    for (const BlobPart& bp : src.hap_parts) sz_hblob += bp.n;
     const uint32_t max_hap = plan.max_hap_len;
     const uint64_t pairs = plan.pairs, cells = plan.cells;
     const std::vector<Task>& tasks = plan.tasks;
@@ -162,8 +172,7 @@ int stage_common(pmm_ctx* c, uint32_t num_read, const uint32_t* read_off, const 
     c->segs = plan.segs;
 
     // ---- pack the input arena ---------------------------------------------------------------------------------
-    const size_t sz_rblob = total_bases * 5, sz_rdesc = sizeof(ReadDesc) * num_read;
-    const size_t sz_hblob = total_hap, sz_hdesc = sizeof(HapDesc) * num_hap;
+    const size_t sz_rdesc = sizeof(ReadDesc) * num_read, sz_hdesc = sizeof(HapDesc) * num_hap;
     const size_t sz_spos = sizeof(uint32_t) * (num_hap + 1), sz_tasks = sizeof(Task) * tasks.size();
     const size_t sz_regions = sizeof(RegionDesc) * num_region;
     const size_t sz_groups = sizeof(GroupDesc) * plan.groups.size();
@@ -180,20 +189,17 @@ int stage_common(pmm_ctx* c, uint32_t num_read, const uint32_t* read_off, const 
     PMM_CUDA(c, c->h_in.reserve(arena));
     PMM_CUDA(c, c->d_in.reserve(arena));
     char* hb = static_cast<char*>(c->h_in.p);
-    const uint32_t r_base = read_off[0], h_base = hap_off[0];
-    for (int t = 0; t < 5; ++t) memcpy(hb + c->off_rblob + (size_t)t * total_bases, rs.base[t] + r_base, total_bases);
-    ReadDesc* rd = reinterpret_cast<ReadDesc*>(hb + c->off_rdesc);
-    for (uint32_t i = 0; i < num_read; ++i)
-        rd[i] = ReadDesc{read_off[i] - r_base, (uint32_t)total_bases, read_off[i + 1] - read_off[i]};
-    memcpy(hb + c->off_hblob, hap_bases + h_base, total_hap);
-    HapDesc* hd = reinterpret_cast<HapDesc*>(hb + c->off_hdesc);
+    {
+        char* w = hb + c->off_rblob;
+        for (const BlobPart& bp : src.read_parts) { memcpy(w, bp.p, bp.n); w += bp.n; }
+        w = hb + c->off_hblob;
+        for (const BlobPart& bp : src.hap_parts) { memcpy(w, bp.p, bp.n); w += bp.n; }
+    }
+    memcpy(hb + c->off_rdesc, src.rdesc, sz_rdesc);
+    memcpy(hb + c->off_hdesc, src.hdesc, sz_hdesc);
     uint32_t* spos = reinterpret_cast<uint32_t*>(hb + c->off_spos);
     uint32_t pos = 0;
-    for (uint32_t h = 0; h < num_hap; ++h) {
-        const uint32_t len = hap_off[h + 1] - hap_off[h];
-        hd[h] = HapDesc{hap_off[h] - h_base, len};
-        spos[h] = pos; pos += len + 1;
-    }
+    for (uint32_t h = 0; h < num_hap; ++h) { spos[h] = pos; pos += src.hdesc[h].len + 1; }
     spos[num_hap] = pos;                           // final separator
     memcpy(hb + c->off_tasks, tasks.data(), sz_tasks);
     memcpy(hb + c->off_regions, rdesc.data(), sz_regions);
@@ -277,46 +283,128 @@ bool scan_haps(const uint8_t* p, uint64_t n, std::vector<uint32_t>& off, std::ve
     return true;
 }
 
-// Gather the wire format into the flat layout (five tracks + offsets) the stager takes.
-int flatten_serialized(pmm_ctx* c, const void* reads_ser, uint64_t reads_bytes, const void* haps_ser, uint64_t haps_bytes)
+// The wire format as the job source: lengths go to tmp_roff / tmp_hoff for the planner, the blobs are the serialized
+// buffers themselves.
+int source_from_serialized(pmm_ctx* c, const void* reads_ser, uint64_t reads_bytes, const void* haps_ser, uint64_t haps_bytes,
+                           JobSource& src)
 {
     std::vector<uint32_t> roff, rlen, hoff, hlen;
     const uint8_t* rp = static_cast<const uint8_t*>(reads_ser);
     const uint8_t* hp = static_cast<const uint8_t*>(haps_ser);
     if (!rp || !hp || !scan_reads(rp, reads_bytes, roff, rlen) || !scan_haps(hp, haps_bytes, hoff, hlen))
         return c->fail(PMM_ERR_INVALID, "malformed serialized block");
+    if (reads_bytes >= (1ull << 31) || haps_bytes >= (1ull << 31)) return c->fail(PMM_ERR_INVALID, "serialized block larger than 2 GiB");
     const size_t nr = roff.size(), nh = hoff.size();
     c->tmp_roff.assign(nr + 1, 0); c->tmp_hoff.assign(nh + 1, 0);
-    for (size_t i = 0; i < nr; ++i) c->tmp_roff[i + 1] = c->tmp_roff[i] + rlen[i];
-    for (size_t i = 0; i < nh; ++i) c->tmp_hoff[i + 1] = c->tmp_hoff[i] + hlen[i];
-    for (int t = 0; t < 5; ++t) c->tmp_tracks[t].resize(c->tmp_roff[nr]);
-    c->tmp_hap.resize(c->tmp_hoff[nh]);
-    for (size_t i = 0; i < nr; ++i)
-        for (int t = 0; t < 5; ++t)
-            memcpy(c->tmp_tracks[t].data() + c->tmp_roff[i], rp + roff[i] + (size_t)t * rlen[i], rlen[i]);
-    for (size_t i = 0; i < nh; ++i) memcpy(c->tmp_hap.data() + c->tmp_hoff[i], hp + hoff[i], hlen[i]);
+    c->tmp_rdesc.resize(nr); c->tmp_hdesc.resize(nh);
+    for (size_t i = 0; i < nr; ++i) {
+        c->tmp_roff[i + 1] = c->tmp_roff[i] + rlen[i];
+        c->tmp_rdesc[i] = ReadDesc{roff[i], rlen[i], rlen[i]};
+    }
+    for (size_t i = 0; i < nh; ++i) {
+        c->tmp_hoff[i + 1] = c->tmp_hoff[i] + hlen[i];
+        c->tmp_hdesc[i] = HapDesc{hoff[i], hlen[i]};
+    }
+    src.read_parts = {BlobPart{rp, (size_t)reads_bytes}};
+    src.hap_parts = {BlobPart{hp, (size_t)haps_bytes}};
+    src.rdesc = c->tmp_rdesc.data(); src.hdesc = c->tmp_hdesc.data();
     return PMM_OK;
 }
 
-int stage_tmp_single_region(pmm_ctx* c)
+// Five flat tracks + one haplotype array, (offset, length) per element.
+void source_from_flat(pmm_ctx* c, uint32_t num_read, const uint32_t* read_off, const uint8_t* const tracks[5],
+                      uint32_t num_hap, const uint32_t* hap_off, const uint8_t* hap_bases, JobSource& src)
+{
+    const uint32_t r_base = read_off[0], h_base = hap_off[0];
+    const size_t total_bases = read_off[num_read] - r_base, total_hap = hap_off[num_hap] - h_base;
+    c->tmp_rdesc.resize(num_read); c->tmp_hdesc.resize(num_hap);
+    for (uint32_t i = 0; i < num_read; ++i)
+        c->tmp_rdesc[i] = ReadDesc{read_off[i] - r_base, (uint32_t)total_bases, read_off[i + 1] - read_off[i]};
+    for (uint32_t h = 0; h < num_hap; ++h) c->tmp_hdesc[h] = HapDesc{hap_off[h] - h_base, hap_off[h + 1] - hap_off[h]};
+    src.read_parts.clear();
+    for (int t = 0; t < 5; ++t) src.read_parts.push_back(BlobPart{tracks[t] + r_base, total_bases});
+    src.hap_parts = {BlobPart{hap_bases + h_base, total_hap}};
+    src.rdesc = c->tmp_rdesc.data(); src.hdesc = c->tmp_hdesc.data();
+}
+
+int stage_single_region(pmm_ctx* c, const JobSource& src)
 {
     const uint32_t nr = (uint32_t)c->tmp_roff.size() - 1, nh = (uint32_t)c->tmp_hoff.size() - 1;
     if (nr == 0 || nh == 0) return c->fail(PMM_ERR_INVALID, "empty batch");
-    ReadSrc rs;
-    for (int t = 0; t < 5; ++t) rs.base[t] = c->tmp_tracks[t].data();
     pmm_region_t reg{0, nr, 0, nh};
-    return stage_common(c, nr, c->tmp_roff.data(), rs, nh, c->tmp_hoff.data(), c->tmp_hap.data(), 1, &reg);
+    return stage_common(c, nr, c->tmp_roff.data(), nh, c->tmp_hoff.data(), src, 1, &reg);
 }
+
+// Host worker threads for the per-result log10 (the one piece of the path that stays on the host so that it uses the
+// host libm like the reference).  Created once per process on first use; a fetch hands out chunks and takes part
+// itself, so small jobs never wait for a wake-up.  Calls from several contexts are serialised (each lasts tens of us).
+class HostWorkers {
+ public:
+    static HostWorkers& get() { static HostWorkers w; return w; }
+    void run(uint64_t n, uint64_t grain, const std::function<void(uint64_t, uint64_t)>& f)
+    {
+        if (n <= grain || th_.empty()) { f(0, n); return; }
+        std::lock_guard<std::mutex> call(call_mu_);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            fn_ = &f; n_ = n; grain_ = grain; next_.store(0); busy_ = (int)th_.size(); ++gen_;
+        }
+        cv_work_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_done_.wait(lk, [&] { return busy_ == 0; });
+        fn_ = nullptr;
+    }
+
+ private:
+    HostWorkers()
+    {
+        const unsigned hw = std::thread::hardware_concurrency();
+        const unsigned n = hw > 1 ? std::min(hw - 1, 7u) : 0;
+        for (unsigned k = 0; k < n; ++k) th_.emplace_back([this] { loop(); });
+    }
+    ~HostWorkers()
+    {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+        cv_work_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    void work()
+    {
+        for (;;) {
+            const uint64_t a = next_.fetch_add(grain_);
+            if (a >= n_) return;
+            (*fn_)(a, std::min(n_, a + grain_));
+        }
+    }
+    void loop()
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_work_.wait(lk, [&] { return stop_ || gen_ != seen; });
+                if (stop_) return;
+                seen = gen_;
+            }
+            work();
+            { std::lock_guard<std::mutex> lk(mu_); --busy_; }
+            cv_done_.notify_one();
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex mu_, call_mu_;
+    std::condition_variable cv_work_, cv_done_;
+    const std::function<void(uint64_t, uint64_t)>* fn_ = nullptr;
+    uint64_t n_ = 0, grain_ = 1, gen_ = 0;
+    std::atomic<uint64_t> next_{0};
+    int busy_ = 0;
+    bool stop_ = false;
+};
 
 void parallel_for(uint64_t n, uint64_t grain, const std::function<void(uint64_t, uint64_t)>& f)
 {
-    unsigned hw = std::thread::hardware_concurrency();
-    uint64_t nt = std::min<uint64_t>(std::max(1u, std::min(hw, 16u)), (n + grain - 1) / std::max<uint64_t>(grain, 1));
-    if (nt <= 1) { f(0, n); return; }
-    std::vector<std::thread> th;
-    for (uint64_t t = 0; t + 1 < nt; ++t) th.emplace_back(f, n * t / nt, n * (t + 1) / nt);
-    f(n * (nt - 1) / nt, n);
-    for (auto& x : th) x.join();
+    HostWorkers::get().run(n, std::max<uint64_t>(grain, 1), f);
 }
 }  // namespace
 
@@ -424,8 +512,14 @@ int pmm_stage_flat(pmm_ctx* c, uint32_t num_read, const uint32_t* read_off,
     if (!c) return PMM_ERR_INVALID;
     if (!bases || !q || !i || !d || !cc || !hap_bases) return c->fail(PMM_ERR_INVALID, "null track");
     cudaSetDevice(c->device);
-    ReadSrc rs{{bases, q, i, d, cc}};
-    return stage_common(c, num_read, read_off, rs, num_hap, hap_off, hap_bases, num_region, regions);
+    if (!read_off || !hap_off || !num_read || !num_hap) return c->fail(PMM_ERR_INVALID, "empty job");
+    if (read_off[num_read] < read_off[0] || hap_off[num_hap] < hap_off[0]) return c->fail(PMM_ERR_INVALID, "offsets not ascending");
+    for (uint32_t k = 0; k < num_read; ++k) if (read_off[k + 1] < read_off[k]) return c->fail(PMM_ERR_INVALID, "offsets not ascending");
+    for (uint32_t k = 0; k < num_hap; ++k) if (hap_off[k + 1] < hap_off[k]) return c->fail(PMM_ERR_INVALID, "offsets not ascending");
+    const uint8_t* const tracks[5] = {bases, q, i, d, cc};
+    JobSource src;
+    source_from_flat(c, num_read, read_off, tracks, num_hap, hap_off, hap_bases, src);
+    return stage_common(c, num_read, read_off, num_hap, hap_off, src, num_region, regions);
 }
 
 int pmm_launch(pmm_ctx* c)
@@ -530,18 +624,25 @@ static int fetch_common(pmm_ctx* c, bool want_lists, uint32_t* nfb_out, uint32_t
     char* ho = static_cast<char*>(c->h_out.p);
     uint32_t* hctrl = reinterpret_cast<uint32_t*>(ho);                          // 256 B header
     float* hraw = reinterpret_cast<float*>(ho + 256);
+    uint32_t* hidx = reinterpret_cast<uint32_t*>(ho + 256 + align_up(sizeof(float) * c->pairs));
+    double* hd = reinterpret_cast<double*>(reinterpret_cast<char*>(hidx) + align_up(sizeof(uint32_t) * c->pairs));
+    // The length of the fallback list is only known on the device.  Copy a first slice of it (an eighth of the pairs)
+    // together with the results, so that the common case needs one round trip; the rest, if any, follows.
+    const uint32_t spec = want_lists ? (uint32_t)std::min<uint64_t>(c->pairs, std::max<uint64_t>(1024, c->pairs / 8)) : 0;
     PMM_CUDA(c, cudaMemcpyAsync(hctrl, c->d_ctrl.p, 12, cudaMemcpyDeviceToHost, s));
     PMM_CUDA(c, cudaMemcpyAsync(hraw, c->d_raw.p, sizeof(float) * c->pairs, cudaMemcpyDeviceToHost, s));
+    if (spec) {
+        PMM_CUDA(c, cudaMemcpyAsync(hidx, c->d_fb_idx.p, sizeof(uint32_t) * spec, cudaMemcpyDeviceToHost, s));
+        PMM_CUDA(c, cudaMemcpyAsync(hd, c->d_dres.p, sizeof(double) * spec, cudaMemcpyDeviceToHost, s));
+    }
     PMM_CUDA(c, cudaStreamSynchronize(s));
     const uint32_t nfb = hctrl[0], ntiny = hctrl[1];
-    uint64_t d2h = 12 + sizeof(float) * c->pairs;
-    if (want_lists && nfb) {
-        uint32_t* hidx = reinterpret_cast<uint32_t*>(ho + 256 + align_up(sizeof(float) * c->pairs));
-        double* hd = reinterpret_cast<double*>(reinterpret_cast<char*>(hidx) + align_up(sizeof(uint32_t) * c->pairs));
-        PMM_CUDA(c, cudaMemcpyAsync(hidx, c->d_fb_idx.p, sizeof(uint32_t) * nfb, cudaMemcpyDeviceToHost, s));
-        PMM_CUDA(c, cudaMemcpyAsync(hd, c->d_dres.p, sizeof(double) * nfb, cudaMemcpyDeviceToHost, s));
+    uint64_t d2h = 12 + sizeof(float) * c->pairs + (sizeof(uint32_t) + sizeof(double)) * spec;
+    if (want_lists && nfb > spec) {
+        PMM_CUDA(c, cudaMemcpyAsync(hidx + spec, static_cast<uint32_t*>(c->d_fb_idx.p) + spec, sizeof(uint32_t) * (nfb - spec), cudaMemcpyDeviceToHost, s));
+        PMM_CUDA(c, cudaMemcpyAsync(hd + spec, static_cast<double*>(c->d_dres.p) + spec, sizeof(double) * (nfb - spec), cudaMemcpyDeviceToHost, s));
         PMM_CUDA(c, cudaStreamSynchronize(s));
-        d2h += (sizeof(uint32_t) + sizeof(double)) * nfb;
+        d2h += (sizeof(uint32_t) + sizeof(double)) * (nfb - spec);
     }
     c->stats.fallback_pairs = nfb; c->stats.flush_pairs = ntiny; c->stats.recheck_pairs = hctrl[2]; c->stats.d2h_bytes = d2h;
     cudaEventElapsedTime(&c->stats.ms_f32, c->ev[0], c->ev[1]);
@@ -577,6 +678,21 @@ int pmm_fetch_fallback_mask(pmm_ctx* c, uint8_t* mask, uint64_t cap)
     return PMM_OK;
 }
 
+int pmm_host_finish_log10(const float* raw, uint64_t n, const uint32_t* fb_index, const double* fb_value, uint64_t n_fb, double* out)
+{
+    if (!out || (n && !raw) || (n_fb && (!fb_index || !fb_value))) return PMM_ERR_INVALID;
+    const HostTables& t = host_tables();
+    const float licf = t.log10_ic_f; const double licd = t.log10_ic_d;
+    // (double)(log10f(v) - log10f(2^120)), float subtraction (PairHMMWorker.cpp:190); host libm on purpose
+    parallel_for(n, 1 << 13, [&](uint64_t a, uint64_t b) { for (uint64_t k = a; k < b; ++k) out[k] = (double)(log10f(raw[k]) - licf); });
+    // log10(d) - log10(2^1020) for the pairs that fell back (PairHMMWorker.cpp:184)
+    for (uint64_t k = 0; k < n_fb; ++k) {
+        if (fb_index[k] >= n) return PMM_ERR_INVALID;
+        out[fb_index[k]] = log10(fb_value[k]) - licd;
+    }
+    return PMM_OK;
+}
+
 int pmm_fetch_log10(pmm_ctx* c, double* out, uint64_t cap, uint64_t* n_fallback)
 {
     if (!c || !out) return PMM_ERR_INVALID;
@@ -589,12 +705,7 @@ int pmm_fetch_log10(pmm_ctx* c, double* out, uint64_t cap, uint64_t* n_fallback)
     const float* hraw = reinterpret_cast<const float*>(ho + 256);
     const uint32_t* hidx = reinterpret_cast<const uint32_t*>(ho + 256 + align_up(sizeof(float) * c->pairs));
     const double* hd = reinterpret_cast<const double*>(reinterpret_cast<const char*>(hidx) + align_up(sizeof(uint32_t) * c->pairs));
-    const HostTables& t = host_tables();
-    const float licf = t.log10_ic_f; const double licd = t.log10_ic_d;
-    // (double)(log10f(v) - log10f(2^120)), float subtraction (PairHMMWorker.cpp:190); host libm on purpose
-    parallel_for(c->pairs, 1 << 15, [&](uint64_t a, uint64_t b) { for (uint64_t k = a; k < b; ++k) out[k] = (double)(log10f(hraw[k]) - licf); });
-    // log10(d) - log10(2^1020) for the pairs that fell back (PairHMMWorker.cpp:184)
-    for (uint32_t k = 0; k < nfb; ++k) out[hidx[k]] = log10(hd[k]) - licd;
+    pmm_host_finish_log10(hraw, c->pairs, hidx, hd, nfb, out);
     if (n_fallback) *n_fallback = nfb;
     c->stats.ms_fetch = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return PMM_OK;
@@ -622,11 +733,12 @@ int pmm_stage_serialized(pmm_ctx* c, const void* reads_ser, uint64_t reads_bytes
 {
     if (!c) return PMM_ERR_INVALID;
     cudaSetDevice(c->device);
-    int rc = flatten_serialized(c, reads_ser, reads_bytes, haps_ser, haps_bytes);
+    JobSource src;
+    int rc = source_from_serialized(c, reads_ser, reads_bytes, haps_ser, haps_bytes, src);
     if (rc) return rc;
     if (num_read) *num_read = (int)c->tmp_roff.size() - 1;
     if (num_hap) *num_hap = (int)c->tmp_hoff.size() - 1;
-    return stage_tmp_single_region(c);
+    return stage_single_region(c, src);
 }
 
 int pmm_get_stats(const pmm_ctx* c, pmm_stats_t* out)
@@ -641,11 +753,12 @@ int pmm_forward_raw_serialized(pmm_ctx* c, const void* reads_ser, uint64_t reads
 {
     if (!c || !out_raw) return PMM_ERR_INVALID;
     cudaSetDevice(c->device);
-    int rc = flatten_serialized(c, reads_ser, reads_bytes, haps_ser, haps_bytes);
+    JobSource src;
+    int rc = source_from_serialized(c, reads_ser, reads_bytes, haps_ser, haps_bytes, src);
     if (rc) return rc;
     if (num_read) *num_read = (int)c->tmp_roff.size() - 1;
     if (num_hap) *num_hap = (int)c->tmp_hoff.size() - 1;
-    if ((rc = stage_tmp_single_region(c))) return rc;
+    if ((rc = stage_single_region(c, src))) return rc;
     if ((rc = pmm_launch(c))) return rc;
     return pmm_fetch_raw(c, out_raw, cap);
 }
@@ -656,11 +769,12 @@ int pmm_forward_log10_serialized(pmm_ctx* c, const void* reads_ser, uint64_t rea
 {
     if (!c || !out) return PMM_ERR_INVALID;
     cudaSetDevice(c->device);
-    int rc = flatten_serialized(c, reads_ser, reads_bytes, haps_ser, haps_bytes);
+    JobSource src;
+    int rc = source_from_serialized(c, reads_ser, reads_bytes, haps_ser, haps_bytes, src);
     if (rc) return rc;
     if (num_read) *num_read = (int)c->tmp_roff.size() - 1;
     if (num_hap) *num_hap = (int)c->tmp_hoff.size() - 1;
-    if ((rc = stage_tmp_single_region(c))) return rc;
+    if ((rc = stage_single_region(c, src))) return rc;
     if ((rc = pmm_launch(c))) return rc;
     return pmm_fetch_log10(c, out, cap, n_fallback);
 }
@@ -670,23 +784,34 @@ int pmm_forward_log10(pmm_ctx* c, const pmm_read_t* reads, int num_read, const p
 {
     if (!c || !reads || !haps || !out || num_read <= 0 || num_hap <= 0) return c ? c->fail(PMM_ERR_INVALID, "bad arguments") : PMM_ERR_INVALID;
     cudaSetDevice(c->device);
+    // every track of every read is one part of the blob, laid out like the wire format (five tracks of a read back to back)
+    JobSource src;
     c->tmp_roff.assign(num_read + 1, 0); c->tmp_hoff.assign(num_hap + 1, 0);
+    c->tmp_rdesc.resize(num_read); c->tmp_hdesc.resize(num_hap);
+    src.read_parts.reserve(5 * (size_t)num_read); src.hap_parts.reserve(num_hap);
+    uint64_t off = 0;
     for (int i = 0; i < num_read; ++i) {
-        if (reads[i].len <= 0) return c->fail(PMM_ERR_INVALID, "read of length 0");
-        c->tmp_roff[i + 1] = c->tmp_roff[i] + (uint32_t)reads[i].len;
+        const pmm_read_t& r = reads[i];
+        if (r.len <= 0 || !r._b || !r._q || !r._i || !r._d || !r._c) return c->fail(PMM_ERR_INVALID, "read of length 0 or null track");
+        const uint32_t len = (uint32_t)r.len;
+        c->tmp_roff[i + 1] = c->tmp_roff[i] + len;
+        c->tmp_rdesc[i] = ReadDesc{(uint32_t)off, len, len};
+        const char* tr[5] = {r._b, r._q, r._i, r._d, r._c};
+        for (int t = 0; t < 5; ++t) src.read_parts.push_back(BlobPart{reinterpret_cast<const uint8_t*>(tr[t]), len});
+        off += 5ull * len;
+        if (off >= (1ull << 31)) return c->fail(PMM_ERR_INVALID, "batch larger than 2 GiB: split it");
     }
+    off = 0;
     for (int i = 0; i < num_hap; ++i) {
-        if (haps[i].len <= 0) return c->fail(PMM_ERR_INVALID, "haplotype of length 0");
-        c->tmp_hoff[i + 1] = c->tmp_hoff[i] + (uint32_t)haps[i].len;
+        if (haps[i].len <= 0 || !haps[i]._b) return c->fail(PMM_ERR_INVALID, "haplotype of length 0 or null");
+        const uint32_t len = (uint32_t)haps[i].len;
+        c->tmp_hoff[i + 1] = c->tmp_hoff[i] + len;
+        c->tmp_hdesc[i] = HapDesc{(uint32_t)off, len};
+        src.hap_parts.push_back(BlobPart{reinterpret_cast<const uint8_t*>(haps[i]._b), len});
+        off += len;
     }
-    for (int t = 0; t < 5; ++t) c->tmp_tracks[t].resize(c->tmp_roff[num_read]);
-    c->tmp_hap.resize(c->tmp_hoff[num_hap]);
-    for (int i = 0; i < num_read; ++i) {
-        const char* src[5] = {reads[i]._b, reads[i]._q, reads[i]._i, reads[i]._d, reads[i]._c};
-        for (int t = 0; t < 5; ++t) memcpy(c->tmp_tracks[t].data() + c->tmp_roff[i], src[t], reads[i].len);
-    }
-    for (int i = 0; i < num_hap; ++i) memcpy(c->tmp_hap.data() + c->tmp_hoff[i], haps[i]._b, haps[i].len);
-    int rc = stage_tmp_single_region(c);
+    src.rdesc = c->tmp_rdesc.data(); src.hdesc = c->tmp_hdesc.data();
+    int rc = stage_single_region(c, src);
     if (rc) return rc;
     if ((rc = pmm_launch(c))) return rc;
     return pmm_fetch_log10(c, out, (uint64_t)num_read * num_hap, n_fallback);

@@ -98,6 +98,16 @@ int plan_job(uint32_t num_read, const uint32_t* read_off, uint32_t num_hap, cons
     auto vkey = [](const Variant& v) { return (v.striped ? 1 << 20 : 0) + v.K * v.W * 64 + v.W; };
     std::stable_sort(gorder.begin(), gorder.end(), [&](uint32_t x, uint32_t y) { return vkey(groups[x].v) > vkey(groups[y].v); });
 
+    {   // upper bound on the task count, so that the vector never reallocates
+        uint64_t est = 0;
+        for (const Group& gr : groups) {
+            const uint32_t nh = plan.regions[gr.region].nhaps;
+            const uint32_t hpt = gr.v.striped ? 1u : std::min(plan.haps_per_task, nh);
+            est += (nh + hpt - 1) / hpt;
+        }
+        plan.tasks.reserve(est);
+        plan.groups.reserve(groups.size());
+    }
     for (uint32_t gi : gorder) {
         const Group& gr = groups[gi];
         const RegionDesc& r = plan.regions[gr.region];

@@ -172,6 +172,12 @@ int  pmm_plan_flat(uint32_t num_read, const uint32_t* read_off, uint32_t num_hap
  * 2 ph2pr f64[128], 3 matchToMatch f64[8256], 4 log10(2^120) f32, 5 log10(2^1020) f64. */
 int  pmm_host_table(int which, void* out, uint64_t capacity_bytes);
 
+/* The host-side tail of PairHMMWorker::getOutput (client/PairHMMWorker.cpp:157-197) for callers that hold the raw floats
+ * and the fallback list (task output blocks 0 and 1): out[k] = (double)(log10f(raw[k]) - log10f(2^120)), then
+ * out[fb_index[j]] = log10(fb_value[j]) - log10(2^1020).  Host libm, several threads. */
+int  pmm_host_finish_log10(const float* raw, uint64_t n, const uint32_t* fb_index, const double* fb_value, uint64_t n_fb,
+                           double* out);
+
 /* Measured FP32 instruction issue rate of this GPU in lane-instructions per second (the roofline denominator of
  * SURVEY.md section 8d; an independent FMUL/FADD stream, ~20 ms).  Also returns the SM clock seen while measuring. */
 int  pmm_measure_fp32_peak(pmm_ctx* ctx, double* lane_instr_per_s, double* sm_mhz);

@@ -2,7 +2,6 @@
 #include "PairHMMWorker.h"
 
 #include <algorithm>
-#include <cmath>
 #include <cstring>
 #include <stdexcept>
 
@@ -12,17 +11,6 @@ namespace {
 
 // threshold of the float result below which the double result is used (MIN_ACCEPTED, client/PairHMMWorker.cpp:176)
 const float kMinAccepted = 1e-28f;
-
-struct Log10Constants {
-  float f; double d;
-  Log10Constants() {
-    // log10f(2^120) and log10(2^1020) as the engine's host tables hold them (Context<float/double>::
-    // LOG10_INITIAL_CONSTANT, xlnx/host/Context.h:109-110,149-150)
-    if (pmm_host_table(4, &f, sizeof f) != PMM_OK || pmm_host_table(5, &d, sizeof d) != PMM_OK)
-      throw std::runtime_error("pmm_host_table failed");
-  }
-};
-const Log10Constants& constants() { static Log10Constants c; return c; }
 
 }  // namespace
 
@@ -40,7 +28,7 @@ void PairHMMWorker::compute() {
 }
 
 void PairHMMWorker::run() {
-  fallback_.clear();
+  fallback_index_.clear(); fallback_value_.clear();
   ran_ = true;
   if (num_read_ == 0 || num_hap_ == 0) return;
 
@@ -66,25 +54,26 @@ void PairHMMWorker::run() {
       uint64_t nfb; memcpy(&nfb, p, sizeof nfb);
       const uint32_t* idx = reinterpret_cast<const uint32_t*>(p + sizeof(uint64_t));
       const double* val = reinterpret_cast<const double*>(p + sizeof(uint64_t) + (nfb * sizeof(uint32_t) + 7) / 8 * 8);
-      for (uint64_t k = 0; k < nfb; ++k) fallback_[(uint64_t)row * num_hap_ + idx[k]] = val[k];
+      for (uint64_t k = 0; k < nfb; ++k) {
+        fallback_index_.push_back((uint32_t)((uint64_t)row * num_hap_ + idx[k]));
+        fallback_value_.push_back(val[k]);
+      }
     }
   }
 }
 
 void PairHMMWorker::getOutput(double* output) {
   if (!ran_) throw std::runtime_error("PairHMMWorker::getOutput() before run()");
-  const Log10Constants& k = constants();
   const size_t total = (size_t)num_read_ * (size_t)num_hap_;
-  for (size_t p = 0; p < total; ++p) {
-    const float v = output_[p];
-    if (v < kMinAccepted) {
-      auto it = fallback_.find(p);
-      if (it == fallback_.end())
-        throw std::runtime_error("PairHMMWorker: float result underflowed but the task returned no double result "
-                                 "(no CPU re-run in this build)");
-      output[p] = log10(it->second) - k.d;                 // double arithmetic (client/PairHMMWorker.cpp:184)
-    } else {
-      output[p] = (double)(log10f(v) - k.f);               // float subtraction, then widened (:190)
-    }
-  }
+  // every result below the threshold must have come back with a double re-run (there is no CPU re-run in this build)
+  size_t under = 0;
+  for (size_t p = 0; p < total; ++p) under += output_[p] < kMinAccepted;
+  if (under != fallback_index_.size())
+    throw std::runtime_error("PairHMMWorker: float results underflowed but the task returned no double results "
+                             "(no CPU re-run in this build)");
+  // log10(d) - log10(2^1020) in double for those (client/PairHMMWorker.cpp:184), (double)(log10f(v) - log10f(2^120))
+  // with a float subtraction for the rest (:190); host libm, on the engine's host worker threads
+  if (pmm_host_finish_log10(output_.data(), total, fallback_index_.data(), fallback_value_.data(),
+                            fallback_index_.size(), output) != PMM_OK)
+    throw std::runtime_error("pmm_host_finish_log10 failed");
 }

@@ -14,7 +14,6 @@
 #define PAIRHMMWORKER_H
 
 #include <cstdint>
-#include <unordered_map>
 #include <vector>
 
 #include "PairHMMClient.h"
@@ -36,7 +35,7 @@ class PairHMMWorker {
   // the reference's CPU fallback entry; throws in this build
   void compute();
 
-  int numRecalculated() const { return (int)fallback_.size(); }
+  int numRecalculated() const { return (int)fallback_index_.size(); }
 
  private:
   PairHMMClient* client_;
@@ -47,7 +46,8 @@ class PairHMMWorker {
   bool ran_;
 
   std::vector<float> output_;                       // raw float likelihoods, read-major
-  std::unordered_map<uint64_t, double> fallback_;   // index in output_ -> double likelihood (scaled by 2^1020)
+  std::vector<uint32_t> fallback_index_;            // positions in output_ that took the double re-run on the GPU
+  std::vector<double>   fallback_value_;            // their double likelihoods (scaled by 2^1020)
 };
 
 #endif
