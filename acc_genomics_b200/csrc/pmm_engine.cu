@@ -153,41 +153,47 @@ int stage_common(pmm_ctx* c, uint32_t num_read, const uint32_t* read_off, uint32
     int rc = ensure_tables(c);
     if (rc) return rc;
 
+    size_t sz_rblob = 0, sz_hblob = 0;
+    for (const BlobPart& bp : src.read_parts) sz_rblob += bp.n;
+    for (const BlobPart& bp : src.hap_parts) sz_hblob += bp.n;
+    const size_t sz_rdesc = sizeof(ReadDesc) * num_read, sz_hdesc = sizeof(HapDesc) * num_hap;
+    const size_t sz_spos = sizeof(uint32_t) * (num_hap + 1), sz_regions = sizeof(RegionDesc) * num_region;
+    size_t sz_tasks = 0, sz_groups = 0, arena = 0;
+    cudaError_t arena_err = cudaSuccess;
+
+    // The planner calls back once it knows how many tasks and groups there are; the input arena is laid out and
+    // reserved then, and the tasks are written straight into pinned memory (no intermediate copy).
     Plan plan;
     {
         std::string perr;
         rc = plan_job(num_read, read_off, num_hap, hap_off, num_region, regions, c->sm_count, c->tasks_per_warp, plan, perr,
-                      c->force.K ? &c->force : nullptr);
+                      c->force.K ? &c->force : nullptr, [&](const Plan& p) -> Task* {
+            sz_tasks = sizeof(Task) * p.num_tasks; sz_groups = sizeof(GroupDesc) * p.groups.size();
+            size_t off = 0;
+            c->off_rblob = off; off = align_up(off + sz_rblob);
+            c->off_rdesc = off; off = align_up(off + sz_rdesc);
+            c->off_hblob = off; off = align_up(off + sz_hblob);
+            c->off_hdesc = off; off = align_up(off + sz_hdesc);
+            c->off_spos = off; off = align_up(off + sz_spos);
+            c->off_tasks = off; off = align_up(off + sz_tasks);
+            c->off_regions = off; off = align_up(off + sz_regions);
+            c->off_groups = off; off = align_up(off + sz_groups);
+            arena = off;
+            if ((arena_err = c->h_in.reserve(arena)) != cudaSuccess) return nullptr;
+            if ((arena_err = c->d_in.reserve(arena)) != cudaSuccess) return nullptr;
+            return reinterpret_cast<Task*>(static_cast<char*>(c->h_in.p) + c->off_tasks);
+        });
+        if (arena_err != cudaSuccess) return c->fail_cuda(arena_err, "input arena");
         if (rc) return c->fail(rc, perr);
     }
-    size_t sz_rblob = 0, sz_hblob = 0;
-    for (const BlobPart& bp : src.read_parts) sz_rblob += bp.n;
-    for (const BlobPart& bp : src.hap_parts) sz_hblob += bp.n;
     const uint32_t max_hap = plan.max_hap_len;
     const uint64_t pairs = plan.pairs, cells = plan.cells;
-    const std::vector<Task>& tasks = plan.tasks;
     const std::vector<RegionDesc>& rdesc = plan.regions;
     c->max_hap_len = max_hap;
     c->f64_rows = pick_f64_rows(plan.max_read_len);
     c->segs = plan.segs;
 
-    // ---- pack the input arena ---------------------------------------------------------------------------------
-    const size_t sz_rdesc = sizeof(ReadDesc) * num_read, sz_hdesc = sizeof(HapDesc) * num_hap;
-    const size_t sz_spos = sizeof(uint32_t) * (num_hap + 1), sz_tasks = sizeof(Task) * tasks.size();
-    const size_t sz_regions = sizeof(RegionDesc) * num_region;
-    const size_t sz_groups = sizeof(GroupDesc) * plan.groups.size();
-    size_t off = 0;
-    c->off_rblob = off; off = align_up(off + sz_rblob);
-    c->off_rdesc = off; off = align_up(off + sz_rdesc);
-    c->off_hblob = off; off = align_up(off + sz_hblob);
-    c->off_hdesc = off; off = align_up(off + sz_hdesc);
-    c->off_spos = off; off = align_up(off + sz_spos);
-    c->off_tasks = off; off = align_up(off + sz_tasks);
-    c->off_regions = off; off = align_up(off + sz_regions);
-    c->off_groups = off; off = align_up(off + sz_groups);
-    const size_t arena = off;
-    PMM_CUDA(c, c->h_in.reserve(arena));
-    PMM_CUDA(c, c->d_in.reserve(arena));
+    // ---- pack the rest of the input arena ---------------------------------------------------------------------
     char* hb = static_cast<char*>(c->h_in.p);
     {
         char* w = hb + c->off_rblob;
@@ -201,7 +207,6 @@ int stage_common(pmm_ctx* c, uint32_t num_read, const uint32_t* read_off, uint32
     uint32_t pos = 0;
     for (uint32_t h = 0; h < num_hap; ++h) { spos[h] = pos; pos += src.hdesc[h].len + 1; }
     spos[num_hap] = pos;                           // final separator
-    memcpy(hb + c->off_tasks, tasks.data(), sz_tasks);
     memcpy(hb + c->off_regions, rdesc.data(), sz_regions);
     memcpy(hb + c->off_groups, plan.groups.data(), sz_groups);
     c->num_groups = (uint32_t)plan.groups.size();
@@ -240,7 +245,7 @@ int stage_common(pmm_ctx* c, uint32_t num_read, const uint32_t* read_off, uint32
                                     static_cast<uint8_t*>(c->d_stream.p) + kStreamFrontPad,
                                     static_cast<float*>(c->d_iyf.p), static_cast<double*>(c->d_iyd.p), ht.ic_f, ht.ic_d, s));
 
-    c->num_read = num_read; c->num_hap = num_hap; c->num_region = num_region; c->num_tasks = (uint32_t)tasks.size();
+    c->num_read = num_read; c->num_hap = num_hap; c->num_region = num_region; c->num_tasks = (uint32_t)plan.num_tasks;
     c->pairs = pairs; c->cells = cells;
     c->regions.assign(regions, regions + num_region);
     c->stats = pmm_stats_t{};

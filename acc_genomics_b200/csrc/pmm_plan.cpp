@@ -30,7 +30,7 @@ Variant pick_variant(int R)
 
 int plan_job(uint32_t num_read, const uint32_t* read_off, uint32_t num_hap, const uint32_t* hap_off,
              uint32_t num_region, const pmm_region_t* regions, int sm_count, int tasks_per_warp,
-             Plan& plan, std::string& err, const Variant* force)
+             Plan& plan, std::string& err, const Variant* force, const std::function<Task*(const Plan&)>& task_dst)
 {
     plan = Plan();
     if (!num_read || !num_hap || !num_region || !read_off || !hap_off || !regions) { err = "empty job"; return PMM_ERR_INVALID; }
@@ -98,16 +98,15 @@ int plan_job(uint32_t num_read, const uint32_t* read_off, uint32_t num_hap, cons
     auto vkey = [](const Variant& v) { return (v.striped ? 1 << 20 : 0) + v.K * v.W * 64 + v.W; };
     std::stable_sort(gorder.begin(), gorder.end(), [&](uint32_t x, uint32_t y) { return vkey(groups[x].v) > vkey(groups[y].v); });
 
-    {   // upper bound on the task count, so that the vector never reallocates
-        uint64_t est = 0;
-        for (const Group& gr : groups) {
-            const uint32_t nh = plan.regions[gr.region].nhaps;
-            const uint32_t hpt = gr.v.striped ? 1u : std::min(plan.haps_per_task, nh);
-            est += (nh + hpt - 1) / hpt;
-        }
-        plan.tasks.reserve(est);
-        plan.groups.reserve(groups.size());
-    }
+    // ---- pass A: group descriptors, launch segments, and the cost of every task (in generation order) -------------
+    // Cost = steps of the wavefront = haplotype bases + separators of the run.
+    plan.groups.reserve(groups.size());
+    std::vector<uint32_t> cost;
+    cost.reserve(std::min<uint64_t>(group_haps, 1u << 24));
+    auto runs_of = [&](const Group& gr, const RegionDesc& r) {
+        const uint32_t hpt = gr.v.striped ? 1u : std::min(plan.haps_per_task, r.nhaps);
+        return (r.nhaps + hpt - 1) / hpt;                             // runs of near-equal length
+    };
     for (uint32_t gi : gorder) {
         const Group& gr = groups[gi];
         const RegionDesc& r = plan.regions[gr.region];
@@ -124,42 +123,58 @@ int plan_job(uint32_t num_read, const uint32_t* read_off, uint32_t num_hap, cons
         gd.param_off = (uint32_t)plan.param_floats;
         plan.param_floats += slots * gd.nstripes * kParamPlanes * kw;
         plan.groups.push_back(gd);
-        const uint32_t hpt = gr.v.striped ? 1u : std::min(plan.haps_per_task, r.nhaps);
-        if (plan.segs.empty() || !(plan.segs.back().v == gr.v)) plan.segs.push_back(LaunchSeg{gr.v, (uint32_t)plan.tasks.size(), 0});
-        const uint32_t nruns = (r.nhaps + hpt - 1) / hpt;          // runs of near-equal length
+        if (plan.segs.empty() || !(plan.segs.back().v == gr.v)) plan.segs.push_back(LaunchSeg{gr.v, (uint32_t)cost.size(), 0});
+        const uint32_t nruns = runs_of(gr, r);
+        const uint32_t* ho = hap_off + r.hap_first;
         for (uint32_t run = 0; run < nruns; ++run) {
             const uint32_t h0 = (uint32_t)((uint64_t)r.nhaps * run / nruns), h1 = (uint32_t)((uint64_t)r.nhaps * (run + 1) / nruns);
-            Task t;
-            for (uint32_t z = 0; z < (uint32_t)kMaxGroups; ++z) {
-                t.read[z] = gr.reads[z];
-                t.out_base[z] = z < gr.n ? r.out_first + (gr.reads[z] - r.read_first) * r.nhaps + h0 : 0;
-            }
-            t.hap_first = r.hap_first + h0; t.nhaps = h1 - h0; t.nreads = gr.n; t.param_off = gd.param_off;
-            plan.tasks.push_back(t);
-            plan.segs.back().task_count++;
+            cost.push_back(ho[h1] - ho[h0] + (h1 - h0));
         }
+        plan.segs.back().task_count += nruns;
+    }
+    plan.num_tasks = cost.size();
+
+    // ---- where the tasks go: the caller's buffer (the engine's pinned staging arena) or plan.tasks ------------------
+    Task* dst = nullptr;
+    if (task_dst) {
+        dst = task_dst(plan);
+        if (!dst) { err = "no room for the task list"; return PMM_ERR_INVALID; }
+    } else {
+        plan.tasks.resize(cost.size());
+        dst = plan.tasks.data();
     }
 
-    // ---- longest tasks first inside each launch: warps pull tasks in order, so the kernel's tail is made of the
-    //      shortest ones.  Cost = steps of the wavefront = haplotype bases + separators of the run.  A counting sort
-    //      on 64 cost classes keeps the planner linear in the number of tasks. ---------------------------------------
-    std::vector<Task> sorted;
-    std::vector<uint32_t> cost;
-    for (const LaunchSeg& seg : plan.segs) {
-        if (seg.task_count < 2) continue;
-        Task* first = plan.tasks.data() + seg.task_first;
-        cost.resize(seg.task_count);
-        uint32_t cmax = 1;
-        for (uint32_t k = 0; k < seg.task_count; ++k) {
-            cost[k] = hap_off[first[k].hap_first + first[k].nhaps] - hap_off[first[k].hap_first] + first[k].nhaps;
-            cmax = std::max(cmax, cost[k]);
+    // ---- pass B: write every task at its final position.  Longest tasks first inside each launch (warps pull tasks
+    //      in order, so the kernel's tail is made of the shortest ones): a counting sort on 64 cost classes, stable,
+    //      linear in the number of tasks, no intermediate copy. -----------------------------------------------------------
+    std::vector<uint32_t> cmax(plan.segs.size(), 1);
+    std::vector<uint32_t> next(plan.segs.size() * 65, 0);              // per launch: write cursor of each cost class
+    for (size_t sg = 0; sg < plan.segs.size(); ++sg) {
+        const LaunchSeg& seg = plan.segs[sg];
+        for (uint32_t k = 0; k < seg.task_count; ++k) cmax[sg] = std::max(cmax[sg], cost[seg.task_first + k]);
+        uint32_t* nx = next.data() + sg * 65;
+        for (uint32_t k = 0; k < seg.task_count; ++k) nx[63 - (uint32_t)((uint64_t)cost[seg.task_first + k] * 63 / cmax[sg]) + 1]++;
+        nx[0] = seg.task_first;
+        for (int b = 0; b < 64; ++b) nx[b + 1] += nx[b];
+    }
+    size_t sg = 0, k = 0;                                               // running launch index and task sequence number
+    for (size_t gk = 0; gk < gorder.size(); ++gk) {
+        const Group& gr = groups[gorder[gk]];
+        const RegionDesc& r = plan.regions[gr.region];
+        const GroupDesc& gd = plan.groups[gk];
+        const uint32_t nruns = runs_of(gr, r);
+        uint32_t rowbase[kMaxGroups];
+        for (uint32_t z = 0; z < (uint32_t)kMaxGroups; ++z) rowbase[z] = z < gr.n ? r.out_first + (gr.reads[z] - r.read_first) * r.nhaps : 0;
+        for (uint32_t run = 0; run < nruns; ++run, ++k) {
+            while (k >= (size_t)plan.segs[sg].task_first + plan.segs[sg].task_count) ++sg;
+            const uint32_t h0 = (uint32_t)((uint64_t)r.nhaps * run / nruns), h1 = (uint32_t)((uint64_t)r.nhaps * (run + 1) / nruns);
+            Task& t = dst[next[sg * 65 + 63 - (uint32_t)((uint64_t)cost[k] * 63 / cmax[sg])]++];
+            for (uint32_t z = 0; z < (uint32_t)kMaxGroups; ++z) {
+                t.read[z] = gr.reads[z];
+                t.out_base[z] = z < gr.n ? rowbase[z] + h0 : 0;
+            }
+            t.hap_first = r.hap_first + h0; t.nhaps = h1 - h0; t.nreads = gr.n; t.param_off = gd.param_off;
         }
-        uint32_t start[65] = {0};
-        for (uint32_t k = 0; k < seg.task_count; ++k) start[63 - (uint32_t)((uint64_t)cost[k] * 63 / cmax) + 1]++;
-        for (int b = 0; b < 64; ++b) start[b + 1] += start[b];
-        sorted.resize(seg.task_count);
-        for (uint32_t k = 0; k < seg.task_count; ++k) sorted[start[63 - (uint32_t)((uint64_t)cost[k] * 63 / cmax)]++] = first[k];
-        std::copy(sorted.begin(), sorted.end(), first);
     }
     return PMM_OK;
 }

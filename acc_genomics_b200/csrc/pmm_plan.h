@@ -1,6 +1,7 @@
 // pmm_plan.h -- host-side planner: cuts a job (regions of reads x haplotypes) into warp-tasks.  Pure C++, no CUDA,
 // so that the CPU test-suite can check it (tests/test_plan.py through pmm_plan_flat).
 #pragma once
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -15,7 +16,8 @@ struct Plan {
     std::vector<RegionDesc> regions;
     std::vector<GroupDesc> groups;      // read groups (reads sharing a warp) and where their row parameters live
     uint64_t param_floats = 0;          // size of the row-parameter buffer
-    std::vector<Task> tasks;            // grouped by variant, see segs
+    std::vector<Task> tasks;            // grouped by variant, see segs (empty when the caller supplied the destination)
+    uint64_t num_tasks = 0;
     std::vector<LaunchSeg> segs;        // one kernel launch each, largest footprint first
     uint64_t pairs = 0, cells = 0;
     uint32_t max_hap_len = 0, max_read_len = 0;
@@ -32,6 +34,8 @@ Variant pick_variant(int R);
 // Returns PMM_OK or PMM_ERR_INVALID with a message.
 int plan_job(uint32_t num_read, const uint32_t* read_off, uint32_t num_hap, const uint32_t* hap_off,
              uint32_t num_region, const pmm_region_t* regions, int sm_count, int tasks_per_warp,
-             Plan& plan, std::string& err, const Variant* force = nullptr);   // force: tuning sweeps only
+             Plan& plan, std::string& err, const Variant* force = nullptr,   // force: tuning sweeps only
+             // called once the task count (plan.num_tasks), groups and launches are known; returns where to write the tasks
+             const std::function<Task*(const Plan&)>& task_dst = nullptr);
 
 }  // namespace pmm
