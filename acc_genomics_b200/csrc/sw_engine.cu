@@ -1,0 +1,205 @@
+// sw_engine.cu -- the C ABI of include/smithwaterman_cuda.h: validation, chunking by backtrack-memory budget, largest
+// pairs first, one kernel launch per chunk, results back.  Stands where the reference has its per-pair CPU loop
+// (/root/reference/htc-sw/host/FalconSW_AVX.cpp:304-313) and the FPGA dispatch (host/sw_host.cpp:13-15).  No CPU path.
+#include "../../include/smithwaterman_cuda.h"
+#include "sw_kernels.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+using namespace sw;
+
+namespace {
+std::string g_sw_create_error;
+
+struct Buf {
+    void* p = nullptr; size_t cap = 0; bool pinned = false;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        release();
+        size_t want = std::max(n, (size_t)4096); want += want / 4;
+        cudaError_t e = pinned ? cudaMallocHost(&p, want) : cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want; else p = nullptr;
+        return e;
+    }
+    void release() { if (p) { if (pinned) cudaFreeHost(p); else cudaFree(p); } p = nullptr; cap = 0; }
+};
+}  // namespace
+
+struct sw_ctx {
+    int device = 0, sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    std::string err;
+    Buf d_seq1, d_seq2, d_pairs, d_bt, d_cigars, d_nelem, d_off, d_score, d_counter;
+    Buf h_stage, h_out;
+    uint64_t bt_budget_words = (1ull << 30);      // 4 GiB of backtrack codes per chunk
+    sw_stats_t stats{};
+    sw_ctx() { h_stage.pinned = true; h_out.pinned = true; }
+    int fail(int code, const std::string& m) { err = m; return code; }
+    int fail_cuda(cudaError_t e, const char* what) { err = std::string(what) + ": " + cudaGetErrorString(e); return SW_ERR_CUDA; }
+};
+
+#define SW_CUDA(ctx, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return (ctx)->fail_cuda(e__, #call); } while (0)
+
+extern "C" {
+
+int sw_create(int device, sw_ctx** out)
+{
+    if (!out) return SW_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        g_sw_create_error = "no CUDA device visible; the aligner has no CPU fallback";
+        return SW_ERR_NO_DEVICE;
+    }
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) device = 0;
+    if (device >= n) { g_sw_create_error = "device index out of range"; return SW_ERR_INVALID; }
+    cudaDeviceProp prop;
+    cudaError_t e;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        g_sw_create_error = cudaGetErrorString(e); return SW_ERR_CUDA;
+    }
+    if (prop.major != 10) { g_sw_create_error = std::string("kernels are built for sm_100a only; device is ") + prop.name; return SW_ERR_NO_DEVICE; }
+    sw_ctx* c = new sw_ctx();
+    c->device = device; c->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) { g_sw_create_error = cudaGetErrorString(e); delete c; return SW_ERR_CUDA; }
+    cudaEventCreate(&c->ev[0]); cudaEventCreate(&c->ev[1]);
+    *out = c;
+    return SW_OK;
+}
+
+void sw_destroy(sw_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (Buf* b : {&c->d_seq1, &c->d_seq2, &c->d_pairs, &c->d_bt, &c->d_cigars, &c->d_nelem, &c->d_off, &c->d_score, &c->d_counter, &c->h_stage, &c->h_out}) b->release();
+    cudaEventDestroy(c->ev[0]); cudaEventDestroy(c->ev[1]);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* sw_last_error(const sw_ctx* c) { return c ? c->err.c_str() : g_sw_create_error.c_str(); }
+
+int sw_get_stats(const sw_ctx* c, sw_stats_t* out)
+{
+    if (!c || !out) return SW_ERR_INVALID;
+    *out = c->stats;
+    return SW_OK;
+}
+
+int sw_align_batch(sw_ctx* c, uint32_t n_pairs,
+                   const uint8_t* seq1_bytes, const uint32_t* seq1_start, const uint32_t* seq1_len,
+                   const uint8_t* seq2_bytes, const uint32_t* seq2_start, const uint32_t* seq2_len,
+                   int w_match, int w_mismatch, int w_open, int w_extend, int overhang_strategy,
+                   uint32_t cigar_cap, sw_cigar_elem_t* cigars, int32_t* n_elem, int32_t* alignment_offset, int32_t* score)
+{
+    if (!c) return SW_ERR_INVALID;
+    if (!n_pairs) return SW_OK;
+    if (!seq1_bytes || !seq1_start || !seq1_len || !seq2_bytes || !seq2_start || !seq2_len || !cigars || !n_elem || !alignment_offset)
+        return c->fail(SW_ERR_INVALID, "null argument");
+    if (overhang_strategy < 0 || overhang_strategy > 3) return c->fail(SW_ERR_INVALID, "unknown overhang strategy");
+    if (!cigar_cap) return c->fail(SW_ERR_INVALID, "cigar_cap must be positive");
+    const auto t0 = std::chrono::steady_clock::now();
+    cudaSetDevice(c->device);
+    cudaStream_t s = c->stream;
+
+    uint64_t ext1 = 0, ext2 = 0, cells = 0;
+    for (uint32_t p = 0; p < n_pairs; ++p) {
+        if (!seq1_len[p] || !seq2_len[p]) return c->fail(SW_ERR_INVALID, "sequence of length 0");
+        if (seq1_len[p] > (uint32_t)kMaxLen || seq2_len[p] > (uint32_t)kMaxLen) return c->fail(SW_ERR_INVALID, "sequence longer than 4095 bases");
+        ext1 = std::max<uint64_t>(ext1, (uint64_t)seq1_start[p] + seq1_len[p]);
+        ext2 = std::max<uint64_t>(ext2, (uint64_t)seq2_start[p] + seq2_len[p]);
+        cells += (uint64_t)seq1_len[p] * seq2_len[p];
+    }
+    if (ext1 >= (1ull << 31) || ext2 >= (1ull << 31)) return c->fail(SW_ERR_INVALID, "sequence blobs larger than 2 GiB");
+
+    // largest pairs first: warps pull pairs in order, the tail of the launch is made of the small ones
+    std::vector<uint32_t> order(n_pairs);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+        return (uint64_t)seq1_len[x] * seq2_len[x] > (uint64_t)seq1_len[y] * seq2_len[y]; });
+
+    SW_CUDA(c, c->d_seq1.reserve(ext1)); SW_CUDA(c, c->d_seq2.reserve(ext2));
+    SW_CUDA(c, c->h_stage.reserve(ext1 + ext2 + sizeof(PairDesc) * (size_t)n_pairs + 64));
+    SW_CUDA(c, c->d_pairs.reserve(sizeof(PairDesc) * (size_t)n_pairs));
+    SW_CUDA(c, c->d_cigars.reserve(sizeof(int2) * (size_t)n_pairs * cigar_cap));
+    SW_CUDA(c, c->d_nelem.reserve(sizeof(int32_t) * (size_t)n_pairs));
+    SW_CUDA(c, c->d_off.reserve(sizeof(int32_t) * (size_t)n_pairs));
+    SW_CUDA(c, c->d_score.reserve(sizeof(int32_t) * (size_t)n_pairs));
+    SW_CUDA(c, c->d_counter.reserve(256));
+    char* hs = static_cast<char*>(c->h_stage.p);
+    memcpy(hs, seq1_bytes, ext1); memcpy(hs + ext1, seq2_bytes, ext2);
+    SW_CUDA(c, cudaMemcpyAsync(c->d_seq1.p, hs, ext1, cudaMemcpyHostToDevice, s));
+    SW_CUDA(c, cudaMemcpyAsync(c->d_seq2.p, hs + ext1, ext2, cudaMemcpyHostToDevice, s));
+
+    // chunks: consecutive pairs (in size order) whose backtrack matrices fit the budget
+    PairDesc* hp = reinterpret_cast<PairDesc*>(hs + ((ext1 + ext2 + 15) & ~(size_t)15));
+    std::vector<std::pair<uint32_t, uint32_t>> chunks;     // [first, last) in `order`
+    uint64_t max_words = 0;
+    for (uint32_t k = 0; k < n_pairs;) {
+        uint64_t words = 0; const uint32_t first = k;
+        while (k < n_pairs) {
+            const uint32_t p = order[k];
+            const uint32_t stride = (seq2_len[p] + 7) / 8;
+            const uint64_t w = (uint64_t)seq1_len[p] * stride;
+            if (k > first && words + w > c->bt_budget_words) break;
+            hp[k] = PairDesc{seq1_start[p], seq1_len[p], seq2_start[p], seq2_len[p], words, stride, p};
+            words += w; ++k;
+        }
+        chunks.emplace_back(first, k);
+        max_words = std::max(max_words, words);
+    }
+    SW_CUDA(c, c->d_bt.reserve(max_words * sizeof(uint32_t)));
+    SW_CUDA(c, cudaMemcpyAsync(c->d_pairs.p, hp, sizeof(PairDesc) * (size_t)n_pairs, cudaMemcpyHostToDevice, s));
+
+    uint32_t launches = 0;
+    SW_CUDA(c, cudaEventRecord(c->ev[0], s));
+    for (const auto& ch : chunks) {
+        Args a{};
+        a.seq1 = static_cast<uint8_t*>(c->d_seq1.p); a.seq2 = static_cast<uint8_t*>(c->d_seq2.p);
+        a.pairs = static_cast<PairDesc*>(c->d_pairs.p) + ch.first; a.npairs = ch.second - ch.first;
+        a.counter = static_cast<uint32_t*>(c->d_counter.p);
+        a.bt = static_cast<uint32_t*>(c->d_bt.p);
+        a.match = w_match; a.mismatch = w_mismatch; a.open = w_open; a.extend = w_extend; a.strategy = overhang_strategy;
+        a.cigar_cap = cigar_cap; a.cigars = static_cast<int2*>(c->d_cigars.p);
+        a.n_elem = static_cast<int32_t*>(c->d_nelem.p); a.offset = static_cast<int32_t*>(c->d_off.p);
+        a.score = static_cast<int32_t*>(c->d_score.p);
+        a.max_l1 = 0; a.max_l2 = 0;
+        for (uint32_t k = ch.first; k < ch.second; ++k) { a.max_l1 = std::max(a.max_l1, hp[k].l1); a.max_l2 = std::max(a.max_l2, hp[k].l2); }
+        SW_CUDA(c, cudaMemsetAsync(a.counter, 0, sizeof(uint32_t), s));
+        SW_CUDA(c, launch_align(a, c->sm_count, s, nullptr));
+        ++launches;
+    }
+    SW_CUDA(c, cudaEventRecord(c->ev[1], s));
+
+    const size_t sz_c = sizeof(int2) * (size_t)n_pairs * cigar_cap, sz_i = sizeof(int32_t) * (size_t)n_pairs;
+    SW_CUDA(c, c->h_out.reserve(sz_c + 3 * sz_i));
+    char* ho = static_cast<char*>(c->h_out.p);
+    SW_CUDA(c, cudaMemcpyAsync(ho, c->d_cigars.p, sz_c, cudaMemcpyDeviceToHost, s));
+    SW_CUDA(c, cudaMemcpyAsync(ho + sz_c, c->d_nelem.p, sz_i, cudaMemcpyDeviceToHost, s));
+    SW_CUDA(c, cudaMemcpyAsync(ho + sz_c + sz_i, c->d_off.p, sz_i, cudaMemcpyDeviceToHost, s));
+    SW_CUDA(c, cudaMemcpyAsync(ho + sz_c + 2 * sz_i, c->d_score.p, sz_i, cudaMemcpyDeviceToHost, s));
+    SW_CUDA(c, cudaStreamSynchronize(s));
+    static_assert(sizeof(sw_cigar_elem_t) == sizeof(int2), "cigar element layout");
+    memcpy(cigars, ho, sz_c);
+    memcpy(n_elem, ho + sz_c, sz_i);
+    memcpy(alignment_offset, ho + sz_c + sz_i, sz_i);
+    if (score) memcpy(score, ho + sz_c + 2 * sz_i, sz_i);
+
+    c->stats = sw_stats_t{};
+    c->stats.pairs = n_pairs; c->stats.cells = cells; c->stats.bytes_backtrack = max_words * sizeof(uint32_t);
+    c->stats.kernel_launches = launches; c->stats.chunks = (uint32_t)chunks.size();
+    cudaEventElapsedTime(&c->stats.ms_kernel, c->ev[0], c->ev[1]);
+    c->stats.ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return SW_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,45 @@
+// sw_kernels.cuh -- device-side data model of the Smith-Waterman aligner (shared by sw_kernels.cu and sw_engine.cu).
+//
+// Layout in HBM for one chunk of pairs:
+//   seq1 / seq2 blobs   bytes; pair p is seq1[s1 .. s1+l1) (reference, matrix rows) against seq2[s2 .. s2+l2) (alternate, columns)
+//   backtrack           per pair l1 rows of `bt_stride` 32-bit words, 8 cells per word, 4 bits per cell: bits 0-1 the move
+//                       (0 diagonal, 1 insertion = left, 2 deletion = up), bit 2 "the insertion was an extension", bit 3 "the
+//                       deletion was an extension" -- the codes of /root/reference/htc-sw/intel_avx/smithwaterman_common.h:18-22
+//   cigars              per pair `cigar_cap` (length, state) elements, forward order; n_elem, alignment offset, score
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace sw {
+
+constexpr int kRowsPerLane = 4;          // a block of rows = 32 lanes x 4 rows
+constexpr int kWarpsPerCta = 4;
+constexpr int kMaxLen = 4095;
+
+struct PairDesc {
+    uint32_t s1, l1, s2, l2;
+    uint64_t bt_off;                     // first word of the pair's backtrack matrix
+    uint32_t bt_stride;                  // words per row = ceil(l2 / 8)
+    uint32_t index;                      // position of the pair in the caller's arrays
+};
+
+struct Args {
+    const uint8_t*  seq1;
+    const uint8_t*  seq2;
+    const PairDesc* pairs;
+    uint32_t        npairs;
+    uint32_t*       counter;             // work-queue cursor, zero at launch
+    uint32_t*       bt;
+    int             match, mismatch, open, extend, strategy;
+    uint32_t        cigar_cap;
+    int2*           cigars;              // (length, state)
+    int32_t*        n_elem;
+    int32_t*        offset;
+    int32_t*        score;
+    uint32_t        max_l1, max_l2;      // of the chunk: sizes the per-warp shared memory
+};
+
+size_t smem_bytes_per_warp(uint32_t max_l1, uint32_t max_l2);
+cudaError_t launch_align(const Args& a, int sm_count, cudaStream_t s, int* ctas_out);
+
+}  // namespace sw

@@ -114,3 +114,72 @@ def reference(fma: bool = False) -> _Lib | None:
             build()
         _cache[key] = _Lib(p, key, "ref_batch") if os.path.exists(p) else None
     return _cache[key]
+
+
+# ---- Smith-Waterman ------------------------------------------------------------------
+SW_SOFTCLIP, SW_INDEL, SW_LEADING_INDEL, SW_IGNORE = 0, 1, 2, 3
+SW_WEIGHTS = (200, -150, -260, -11)        # W_MATCH, W_MISMATCH, W_OPEN, W_EXTEND (htc-sw/host/common.h:15-18)
+_CIGAR_CAP = 4096
+
+
+class _SwLib:
+    """align(ref, alt, strategy, weights) -> (offset, [(length, state), ...]); states 0 M, 1 I, 2 D, 4 S."""
+
+    def __init__(self, path: str, kind: str):
+        self.kind = kind
+        self.lib = C.CDLL(path)
+        ip = C.POINTER(C.c_int)
+        if kind == "port":
+            f = self.lib.sw_oracle_align
+            f.restype = C.c_int
+            f.argtypes = [C.c_int] * 4 + [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, ip, ip, C.c_int, ip, ip]
+        else:
+            f = self.lib.ref_sw_gkl
+            f.restype = C.c_int
+            f.argtypes = [C.c_int] * 4 + [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, ip, ip, C.c_int, ip]
+            g = self.lib.ref_sw_falcon
+            g.restype = C.c_int
+            g.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, ip, ip, C.c_int, ip, ip]
+        self._len = (C.c_int * _CIGAR_CAP)()
+        self._st = (C.c_int * _CIGAR_CAP)()
+
+    def align(self, ref: bytes, alt: bytes, strategy: int, weights=SW_WEIGHTS):
+        n = C.c_int()
+        if self.kind == "port":
+            sc = C.c_int()
+            off = self.lib.sw_oracle_align(*weights, ref, len(ref), alt, len(alt), strategy, self._len, self._st, _CIGAR_CAP,
+                                           C.byref(n), C.byref(sc))
+        else:
+            off = self.lib.ref_sw_gkl(*weights, ref, len(ref), alt, len(alt), strategy, self._len, self._st, _CIGAR_CAP, C.byref(n))
+        return off, [(self._len[k], self._st[k]) for k in range(n.value)]
+
+    def align_falcon(self, ref: bytes, alt: bytes, strategy: int, option: int = 1):
+        """Falcon's own SWPairwiseAlignmentOneBatch (fixed weights); option 1 = scalar baseline, 0 = its SIMD variant."""
+        n, rc = C.c_int(), C.c_int()
+        off = self.lib.ref_sw_falcon(ref, len(ref), alt, len(alt), strategy, option, self._len, self._st, _CIGAR_CAP,
+                                     C.byref(n), C.byref(rc))
+        return rc.value, off, [(self._len[k], self._st[k]) for k in range(n.value)]
+
+
+def sw_port() -> "_SwLib":
+    p = os.path.join(_HERE, "liboracle.so")
+    if not os.path.exists(p):
+        build()
+    return _SwLib(p, "port")
+
+
+def sw_reference():
+    """The reference's own Smith-Waterman (oracle/_ref/libsw_ref.so); None if absent or the CPU lacks AVX2."""
+    p = os.path.join(_HERE, "_ref", "libsw_ref.so")
+    if not os.path.exists(p):
+        if os.path.isdir("/root/reference/htc-sw"):
+            build()
+        if not os.path.exists(p):
+            return None
+    try:
+        with open("/proc/cpuinfo") as f:
+            if "avx2" not in f.read():
+                return None
+    except OSError:
+        pass
+    return _SwLib(p, "reference")
