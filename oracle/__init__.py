@@ -145,6 +145,8 @@ class _SwLib:
 
     def align(self, ref: bytes, alt: bytes, strategy: int, weights=SW_WEIGHTS):
         n = C.c_int()
+        if self.kind != "port" and (len(ref) > 1536 or len(alt) > 1536):
+            raise ValueError("the reference's Smith-Waterman has fixed 1536-base buffers (MAX_SEQ_LEN); use sw_port()")
         if self.kind == "port":
             sc = C.c_int()
             off = self.lib.sw_oracle_align(*weights, ref, len(ref), alt, len(alt), strategy, self._len, self._st, _CIGAR_CAP,

@@ -65,9 +65,13 @@ def test_block_boundaries_and_long_sequences(aligner, sw_checker):
             pairs += sw.haplotype_pairs(n1 * 131 + n2, 1, ref_len=n1, per_ref=1, trim=0.0)
             r, a = pairs[-1]
             pairs[-1] = (r, (a * 3)[:n2] if len(a) < n2 else a[:n2])
-    pairs += sw.haplotype_pairs(99, 3, ref_len=(1500, 1536), per_ref=3)
+    pairs += [(r[:1536], a[:1536]) for r, a in sw.haplotype_pairs(99, 3, ref_len=(1500, 1536), per_ref=3)]
     for st in range(4):
         check(aligner, sw_checker, pairs, st)
+    # beyond the reference's fixed buffers (MAX_SEQ_LEN = 1536) only the C restatement can check
+    long = sw.haplotype_pairs(98, 2, ref_len=(2500, 3000), per_ref=2)
+    check(aligner, oracle.sw_port(), long, 0)
+    check(aligner, oracle.sw_port(), long, 3)
 
 
 def test_repeats_and_ties(aligner, sw_checker):
@@ -100,3 +104,26 @@ def test_invalid_inputs(aligner):
     with pytest.raises(sw.SwError):
         aligner.align([(b"A" * 5000, b"ACGT")], 0)
     assert aligner.align([], 0) == []
+
+
+def test_cpp_host_layer(built, sw_checker, tmp_path):
+    """htc-sw/: the reference's host entry points (SWPairwiseAlignmentMultiBatch, FalconSWFPGA_run, single pair) on the GPU --
+    the self-checking bench, and a pair file whose output is compared with the oracle."""
+    import subprocess
+    root = ROOT
+    exe = os.path.join(root, "htc-sw", "bin", "sw_host")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.join(root, "htc-sw")], check=True, stdout=subprocess.DEVNULL)
+    p = subprocess.run([exe, "cuda:0"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "0 failures" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+    pairs = sw.haplotype_pairs(31, 40, ref_len=(50, 400), per_ref=5)
+    lines, want = [], []
+    for k, (r, a) in enumerate(pairs):
+        st = k % 4
+        lines.append(f"{st} {r.decode()} {a.decode()}")
+        off, cig = sw_checker.align(r, a, st)
+        want.append(f"{off} {sw.cigar_string(cig)}")
+    (tmp_path / "pairs.txt").write_text("\n".join(lines) + "\n")
+    p = subprocess.run([exe, "cuda:0", str(tmp_path / "pairs.txt")], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr
+    assert p.stdout.split("\n")[:len(want)] == want
