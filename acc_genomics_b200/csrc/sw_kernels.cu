@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sw_align_kernel(const Args 
             int Hrow[K], E[K];
             uint32_t acc[K];
             int c1[K];
+            uint32_t* brow[K];                                         // backtrack row of each of the lane's rows
             #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const int i = ifirst + k;
@@ -100,53 +101,88 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sw_align_kernel(const Args 
                 Hrow[k] = indel ? open + (i - 1) * extend : 0;       // H[i][0]
                 E[k] = kLowInit;
                 acc[k] = 0;
+                brow[k] = i <= nrow ? B + (size_t)(i - 1) * stride : nullptr;
             }
             int prev_up = (ifirst - 1 == 0) ? 0 : (indel ? open + (ifirst - 2) * extend : 0);   // H[ifirst-1][0]
             int lastF = kLowInit;
+            // the lane and row that hold the matrix's last row (for the end-cell search); -1 if not in this block
+            const int own_k = (nrow >= ifirst && nrow < ifirst + K) ? nrow - ifirst : -1;
+
+            // one step: column j of this lane's K rows.  MAIN_CODE (PairWiseSW.h:4-40): same comparisons, same order;
+            // the max-with-predicate forms (__vibmax_s32) give each maximum and its tie-break bit in one instruction.
+            auto step = [&](const int j, int upH, int upF) {
+                const int c2 = (int)sm.alt[j - 1];
+                int diag = prev_up;
+                prev_up = upH;
+                int hup = upH, fup = upF;
+                const int sh = 4 * ((j - 1) & 7);
+                const bool flush = ((j - 1) & 7) == 7 || j == ncol;
+                #pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int hleft = Hrow[k];
+                    bool ins_ext, del_ext, keep1, keep2;
+                    const int e11 = __vibmax_s32(E[k] + extend, hleft + open, &ins_ext);     // ins_ext = !(open > extend): extension on ties
+                    const int f11 = __vibmax_s32(fup + extend, hup + open, &del_ext);
+                    const int m11 = diag + (c1[k] == c2 ? match : mismatch);
+                    int h11 = max(kMinCutoff, m11);
+                    h11 = __vibmax_s32(h11, e11, &keep1);                                    // keep1 = !(e11 > h11)
+                    h11 = __vibmax_s32(h11, f11, &keep2);                                    // keep2 = !(f11 > h11)
+                    const int mv = keep2 ? (keep1 ? 0 : kInsert) : kDelete;
+                    const int code = mv | (ins_ext ? kInsertExt : 0) | (del_ext ? kDeleteExt : 0);
+                    diag = hleft;
+                    Hrow[k] = h11; E[k] = e11; hup = h11; fup = f11;
+                    acc[k] |= (uint32_t)code << sh;
+                    if (flush) {
+                        if (brow[k]) brow[k][(j - 1) >> 3] = acc[k];
+                        acc[k] = 0;
+                    }
+                }
+                lastF = fup;
+                if (own_k >= 0) {
+                    int v = Hrow[0];
+                    #pragma unroll
+                    for (int k = 1; k < K; ++k) v = own_k == k ? Hrow[k] : v;
+                    sm.lastrow[j] = v;
+                }
+                if (lane == 31) { sm.carryH[j] = Hrow[K - 1]; sm.carryF[j] = lastF; }
+            };
+
             const int steps = ncol + 31;
+            int t = 0;
+            // fill: lanes join one per step
             #pragma unroll 1
-            for (int t = 0; t < steps; ++t) {
+            for (; t < min(31, steps); ++t) {
                 int upH = __shfl_up_sync(0xffffffffu, Hrow[K - 1], 1);
                 int upF = __shfl_up_sync(0xffffffffu, lastF, 1);
                 const int j = t - lane + 1;
                 if (j >= 1 && j <= ncol) {
                     if (lane == 0) { upH = sm.carryH[j]; upF = sm.carryF[j]; }
-                    const int c2 = (int)sm.alt[j - 1];
-                    int diag = prev_up;
-                    prev_up = upH;
-                    int hup = upH, fup = upF;
-                    const int sh = 4 * ((j - 1) & 7);
-                    const bool flush = ((j - 1) & 7) == 7 || j == ncol;
-                    #pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        const int hleft = Hrow[k];
-                        // MAIN_CODE (PairWiseSW.h:4-40), same comparisons in the same order
-                        const int ext_h = E[k] + extend, open_h = hleft + open;
-                        const int e11 = max(open_h, ext_h);
-                        int bt = open_h > ext_h ? 0 : kInsertExt;
-                        const int ext_v = fup + extend, open_v = hup + open;
-                        const int f11 = max(ext_v, open_v);
-                        if (!(open_v > ext_v)) bt |= kDeleteExt;
-                        const int m11 = diag + (c1[k] == c2 ? match : mismatch);
-                        int h11 = max(kMinCutoff, m11);
-                        int mv = 0;
-                        if (e11 > h11) { mv = kInsert; h11 = e11; }
-                        if (f11 > h11) { mv = kDelete; h11 = f11; }
-                        diag = hleft;
-                        Hrow[k] = h11; E[k] = e11; hup = h11; fup = f11;
-                        acc[k] |= (uint32_t)(bt | mv) << sh;
-                        const int i = ifirst + k;
-                        if (i <= nrow) {
-                            if (flush) B[(size_t)(i - 1) * stride + ((j - 1) >> 3)] = acc[k];
-                            if (j == ncol) sm.lastcol[i] = h11;
-                            if (i == nrow) sm.lastrow[j] = h11;
-                        }
-                        if (flush) acc[k] = 0;
-                    }
-                    lastF = fup;
-                    if (lane == 31) { sm.carryH[j] = Hrow[K - 1]; sm.carryF[j] = lastF; }
+                    step(j, upH, upF);
                 }
             }
+            // steady: every lane has a column
+            #pragma unroll 1
+            for (; t < ncol; ++t) {
+                int upH = __shfl_up_sync(0xffffffffu, Hrow[K - 1], 1);
+                int upF = __shfl_up_sync(0xffffffffu, lastF, 1);
+                const int j = t - lane + 1;
+                if (lane == 0) { upH = sm.carryH[j]; upF = sm.carryF[j]; }
+                step(j, upH, upF);
+            }
+            // drain
+            #pragma unroll 1
+            for (; t < steps; ++t) {
+                int upH = __shfl_up_sync(0xffffffffu, Hrow[K - 1], 1);
+                int upF = __shfl_up_sync(0xffffffffu, lastF, 1);
+                const int j = t - lane + 1;
+                if (j >= 1 && j <= ncol) {
+                    if (lane == 0) { upH = sm.carryH[j]; upF = sm.carryF[j]; }
+                    step(j, upH, upF);
+                }
+            }
+            // H[i][ncol] of the lane's rows: still in registers, nothing touched them after the last column
+            #pragma unroll
+            for (int k = 0; k < K; ++k) if (ifirst + k <= nrow) sm.lastcol[ifirst + k] = Hrow[k];
             __syncwarp();
         }
 
@@ -196,13 +232,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sw_align_kernel(const Args 
                 for (int w = 0; w < 8; ++w) {
                     uint32_t v = 0;
                     if (row >= 1 && (uint32_t)(cw0 + w) < stride) v = __ldcg(B + (size_t)(row - 1) * stride + cw0 + w);
-                    sm.tile[lane * 8 + w] = v;
+                    sm.tile[w * 32 + lane] = v;
                 }
             }
             __syncwarp();
             if (lane == 0) {
                 while (ti > 0 && tj > 0 && ai - ti < 32 && ((tj - 1) >> 3) >= cw0) {
-                    const int btr = (int)((sm.tile[(ai - ti) * 8 + ((tj - 1) >> 3) - cw0] >> (4 * ((tj - 1) & 7))) & 15u);
+                    const int btr = (int)((sm.tile[(((tj - 1) >> 3) - cw0) * 32 + (ai - ti)] >> (4 * ((tj - 1) & 7))) & 15u);
                     if (state == kInsertExt) { --tj; emit(kInsert, 1); state = btr & kInsertExt; }
                     else if (state == kDeleteExt) { --ti; emit(kDelete, 1); state = btr & kDeleteExt; }
                     else {

@@ -57,7 +57,7 @@ def test_all_small_lengths(aligner, sw_checker, strategy):
 
 
 def test_block_boundaries_and_long_sequences(aligner, sw_checker):
-    """Row counts around the 128-row block (32 lanes x 4 rows), column counts around the 8-cell backtrack word and the
+    """Row counts around the 128- and 256-row blocks (32 lanes x 4 or 8 rows), column counts around the 8-cell backtrack word and the
     64-column traceback tile, and the reference's maximum (1536)."""
     pairs = []
     for n1 in (127, 128, 129, 255, 256, 257):
