@@ -353,7 +353,11 @@ def _main(args, real_stdout):
             "gpu_launches": int(st["kernel_launches"]) * args.steps,
             "clocks": clocks,
             "roofline": {"bound": "fp32_issue", "kernel": "pmm_forward_kernel<float,K,W> (float pass)", "achieved": achieved, "peak": peak,
-                         "unit": "T FP32 lane-instr/s", "frac": achieved / peak, "traffic": None,
+                         "unit": "T FP32 lane-instr/s", "frac": achieved / peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one float-pass launch on this workload, from the
+                         # ncu --set full capture under profiles/ (r01h): the kernel is nowhere near a memory bound
+                         "traffic": 5702144 if (args.config == 2 and args.scale == 1.0) else None,
+                         "traffic_source": "profiles/r01h_f32_K19W8_ncu_metrics.txt (5.70 MB read, 0 written per launch; algorithmic input 1.2 MB + 4.9 MB row parameters)",
                          "kernel_ms": f32_ms_avg, "kernel_gcups": f32_cells_per_s * 1e-9,
                          "kernel_ms_note": "CUDA events around read_params_kernel + the float forward launch(es) on the engine's stream",
                          "fallback_pass_ms": float(np.mean(fb_ms)),
