@@ -463,35 +463,8 @@ __global__ void build_stream_kernel(const uint8_t* __restrict__ blob, const HapD
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Fallback compaction: raw < 1e-28f  ->  single-pair task for the double kernel (PairHMMWorker.cpp:176).
+// Second-level list: double results so small that x86 flush-to-zero may have mattered (see launch_compact_tiny).
 // ---------------------------------------------------------------------------------------------------------
-__global__ void compact_fallback_kernel(const float* __restrict__ raw, const RegionDesc* __restrict__ regions,
-                                        uint32_t nregions, uint32_t total_pairs, Task* __restrict__ fb_tasks,
-                                        uint32_t* __restrict__ fb_out_index, uint32_t* fb_count, uint32_t cap)
-{
-    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total_pairs) return;
-    const float v = raw[idx];
-    if (!(v < 1e-28f)) return;                    // float compare, NaN -> false, exactly the reference's test
-    // locate the region by binary search on out_first
-    uint32_t lo = 0, hi = nregions - 1;
-    while (lo < hi) {
-        const uint32_t mid = (lo + hi + 1) >> 1;
-        if (regions[mid].out_first <= idx) lo = mid; else hi = mid - 1;
-    }
-    const RegionDesc r = regions[lo];
-    const uint32_t local = idx - r.out_first;
-    const uint32_t slot = atomicAdd(fb_count, 1u);
-    if (slot >= cap) return;
-    Task t;
-    t.read[0] = r.read_first + local / r.nhaps; t.read[1] = t.read[2] = t.read[3] = 0;
-    t.out_base[0] = slot; t.out_base[1] = t.out_base[2] = t.out_base[3] = 0;
-    t.hap_first = r.hap_first + local % r.nhaps;
-    t.nhaps = 1; t.nreads = 1; t.param_off = 0;
-    fb_tasks[slot] = t;
-    fb_out_index[slot] = idx;
-}
-
 __global__ void compact_tiny_kernel(const double* __restrict__ dres, const Task* __restrict__ fb_tasks,
                                     const uint32_t* __restrict__ fb_count, double threshold,
                                     Task* __restrict__ tiny_tasks, uint32_t* tiny_count)
@@ -631,16 +604,6 @@ cudaError_t launch_read_params(const uint8_t* read_blob, const ReadDesc* reads, 
 {
     if (ngroups == 0) return cudaSuccess;
     read_params_kernel<<<ngroups, 128, 0, s>>>(read_blob, reads, groups, ngroups, tab, params);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_compact_fallback(const float* raw, const RegionDesc* regions, uint32_t nregions,
-                                    uint32_t total_pairs, Task* fb_tasks, uint32_t* fb_out_index,
-                                    uint32_t* fb_count, uint32_t fb_capacity, cudaStream_t s)
-{
-    if (total_pairs == 0) return cudaSuccess;
-    compact_fallback_kernel<<<(total_pairs + 255) / 256, 256, 0, s>>>(raw, regions, nregions, total_pairs, fb_tasks,
-                                                                     fb_out_index, fb_count, fb_capacity);
     return cudaGetLastError();
 }
 

@@ -89,11 +89,6 @@ cudaError_t launch_build_stream(const uint8_t* hap_blob, const HapDesc* haps, co
 cudaError_t launch_read_params(const uint8_t* read_blob, const ReadDesc* reads, const GroupDesc* groups, uint32_t ngroups,
                                const DeviceTables& tab, float* params, cudaStream_t s);
 
-// Scan raw[] for values below 1e-28f and append one single-pair Task per hit (read, hap, slot) to fb_tasks.
-// (Not used by the engine any more -- the float kernel appends inline -- kept for the standalone tests/tools.)
-cudaError_t launch_compact_fallback(const float* raw, const RegionDesc* regions, uint32_t nregions,
-                                    uint32_t total_pairs, Task* fb_tasks, uint32_t* fb_out_index,
-                                    uint32_t* fb_count, uint32_t fb_capacity, cudaStream_t s);
 // Second-level scan: double results below `threshold` are re-queued for the flush-emulating kernel.
 cudaError_t launch_compact_tiny(const double* dres, const Task* fb_tasks, const uint32_t* fb_count,
                                 double threshold, Task* tiny_tasks, uint32_t* tiny_count, cudaStream_t s);
