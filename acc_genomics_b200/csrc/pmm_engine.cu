@@ -865,10 +865,10 @@ int pmm_measure_fp32_peak(pmm_ctx* c, double* lane_instr_per_s, double* sm_mhz)
 {
     if (!c || !lane_instr_per_s) return PMM_ERR_INVALID;
     cudaSetDevice(c->device);
-    const int ctas = c->sm_count * 8, iters = 4000;
+    const int ctas = c->sm_count * 8, iters = 500;
     PMM_CUDA(c, c->d_probe.reserve(sizeof(float) * ctas * 256));
     cudaStream_t s = c->stream;
-    PMM_CUDA(c, launch_fp32_probe(static_cast<float*>(c->d_probe.p), 200, ctas, s));
+    PMM_CUDA(c, launch_fp32_probe(static_cast<float*>(c->d_probe.p), 25, ctas, s));
     double best = 0;
     for (int rep = 0; rep < 3; ++rep) {
         PMM_CUDA(c, cudaEventRecord(c->ev[3], s));
@@ -877,7 +877,7 @@ int pmm_measure_fp32_peak(pmm_ctx* c, double* lane_instr_per_s, double* sm_mhz)
         PMM_CUDA(c, cudaEventRecord(e1, s));
         PMM_CUDA(c, cudaEventSynchronize(e1));
         float ms = 0; cudaEventElapsedTime(&ms, c->ev[3], e1); cudaEventDestroy(e1);
-        const double ops = (double)ctas * 256 * iters * 64.0;
+        const double ops = (double)ctas * 256 * iters * 512.0;
         best = std::max(best, ops / (ms * 1e-3));
     }
     *lane_instr_per_s = best;

@@ -349,6 +349,8 @@ def _main(args, real_stdout):
         f32_cells_per_s = cells / (f32_ms_avg * 1e-3)
         achieved = f32_cells_per_s * 12 * 1e-12
         peak = peak_lane_instr * 1e-12
+        sms = torch.cuda.get_device_properties(local).multi_processor_count
+        nominal_peak = sms * 128 * clocks["sm_mhz"] * 1e6 * 1e-12 if clocks.get("sm_mhz") else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -379,6 +381,8 @@ def _main(args, real_stdout):
                          "peak_source": "measured live: independent FMUL/FADD streams (pmm_measure_fp32_peak); "
                                         "MEASURED_PEAKS.json has no FP32 figure",
                          "frac_flop_convention": achieved / (2 * peak),
+                         "nominal_peak": nominal_peak, "frac_vs_nominal": (achieved / nominal_peak) if nominal_peak else None,
+                         "nominal_peak_note": "SMs x 128 FP32 lanes x the SM clock sampled during the timed region",
                          "hbm_view": hbm_view(5702144 if (args.config == 2 and args.scale == 1.0) else None, f32_ms_avg)},
         }
         if fast:
