@@ -716,6 +716,28 @@ int pmm_fetch_log10(pmm_ctx* c, double* out, uint64_t cap, uint64_t* n_fallback)
     return PMM_OK;
 }
 
+int pmm_fetch_log10_indexed(pmm_ctx* c, double* out, uint64_t cap, uint32_t* fb_index, uint64_t fb_cap, uint64_t* n_fallback)
+{
+    if (!c || !out || !n_fallback) return PMM_ERR_INVALID;
+    if (cap < c->pairs) return c->fail(PMM_ERR_INVALID, "output buffer too small");
+    auto t0 = std::chrono::steady_clock::now();
+    uint32_t nfb = 0;
+    int rc = fetch_common(c, true, &nfb, nullptr);
+    if (rc) return rc;
+    const char* ho = static_cast<const char*>(c->h_out.p);
+    const float* hraw = reinterpret_cast<const float*>(ho + 256);
+    const uint32_t* hidx = reinterpret_cast<const uint32_t*>(ho + 256 + align_up(sizeof(float) * c->pairs));
+    const double* hd = reinterpret_cast<const double*>(reinterpret_cast<const char*>(hidx) + align_up(sizeof(uint32_t) * c->pairs));
+    pmm_host_finish_log10(hraw, c->pairs, hidx, hd, nfb, out);
+    *n_fallback = nfb;
+    if (fb_index) {
+        if (fb_cap < nfb) return c->fail(PMM_ERR_INVALID, "fallback index buffer too small");
+        memcpy(fb_index, hidx, sizeof(uint32_t) * nfb);
+    }
+    c->stats.ms_fetch = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return PMM_OK;
+}
+
 int pmm_fetch_fallback(pmm_ctx* c, uint32_t* index, double* value, uint64_t cap, uint64_t* count)
 {
     if (!c || !count) return PMM_ERR_INVALID;

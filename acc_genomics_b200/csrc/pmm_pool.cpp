@@ -10,6 +10,7 @@
 // and the FPGA processing-unit balancer (/root/reference/pairhmm/interface/PairHMMFpgaInterface.cpp:67-170).
 #include "../../include/pairhmm_cuda.h"
 
+#include <algorithm>
 #include <atomic>
 #include <condition_variable>
 #include <cstring>
@@ -59,32 +60,122 @@ struct pmm_pool {
     std::vector<uint64_t> cells_per_device, jobs_per_device;
     int n_devices = 0;
     std::vector<int> devices;
+    bool merge = true;                  // feeders merge small waiting jobs into one GPU job
+    uint64_t merged_batches = 0;
 };
 
 static std::string g_pool_error;
 
+// Merging thresholds: a feeder that finds several jobs waiting takes more of them while the merged job stays below
+// kMergeCells cells, kMergeJobs jobs and the engine's per-job limits.  A job that is already large runs alone.
+constexpr uint64_t kMergeCells = 3000000000ull;
+constexpr size_t kMergeJobs = 64;
+constexpr uint64_t kMergeBytes = 1ull << 29, kMergePairs = 1ull << 27;
+
+struct MergeBuf {                       // per feeder, reused from batch to batch
+    std::vector<uint32_t> read_off, hap_off, fb_index;
+    std::vector<uint8_t> tr[5], hap;
+    std::vector<pmm_region_t> regions;
+    std::vector<double> out;
+    std::vector<uint64_t> out_first;    // result offset of each merged job (+ total at the end)
+};
+
+static uint64_t job_pairs(const Job* j)
+{
+    uint64_t n = 0;
+    for (uint32_t g = 0; g < j->num_region; ++g) n += (uint64_t)j->regions[g].num_read * j->regions[g].num_hap;
+    return n;
+}
+static uint64_t job_bytes(const Job* j)
+{
+    return 5ull * (j->read_off[j->num_read] - j->read_off[0]) + (j->hap_off[j->num_hap] - j->hap_off[0]);
+}
+
+static void run_single(pmm_pool* p, pmm_ctx* c, Job* j)
+{
+    int rc = pmm_stage_flat(c, j->num_read, j->read_off, j->tr[0], j->tr[1], j->tr[2], j->tr[3], j->tr[4],
+                            j->num_hap, j->hap_off, j->hap, j->num_region, j->regions);
+    if (rc == PMM_OK) rc = pmm_launch(c);
+    uint64_t nfb = 0;
+    if (rc == PMM_OK) rc = pmm_fetch_log10(c, j->out, j->out_capacity, &nfb);
+    j->rc = rc; j->n_fallback = nfb;
+    if (rc != PMM_OK) j->err = pmm_last_error(c);
+}
+
+static void run_merged(pmm_pool* p, pmm_ctx* c, std::vector<Job*>& batch, MergeBuf& m)
+{
+    m.read_off.assign(1, 0); m.hap_off.assign(1, 0); m.regions.clear(); m.out_first.assign(1, 0);
+    for (int t = 0; t < 5; ++t) m.tr[t].clear();
+    m.hap.clear();
+    for (Job* j : batch) {
+        const uint32_t rbase = (uint32_t)m.read_off.size() - 1, hbase = (uint32_t)m.hap_off.size() - 1;
+        const uint32_t r0 = j->read_off[0], h0 = j->hap_off[0];
+        const uint32_t rshift = m.read_off.back(), hshift = m.hap_off.back();
+        for (uint32_t k = 1; k <= j->num_read; ++k) m.read_off.push_back(j->read_off[k] - r0 + rshift);
+        for (uint32_t k = 1; k <= j->num_hap; ++k) m.hap_off.push_back(j->hap_off[k] - h0 + hshift);
+        const size_t rb = j->read_off[j->num_read] - r0, hb = j->hap_off[j->num_hap] - h0;
+        for (int t = 0; t < 5; ++t) m.tr[t].insert(m.tr[t].end(), j->tr[t] + r0, j->tr[t] + r0 + rb);
+        m.hap.insert(m.hap.end(), j->hap + h0, j->hap + h0 + hb);
+        for (uint32_t g = 0; g < j->num_region; ++g) {
+            const pmm_region_t& r = j->regions[g];
+            m.regions.push_back(pmm_region_t{r.read_first + rbase, r.num_read, r.hap_first + hbase, r.num_hap});
+        }
+        m.out_first.push_back(m.out_first.back() + job_pairs(j));
+    }
+    const uint64_t total = m.out_first.back();
+    m.out.resize(total); m.fb_index.resize(total);
+    int rc = pmm_stage_flat(c, (uint32_t)m.read_off.size() - 1, m.read_off.data(), m.tr[0].data(), m.tr[1].data(), m.tr[2].data(),
+                            m.tr[3].data(), m.tr[4].data(), (uint32_t)m.hap_off.size() - 1, m.hap_off.data(), m.hap.data(),
+                            (uint32_t)m.regions.size(), m.regions.data());
+    if (rc == PMM_OK) rc = pmm_launch(c);
+    uint64_t nfb = 0;
+    if (rc == PMM_OK) rc = pmm_fetch_log10_indexed(c, m.out.data(), total, m.fb_index.data(), total, &nfb);
+    const std::string err = rc == PMM_OK ? std::string() : std::string(pmm_last_error(c));
+    for (size_t b = 0; b < batch.size(); ++b) {
+        Job* j = batch[b];
+        j->rc = rc; j->err = err; j->n_fallback = 0;
+        if (rc == PMM_OK) memcpy(j->out, m.out.data() + m.out_first[b], sizeof(double) * (m.out_first[b + 1] - m.out_first[b]));
+    }
+    if (rc == PMM_OK)
+        for (uint64_t k = 0; k < nfb; ++k) {
+            const size_t b = std::upper_bound(m.out_first.begin(), m.out_first.end(), (uint64_t)m.fb_index[k]) - m.out_first.begin() - 1;
+            if (b < batch.size()) batch[b]->n_fallback++;
+        }
+}
+
 static void feeder_main(pmm_pool* p, size_t slot)
 {
     pmm_ctx* c = p->ctxs[slot];
+    MergeBuf merge;
+    std::vector<Job*> batch;
     for (;;) {
-        Job* j = nullptr;
+        batch.clear();
         {
             std::unique_lock<std::mutex> lk(p->mu);
             p->cv_work.wait(lk, [&] { return p->stopping || !p->queue.empty(); });
             if (p->queue.empty()) return;          // stopping and drained
-            j = p->queue.top(); p->queue.pop();
+            Job* j = p->queue.top(); p->queue.pop();
+            batch.push_back(j);
+            // the queue is ordered largest first: everything behind a small job is small too
+            uint64_t cells = j->cells, bytes = job_bytes(j), pairs = job_pairs(j);
+            while (p->merge && !p->queue.empty() && batch.size() < kMergeJobs) {
+                Job* n = p->queue.top();
+                if (cells + n->cells > kMergeCells || bytes + job_bytes(n) > kMergeBytes || pairs + job_pairs(n) > kMergePairs) break;
+                p->queue.pop();
+                batch.push_back(n);
+                cells += n->cells; bytes += job_bytes(n); pairs += job_pairs(n);
+            }
         }
-        int rc = pmm_stage_flat(c, j->num_read, j->read_off, j->tr[0], j->tr[1], j->tr[2], j->tr[3], j->tr[4],
-                                j->num_hap, j->hap_off, j->hap, j->num_region, j->regions);
-        if (rc == PMM_OK) rc = pmm_launch(c);
-        uint64_t nfb = 0;
-        if (rc == PMM_OK) rc = pmm_fetch_log10(c, j->out, j->out_capacity, &nfb);
-        std::string err = rc == PMM_OK ? std::string() : std::string(pmm_last_error(c));
+        if (batch.size() == 1) run_single(p, c, batch[0]);
+        else run_merged(p, c, batch, merge);
         {
             std::lock_guard<std::mutex> lk(p->mu);
-            j->rc = rc; j->err = err; j->n_fallback = nfb; j->device = p->ctx_device[slot]; j->done = true;
-            for (int d = 0; d < p->n_devices; ++d)
-                if (p->devices[d] == j->device) { p->cells_per_device[d] += j->cells; p->jobs_per_device[d]++; }
+            for (Job* j : batch) {
+                j->device = p->ctx_device[slot]; j->done = true;
+                for (int d = 0; d < p->n_devices; ++d)
+                    if (p->devices[d] == j->device) { p->cells_per_device[d] += j->cells; p->jobs_per_device[d]++; }
+            }
+            p->merged_batches += batch.size() > 1;
         }
         p->cv_done.notify_all();
     }
@@ -208,6 +299,15 @@ int pmm_pool_wait(pmm_pool* p, uint64_t ticket, uint64_t* n_fallback, int* devic
     p->jobs.erase(it);
     delete j;
     return rc;
+}
+
+int pmm_pool_set_merge(pmm_pool* p, int on, uint64_t* merged_batches)
+{
+    if (!p) return PMM_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(p->mu);
+    if (on >= 0) p->merge = on != 0;
+    if (merged_batches) *merged_batches = p->merged_batches;
+    return PMM_OK;
 }
 
 int pmm_pool_device_load(const pmm_pool* p, int slot, int* device, uint64_t* jobs, uint64_t* cells)

@@ -42,3 +42,28 @@ def test_pool_rejects_bad_jobs(built):
     pool.close()
     with pytest.raises(PmmError):
         PairHMMPool(devices=[99])
+
+
+def test_small_jobs_are_merged_and_split_again(built, checker):
+    """Many small jobs queued at once: feeders merge them into multi-region GPU jobs; every caller still gets exactly its
+    own results and its own fallback count."""
+    from acc_genomics_b200.engine import PairHMMPool
+    pool = PairHMMPool(devices=[0], contexts_per_device=1)
+    regions = synth.config(5, scale=0.016, seed=12)                      # 40 regions
+    regions += [synth.config(3, scale=0.02, seed=13)[0]]                 # one fallback-heavy region
+    want = [checker.batch(b, threads=8) for b in regions]
+    for rep in range(2):                                                 # second round: buffers reused
+        tickets = [pool.submit(b) for b in regions]
+        for b, t, (_, out_r, fb_r) in zip(regions, tickets, want):
+            out, nfb, _ = pool.wait(t)
+            assert_bits_equal(out, out_r.ravel(), "merged job")
+            assert nfb == int(fb_r.sum())
+    assert pool.set_merge() > 0, "nothing was merged"
+    # and with merging off the answers are the same
+    pool.set_merge(False)
+    before = pool.set_merge()
+    tickets = [pool.submit(b) for b in regions[:8]]
+    for t, (_, out_r, _) in zip(tickets, want):
+        assert_bits_equal(pool.wait(t)[0], out_r.ravel(), "unmerged job")
+    assert pool.set_merge() == before
+    pool.close()
