@@ -226,8 +226,8 @@ int stage_common(pmm_ctx* c, uint32_t num_read, const uint32_t* read_off, uint32
     PMM_CUDA(c, c->h_out.reserve(256 + align_up(sizeof(float) * pairs) + align_up(sizeof(uint32_t) * pairs) + sizeof(double) * pairs + 256));
     // carry rows of the striped kernels: one haplotype (+2 separators) per warp, three rows of doubles
     {
-        const int ctas64 = std::max(std::max(forward_f64_ctas_per_sm(5, false), forward_f64_ctas_per_sm(5, true)),
-                                    std::max(forward_f64_ctas_per_sm(6, false), forward_f64_ctas_per_sm(6, true)));
+        int ctas64 = 1;
+        for (int k : {4, 5, 6, 8}) ctas64 = std::max(ctas64, std::max(forward_f64_ctas_per_sm(k, false), forward_f64_ctas_per_sm(k, true)));
         const int ctas32 = std::max(std::max(forward_f32_ctas_per_sm(kStripedK, 32, true, false), forward_f32_ctas_per_sm(kStripedK, 32, true, true)),
                                     recheck_f32_ctas_per_sm());
         const size_t warps = (size_t)c->sm_count * std::max(ctas64, ctas32) * kWarpsPerCta;

@@ -87,7 +87,7 @@ __host__ __device__ constexpr int wtab_elems() { return 5 * ((K + Arith<T>::kVec
 // (5 parameters + M, X, Y), so K decides the occupancy step (64K registers / 128 threads).
 template <typename T, int K> __host__ __device__ constexpr int min_ctas()
 {
-    return sizeof(T) == 8 ? 3 : K <= 11 ? 4 : K <= 16 ? 3 : 2;
+    return sizeof(T) == 8 ? (K <= 6 ? 3 : 2) : K <= 11 ? 4 : K <= 16 ? 3 : 2;
 }
 
 // ---- fallback list: the float pass appends the pairs whose result is below 1e-28f the moment the result exists ----
@@ -565,31 +565,38 @@ cudaError_t launch_recheck_f32(const ForwardArgs& a, const FallbackQueue& fq, in
 
 int recheck_f32_ctas_per_sm() { return variant_ctas_per_sm<float, kStripedK, 32, true, kPush | kInline>(); }
 
-// Double re-run: rows per lane K in {5, 6} (W = 32, multi-stripe capable); see pick_f64_rows().
+// Double re-run: rows per lane K in {4, 5, 6, 8} (W = 32, multi-stripe capable); see pick_f64_rows().
+#define PMM_F64_ROWS(X) X(4) X(5) X(6) X(8)
+
 cudaError_t launch_forward_f64(int K, bool flush, const ForwardArgs& a, int ctas, cudaStream_t s)
 {
     const FallbackQueue none{};
-    if (K == 5) return flush ? launch_variant<double, 5, 32, true, kFlush>(a, none, ctas, s)
-                             : launch_variant<double, 5, 32, true, 0>(a, none, ctas, s);
-    if (K == 6) return flush ? launch_variant<double, 6, 32, true, kFlush>(a, none, ctas, s)
-                             : launch_variant<double, 6, 32, true, 0>(a, none, ctas, s);
+#define X(k) if (K == k) return flush ? launch_variant<double, k, 32, true, kFlush>(a, none, ctas, s) \
+                                      : launch_variant<double, k, 32, true, 0>(a, none, ctas, s);
+    PMM_F64_ROWS(X)
+#undef X
     return cudaErrorInvalidValue;
 }
 
 int forward_f64_ctas_per_sm(int K, bool flush)
 {
-    if (K == 5) return flush ? variant_ctas_per_sm<double, 5, 32, true, kFlush>() : variant_ctas_per_sm<double, 5, 32, true, 0>();
-    if (K == 6) return flush ? variant_ctas_per_sm<double, 6, 32, true, kFlush>() : variant_ctas_per_sm<double, 6, 32, true, 0>();
+#define X(k) if (K == k) return flush ? variant_ctas_per_sm<double, k, 32, true, kFlush>() : variant_ctas_per_sm<double, k, 32, true, 0>();
+    PMM_F64_ROWS(X)
+#undef X
     return 0;
 }
 
-// Rows per lane of the double kernel for a job whose longest read has max_read_len bases: the block (160 or 192
-// rows per stripe) that wastes the fewest rows on it.
+// Rows per lane of the double kernel for a job whose longest read has max_read_len bases: the block (128, 160, 192 or
+// 256 rows per stripe) that wastes the fewest rows on it; ties go to the larger block (fewer stripes, shorter chain).
 int pick_f64_rows(uint32_t max_read_len)
 {
     const uint32_t rows = max_read_len + 1;
-    const uint32_t p5 = (rows + 159) / 160 * 160, p6 = (rows + 191) / 192 * 192;
-    return p5 <= p6 ? 5 : 6;
+    int best = 0; uint32_t best_padded = 0;
+    for (int k : {4, 5, 6, 8}) {
+        const uint32_t blk = 32u * k, padded = (rows + blk - 1) / blk * blk;
+        if (!best || padded <= best_padded) { best = k; best_padded = padded; }
+    }
+    return best;
 }
 
 cudaError_t launch_build_stream(const uint8_t* hap_blob, const HapDesc* haps, const uint32_t* spos, uint32_t num_hap,

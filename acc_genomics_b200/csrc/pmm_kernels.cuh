@@ -74,7 +74,7 @@ cudaError_t launch_forward_f32(int K, int W, bool striped, bool fast, const Forw
 // Exact float re-run of the single-pair tasks on the re-check list (fast mode), overwriting their results.
 cudaError_t launch_recheck_f32(const ForwardArgs& a, const FallbackQueue& fq, int ctas, cudaStream_t s);
 int recheck_f32_ctas_per_sm();
-// Double re-run (fallback list), K rows per lane from pick_f64_rows().  flush = emulate x86 flush-to-zero on every product.
+// Double re-run (fallback list), K in {4, 5, 6, 8} rows per lane from pick_f64_rows().  flush = emulate x86 flush-to-zero on every product.
 cudaError_t launch_forward_f64(int K, bool flush, const ForwardArgs& a, int ctas, cudaStream_t s);
 int pick_f64_rows(uint32_t max_read_len);
 // CTAs per SM the given variant reaches.
