@@ -28,6 +28,14 @@ constexpr int kInsert = 1, kDelete = 2, kInsertExt = 4, kDeleteExt = 8;
 constexpr int kStateClip = 4;                    // STATE_CLIP (host/common.h:23)
 constexpr int kSoftClip = 0, kIndel = 1, kLeadingIndel = 2, kIgnore = 3;
 
+// Integer multiply-add / high multiply as explicit PTX so that they stay IMAD / IMAD.HI (FMA pipe).
+__device__ __forceinline__ int imad(int a, int b, int c)
+{
+    int d;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 struct WarpSmem {
     int* carryH; int* carryF; int* lastrow; int* lastcol; uint32_t* tile; uint8_t* alt;
 };
@@ -63,6 +71,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sw_align_kernel(const Args 
     const WarpSmem sm = carve(reinterpret_cast<char*>(smem_raw) + warp * per_warp, a.max_l1, a.max_l2);
     const int match = a.match, mismatch = a.mismatch, open = a.open, extend = a.extend, strategy = a.strategy;
     const bool indel = strategy == kIndel || strategy == kLeadingIndel;
+    // multipliers the compiler must not know (see the step function): the host passes -1, 2, 4, 8
+    const int neg1 = a.k_neg1, two = a.k_two, four = a.k_four, eight = a.k_eight;
+    auto sign_of = [](int x) { return (unsigned)x >> 31; };
 
     for (;;) {
         uint32_t p = 0;
@@ -108,30 +119,40 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sw_align_kernel(const Args 
             // the lane and row that hold the matrix's last row (for the end-cell search); -1 if not in this block
             const int own_k = (nrow >= ifirst && nrow < ifirst + K) ? nrow - ifirst : -1;
 
-            // one step: column j of this lane's K rows.  MAIN_CODE (PairWiseSW.h:4-40): same comparisons, same order;
-            // the max-with-predicate forms (__vibmax_s32) give each maximum and its tie-break bit in one instruction.
+            // one step: column j of this lane's K rows.  MAIN_CODE (PairWiseSW.h:4-40): same comparisons, same order.
+            // Pipe balance: compares, selects, min/max and shifts issue on the ALU pipe, multiply-adds on the FMA pipe, and
+            // the straightforward form of this update is 29 ALU instructions per cell.  Here each tie-break bit is the
+            // sign of a difference (a multiply-add by -1 that ptxas cannot see through, then one shift) instead of a
+            // compare plus a select, and the four bits are packed and appended to the row's word by multiply-adds.
+            // Measured on 16 640 pairs: 431 GCUPS against 406 for compare/select; moving the remaining adds and the
+            // sign extraction (mul.hi) to the FMA pipe as well was slower (366): three-register IMAD forms issue at half
+            // rate like three-register FFMA.  (Differences cannot overflow: |values| <= 2^30 + 2^20.)
             auto step = [&](const int j, int upH, int upF) {
                 const int c2 = (int)sm.alt[j - 1];
                 int diag = prev_up;
                 prev_up = upH;
                 int hup = upH, fup = upF;
-                const int sh = 4 * ((j - 1) & 7);
+                const int pw = 1 << (4 * ((j - 1) & 7));               // where this column's 4 bits go in the word
                 const bool flush = ((j - 1) & 7) == 7 || j == ncol;
                 #pragma unroll
                 for (int k = 0; k < K; ++k) {
                     const int hleft = Hrow[k];
-                    bool ins_ext, del_ext, keep1, keep2;
-                    const int e11 = __vibmax_s32(E[k] + extend, hleft + open, &ins_ext);     // ins_ext = !(open > extend): extension on ties
-                    const int f11 = __vibmax_s32(fup + extend, hup + open, &del_ext);
+                    const int ext_h = E[k] + extend, open_h = hleft + open;
+                    const int e11 = max(ext_h, open_h);
+                    const unsigned ins_open = sign_of(imad(open_h, neg1, ext_h));   // open_h > ext_h; ties extend
+                    const int ext_v = fup + extend, open_v = hup + open;
+                    const int f11 = max(ext_v, open_v);
+                    const unsigned del_open = sign_of(imad(open_v, neg1, ext_v));
                     const int m11 = diag + (c1[k] == c2 ? match : mismatch);
-                    int h11 = max(kMinCutoff, m11);
-                    h11 = __vibmax_s32(h11, e11, &keep1);                                    // keep1 = !(e11 > h11)
-                    h11 = __vibmax_s32(h11, f11, &keep2);                                    // keep2 = !(f11 > h11)
-                    const int mv = keep2 ? (keep1 ? 0 : kInsert) : kDelete;
-                    const int code = mv | (ins_ext ? kInsertExt : 0) | (del_ext ? kDeleteExt : 0);
+                    const int h0 = max(kMinCutoff, m11);
+                    const unsigned take_ins = sign_of(imad(e11, neg1, h0));          // e11 > h0
+                    const int h1 = max(h0, e11);
+                    const unsigned take_del = sign_of(imad(f11, neg1, h1));          // f11 > h1
+                    const int h11 = max(h1, f11);
+                    const int code = imad((int)take_del, eight, imad((int)take_ins, four, imad((int)del_open, two, (int)ins_open)));
                     diag = hleft;
                     Hrow[k] = h11; E[k] = e11; hup = h11; fup = f11;
-                    acc[k] |= (uint32_t)code << sh;
+                    acc[k] = (uint32_t)imad(code, pw, (int)acc[k]);
                     if (flush) {
                         if (brow[k]) brow[k][(j - 1) >> 3] = acc[k];
                         acc[k] = 0;
@@ -239,12 +260,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sw_align_kernel(const Args 
             if (lane == 0) {
                 while (ti > 0 && tj > 0 && ai - ti < 32 && ((tj - 1) >> 3) >= cw0) {
                     const int btr = (int)((sm.tile[(((tj - 1) >> 3) - cw0) * 32 + (ai - ti)] >> (4 * ((tj - 1) & 7))) & 15u);
-                    if (state == kInsertExt) { --tj; emit(kInsert, 1); state = btr & kInsertExt; }
-                    else if (state == kDeleteExt) { --ti; emit(kDelete, 1); state = btr & kDeleteExt; }
+                    // stored bits: 0 insertion opened (not an extension), 1 deletion opened, 2 insertion taken, 3 deletion
+                    // taken (it wins over the insertion); the reference's codes are move + "was an extension" flags
+                    const int ins_ext = (btr & 1) ? 0 : kInsertExt, del_ext = (btr & 2) ? 0 : kDeleteExt;
+                    if (state == kInsertExt) { --tj; emit(kInsert, 1); state = ins_ext; }
+                    else if (state == kDeleteExt) { --ti; emit(kDelete, 1); state = del_ext; }
                     else {
-                        const int mv = btr & 3;
-                        if (mv == kInsert) { --tj; emit(kInsert, 1); state = btr & kInsertExt; }
-                        else if (mv == kDelete) { --ti; emit(kDelete, 1); state = btr & kDeleteExt; }
+                        if (btr & 8) { --ti; emit(kDelete, 1); state = del_ext; }
+                        else if (btr & 4) { --tj; emit(kInsert, 1); state = ins_ext; }
                         else { --ti; --tj; emit(0, (raw_ops == 0 && strategy == kIgnore) ? seg + 1 : 1); state = 0; }
                         ++raw_ops;
                     }

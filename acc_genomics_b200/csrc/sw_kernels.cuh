@@ -2,9 +2,10 @@
 //
 // Layout in HBM for one chunk of pairs:
 //   seq1 / seq2 blobs   bytes; pair p is seq1[s1 .. s1+l1) (reference, matrix rows) against seq2[s2 .. s2+l2) (alternate, columns)
-//   backtrack           per pair l1 rows of `bt_stride` 32-bit words, 8 cells per word, 4 bits per cell: bits 0-1 the move
-//                       (0 diagonal, 1 insertion = left, 2 deletion = up), bit 2 "the insertion was an extension", bit 3 "the
-//                       deletion was an extension" -- the codes of /root/reference/htc-sw/intel_avx/smithwaterman_common.h:18-22
+//   backtrack           per pair l1 rows of `bt_stride` 32-bit words, 8 cells per word, 4 bits per cell: bit 0 "the insertion
+//                       into this cell opens a gap" (else it extends one), bit 1 the same for the deletion, bit 2 "the
+//                       insertion beats the diagonal", bit 3 "the deletion beats both" -- the information of the reference's
+//                       codes (/root/reference/htc-sw/intel_avx/smithwaterman_common.h:18-22) as raw comparison results
 //   cigars              per pair `cigar_cap` (length, state) elements, forward order; n_elem, alignment offset, score
 #pragma once
 #include <cstdint>
@@ -37,6 +38,7 @@ struct Args {
     int32_t*        offset;
     int32_t*        score;
     uint32_t        max_l1, max_l2;      // of the chunk: sizes the per-warp shared memory
+    int             k_neg1, k_two, k_four, k_eight;   // -1, 2, 4, 8: multipliers kept opaque to the compiler
 };
 
 size_t smem_bytes_per_warp(uint32_t max_l1, uint32_t max_l2);
