@@ -227,7 +227,7 @@ int stage_common(pmm_ctx* c, uint32_t num_read, const uint32_t* read_off, uint32
     // carry rows of the striped kernels: one haplotype (+2 separators) per warp, three rows of doubles
     {
         int ctas64 = 1;
-        for (int k : {4, 5, 6, 8}) ctas64 = std::max(ctas64, std::max(forward_f64_ctas_per_sm(k, false), forward_f64_ctas_per_sm(k, true)));
+        for (int k : {4, 5, 6, 8}) ctas64 = std::max(ctas64, forward_f64_ctas_per_sm(k));
         const int ctas32 = std::max(std::max(forward_f32_ctas_per_sm(kStripedK, 32, true, false), forward_f32_ctas_per_sm(kStripedK, 32, true, true)),
                                     recheck_f32_ctas_per_sm());
         const size_t warps = (size_t)c->sm_count * std::max(ctas64, ctas32) * kWarpsPerCta;
@@ -592,16 +592,8 @@ int pmm_launch(pmm_ctx* c)
     a.inity = c->d_iyd.p; a.out = c->d_dres.p; a.tasks = static_cast<Task*>(c->d_fb_tasks.p);
     a.ntasks = 0; a.ntasks_dev = ctrl + 0; a.counter = ctrl + cursor; cursor += 32;
     const int KD = c->f64_rows;
-    PMM_CUDA(c, launch_forward_f64(KD, false, a, c->sm_count * std::max(1, forward_f64_ctas_per_sm(KD, false)), s));
-    ++launches;
-    // Intermediate products below DBL_MIN are flushed to zero on the reference's x86 (FTZ on); they can only
-    // influence results that are themselves tiny.  Everything below 2^-800 (scaled by 2^1020) is recomputed with
-    // the flush emulated after every product; above it the two arithmetics agree ("FTZ").
-    PMM_CUDA(c, launch_compact_tiny(static_cast<double*>(c->d_dres.p), static_cast<Task*>(c->d_fb_tasks.p), ctrl + 0,
-                                    ldexp(1.0, -800), static_cast<Task*>(c->d_tiny_tasks.p), ctrl + 1, s));
-    ++launches;
-    a.tasks = static_cast<Task*>(c->d_tiny_tasks.p); a.ntasks_dev = ctrl + 1; a.counter = ctrl + cursor;
-    PMM_CUDA(c, launch_forward_f64(KD, true, a, c->sm_count * std::max(1, forward_f64_ctas_per_sm(KD, true)), s));
+    a.tiny_threshold = ldexp(1.0, -800); a.tiny_count = ctrl + 1;
+    PMM_CUDA(c, launch_forward_f64(KD, a, c->sm_count * std::max(1, forward_f64_ctas_per_sm(KD)), s));
     ++launches;
     PMM_CUDA(c, cudaEventRecord(c->ev[2], s));
     c->stats.kernel_launches = launches;

@@ -129,6 +129,9 @@ __device__ __forceinline__ void push_recheck(const FallbackQueue& fq, uint32_t r
 // kInline: compute the float row parameters in the kernel instead of reading read_params_kernel's planes (single-pair
 // re-check tasks have no parameter block).
 constexpr int kFlush = 1, kPush = 2, kFast = 4, kInline = 8;
+// kRetry (kernel level, double only): a single-pair task whose result is below tiny_threshold is run again at once with
+// kFlush -- the case where x86 flush-to-zero of intermediate products may have changed the reference's result.
+constexpr int kRetry = 16;
 
 template <typename T, int K, int W, bool STRIPED, int F>
 __device__ __forceinline__ void run_task(const ForwardArgs& a, const Task* tk, T* wtab, const int lane,
@@ -392,7 +395,20 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, min_ctas<T, K>()) pmm_forwa
         if (lane == 0) ti = atomicAdd(a.counter, 1u);
         ti = __shfl_sync(0xffffffffu, ti, 0);
         if (ti >= ntasks) break;
-        run_task<T, K, W, STRIPED, F>(a, a.tasks + ti, wtab, lane, gwarp, fq);
+        run_task<T, K, W, STRIPED, F & ~kRetry>(a, a.tasks + ti, wtab, lane, gwarp, fq);
+        if constexpr ((F & kRetry) != 0) {
+            // Intermediate products below DBL_MIN are flushed to zero on the reference's x86 (FTZ on); they can only
+            // influence results that are themselves tiny.  Everything below tiny_threshold (2^-800, scaled by 2^1020) is
+            // recomputed with the flush emulated after every product; above it the two arithmetics agree.
+            static_assert(std::is_same<T, double>::value && W == 32, "retry is for the single-pair double tasks");
+            __syncwarp();
+            const uint32_t slot = a.tasks[ti].out_base[0];
+            const double r = __ldcg(static_cast<const double*>(a.out) + slot);       // written by lane 31 a moment ago
+            if (r < a.tiny_threshold) {
+                if (lane == 0) atomicAdd(a.tiny_count, 1u);
+                run_task<T, K, W, STRIPED, (F & ~kRetry) | kFlush>(a, a.tasks + ti, wtab, lane, gwarp, fq);
+            }
+        }
     }
 }
 
@@ -460,22 +476,6 @@ __global__ void build_stream_kernel(const uint8_t* __restrict__ blob, const HapD
         if (h + 1 == num_hap) dst[1 + d.len] = kSep;
     }
     for (uint32_t k = threadIdx.x; k < d.len; k += blockDim.x) dst[1 + k] = (uint8_t)base_class(blob[d.off + k]);
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// Second-level list: double results so small that x86 flush-to-zero may have mattered (see launch_compact_tiny).
-// ---------------------------------------------------------------------------------------------------------
-__global__ void compact_tiny_kernel(const double* __restrict__ dres, const Task* __restrict__ fb_tasks,
-                                    const uint32_t* __restrict__ fb_count, double threshold,
-                                    Task* __restrict__ tiny_tasks, uint32_t* tiny_count)
-{
-    const uint32_t n = *fb_count;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        if (dres[i] < threshold) {
-            const uint32_t slot = atomicAdd(tiny_count, 1u);
-            tiny_tasks[slot] = fb_tasks[i];       // same read, hap and result slot: the re-run overwrites dres[i]
-        }
-    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -568,19 +568,18 @@ int recheck_f32_ctas_per_sm() { return variant_ctas_per_sm<float, kStripedK, 32,
 // Double re-run: rows per lane K in {4, 5, 6, 8} (W = 32, multi-stripe capable); see pick_f64_rows().
 #define PMM_F64_ROWS(X) X(4) X(5) X(6) X(8)
 
-cudaError_t launch_forward_f64(int K, bool flush, const ForwardArgs& a, int ctas, cudaStream_t s)
+cudaError_t launch_forward_f64(int K, const ForwardArgs& a, int ctas, cudaStream_t s)
 {
     const FallbackQueue none{};
-#define X(k) if (K == k) return flush ? launch_variant<double, k, 32, true, kFlush>(a, none, ctas, s) \
-                                      : launch_variant<double, k, 32, true, 0>(a, none, ctas, s);
+#define X(k) if (K == k) return launch_variant<double, k, 32, true, kRetry>(a, none, ctas, s);
     PMM_F64_ROWS(X)
 #undef X
     return cudaErrorInvalidValue;
 }
 
-int forward_f64_ctas_per_sm(int K, bool flush)
+int forward_f64_ctas_per_sm(int K)
 {
-#define X(k) if (K == k) return flush ? variant_ctas_per_sm<double, k, 32, true, kFlush>() : variant_ctas_per_sm<double, k, 32, true, 0>();
+#define X(k) if (K == k) return variant_ctas_per_sm<double, k, 32, true, kRetry>();
     PMM_F64_ROWS(X)
 #undef X
     return 0;
@@ -613,13 +612,6 @@ cudaError_t launch_read_params(const uint8_t* read_blob, const ReadDesc* reads, 
 {
     if (ngroups == 0) return cudaSuccess;
     read_params_kernel<<<ngroups, 128, 0, s>>>(read_blob, reads, groups, ngroups, tab, params);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_compact_tiny(const double* dres, const Task* fb_tasks, const uint32_t* fb_count,
-                                double threshold, Task* tiny_tasks, uint32_t* tiny_count, cudaStream_t s)
-{
-    compact_tiny_kernel<<<148, 256, 0, s>>>(dres, fb_tasks, fb_count, threshold, tiny_tasks, tiny_count);
     return cudaGetLastError();
 }
 

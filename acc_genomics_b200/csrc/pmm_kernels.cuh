@@ -49,6 +49,8 @@ struct ForwardArgs {
     void*           out;           // float* or double*
     void*           scratch;       // STRIPED only: per-warp carry rows, 3 * scratch_stride elements per warp
     uint32_t        scratch_stride;
+    double          tiny_threshold;   // double kernel: results below it are re-run with flush-to-zero emulated ...
+    uint32_t*       tiny_count;       // ... and counted here
     DeviceTables    tab;
 };
 
@@ -74,12 +76,13 @@ cudaError_t launch_forward_f32(int K, int W, bool striped, bool fast, const Forw
 // Exact float re-run of the single-pair tasks on the re-check list (fast mode), overwriting their results.
 cudaError_t launch_recheck_f32(const ForwardArgs& a, const FallbackQueue& fq, int ctas, cudaStream_t s);
 int recheck_f32_ctas_per_sm();
-// Double re-run (fallback list), K in {4, 5, 6, 8} rows per lane from pick_f64_rows().  flush = emulate x86 flush-to-zero on every product.
-cudaError_t launch_forward_f64(int K, bool flush, const ForwardArgs& a, int ctas, cudaStream_t s);
+// Double re-run (fallback list), K in {4, 5, 6, 8} rows per lane from pick_f64_rows().  Results below a.tiny_threshold are
+// recomputed in the same kernel with x86 flush-to-zero emulated on every product.
+cudaError_t launch_forward_f64(int K, const ForwardArgs& a, int ctas, cudaStream_t s);
 int pick_f64_rows(uint32_t max_read_len);
 // CTAs per SM the given variant reaches.
 int forward_f32_ctas_per_sm(int K, int W, bool striped, bool fast = false);
-int forward_f64_ctas_per_sm(int K, bool flush);
+int forward_f64_ctas_per_sm(int K);
 
 cudaError_t launch_build_stream(const uint8_t* hap_blob, const HapDesc* haps, const uint32_t* spos, uint32_t num_hap,
                                 uint8_t* stream, float* inity_f, double* inity_d, float ic_f, double ic_d,
@@ -88,10 +91,6 @@ cudaError_t launch_build_stream(const uint8_t* hap_blob, const HapDesc* haps, co
 // Row parameters of the float pass, one CTA per read group (layout: GroupDesc in pmm_types.h).
 cudaError_t launch_read_params(const uint8_t* read_blob, const ReadDesc* reads, const GroupDesc* groups, uint32_t ngroups,
                                const DeviceTables& tab, float* params, cudaStream_t s);
-
-// Second-level scan: double results below `threshold` are re-queued for the flush-emulating kernel.
-cudaError_t launch_compact_tiny(const double* dres, const Task* fb_tasks, const uint32_t* fb_count,
-                                double threshold, Task* tiny_tasks, uint32_t* tiny_count, cudaStream_t s);
 
 // FP32 issue-rate probe used for the roofline denominator (dependent-free FMUL/FADD streams).
 cudaError_t launch_fp32_probe(float* sink, int iters, int ctas, cudaStream_t s);

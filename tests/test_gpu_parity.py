@@ -36,7 +36,7 @@ def test_golden_vectors(engine, golden):
         assert np.array_equal(m, mask), f"{name} mask"
         assert_bits_equal(out, log10_bits.view(np.float64), f"{name} log10")
     st = engine.stats()
-    assert st["kernel_launches"] >= 5
+    assert st["kernel_launches"] >= 3          # row parameters, float pass, double pass
 
 
 def test_flush_to_zero_path_taken(engine, golden):
