@@ -501,8 +501,8 @@ int pmm_set_option(pmm_ctx* c, const char* key, const char* value)
     }
     if (k == "force_variant") {
         int K = 0, W = 0;
-        if (sscanf(value, "%d,%d", &K, &W) != 2 || (K && !forward_f32_has_variant(K, W)))
-            return c->fail(PMM_ERR_INVALID, "force_variant wants \"K,W\" of an instantiated float kernel, or \"0,0\"");
+        if (sscanf(value, "%d,%d", &K, &W) != 2 || (K > 0 && !forward_f32_has_variant(K, W)))
+            return c->fail(PMM_ERR_INVALID, "force_variant wants \"K,W\" of an instantiated float kernel, \"0,0\" (planner's choice) or \"-1,0\" (no consolidation of rare variants)");
         c->force = Variant{K, W, false};
         return PMM_OK;
     }

@@ -28,11 +28,66 @@ Variant pick_variant(int R)
     return best;
 }
 
+struct Group { Variant v; uint32_t region; uint32_t reads[kMaxGroups]; uint32_t n; };
+
+// Every variant present costs one kernel launch, and a launch is inefficient when it has few tasks: it lasts at
+// least as long as its longest task, and its tail leaves most of the GPU idle.  A mixed-length job (config 5: 10 % of
+// the reads soft-clipped to 60..150 bases) picks eleven variants for 8 % of its work; measured on B200 for a 25-region
+// job: every variant its own launch 3.37 ms, everything in the K = 19 launch 2.77 ms.  So: a variant moves up into the
+// next larger one of the same W (same reads per warp, hence the same groups) whenever running its tasks with the
+// unused rows is estimated cheaper than a launch of its own.  Smallest K first, so that moves cascade.
+// Model (calibrated on that measurement): own launch = work / GPU rate + half the solo run time of the longest task
+// (ramp + tail) + launch gap; moved = work at the larger variant's step cost / GPU rate.
+static void merge_rare_variants(std::vector<Group>& groups, const std::vector<RegionDesc>& regions,
+                                const uint32_t* hap_off, int sm_count, uint32_t longest_task_steps)
+{
+    constexpr double kSlotsPerUs = 1900.0;         // issue slots of one SMSP per microsecond (SM clock ~1.9 GHz)
+    constexpr double kBusy = 0.85;                 // share of them this kernel uses on a full GPU
+    constexpr double kSoloIpc = 0.55;              // what a warp alone on its SMSP reaches (dependent issue)
+    constexpr double kLaunchUs = 4.0;              // launch gap
+    double steps[3][kMaxK + 1] = {};               // [log2(W) - 3][K]: wavefront steps of all tasks of the variant
+    auto widx = [](int W) { return W == 8 ? 0 : W == 16 ? 1 : 2; };
+    for (const Group& g : groups) {
+        if (g.v.striped) continue;
+        const RegionDesc& r = regions[g.region];
+        steps[widx(g.v.W)][g.v.K] += hap_off[r.hap_first + r.nhaps] - hap_off[r.hap_first] + r.nhaps;
+    }
+    const double gpu_slots_per_us = std::max(1, sm_count) * 4.0 * kSlotsPerUs * kBusy;
+    int target[3][kMaxK + 1];
+    bool any = false;
+    for (int w = 0; w < 3; ++w) {
+        for (int K = 0; K <= kMaxK; ++K) target[w][K] = K;
+        for (int K = 1; K <= kMaxK; ++K) {
+            if (steps[w][K] == 0) continue;
+            int up = 0;
+            for (int K2 = K + 1; K2 <= kMaxK && !up; ++K2) if (steps[w][K2] > 0) up = K2;
+            if (!up) continue;
+            const double own = steps[w][K] * step_cost(K) / gpu_slots_per_us +
+                               0.5 * longest_task_steps * step_cost(K) / (kSlotsPerUs * kSoloIpc) + kLaunchUs;
+            const double moved = steps[w][K] * step_cost(up) / gpu_slots_per_us;
+            if (moved >= own) continue;
+            steps[w][up] += steps[w][K];
+            steps[w][K] = 0;
+            target[w][K] = up; any = true;
+        }
+    }
+    if (!any) return;
+    for (Group& g : groups) {
+        if (g.v.striped) continue;
+        int K = g.v.K;
+        const int w = widx(g.v.W);
+        while (target[w][K] != K) K = target[w][K];
+        g.v.K = K;
+    }
+}
+
 int plan_job(uint32_t num_read, const uint32_t* read_off, uint32_t num_hap, const uint32_t* hap_off,
              uint32_t num_region, const pmm_region_t* regions, int sm_count, int tasks_per_warp,
              Plan& plan, std::string& err, const Variant* force, const std::function<Task*(const Plan&)>& task_dst)
 {
     plan = Plan();
+    const bool keep_all_variants = force && force->K < 0;             // tuning sweeps: "-1,0" = no consolidation
+    if (keep_all_variants) force = nullptr;
     if (!num_read || !num_hap || !num_region || !read_off || !hap_off || !regions) { err = "empty job"; return PMM_ERR_INVALID; }
     const uint64_t total_bases = (uint64_t)read_off[num_read] - read_off[0];
     const uint64_t total_hap = (uint64_t)hap_off[num_hap] - hap_off[0];
@@ -64,7 +119,6 @@ int plan_job(uint32_t num_read, const uint32_t* read_off, uint32_t num_hap, cons
     // ---- read groups --------------------------------------------------------------------------------------------
     // Reads of a region are sorted by length (longest first); the longest unassigned read picks the (K, W)
     // variant and shares its warp with the next 32/W - 1 reads.
-    struct Group { Variant v; uint32_t region; uint32_t reads[kMaxGroups]; uint32_t n; };
     std::vector<Group> groups;
     std::vector<uint32_t> order;
     uint64_t group_haps = 0;
@@ -91,6 +145,8 @@ int plan_job(uint32_t num_read, const uint32_t* read_off, uint32_t num_hap, cons
     const uint64_t resident_warps = (uint64_t)std::max(1, sm_count) * 16;
     const uint64_t target_tasks = std::max<uint64_t>(1, resident_warps * (uint64_t)std::max(1, tasks_per_warp));
     plan.haps_per_task = (uint32_t)std::max<uint64_t>(1, (group_haps + target_tasks - 1) / target_tasks);
+    if (!force && !keep_all_variants)
+        merge_rare_variants(groups, plan.regions, hap_off, sm_count, plan.haps_per_task * (plan.max_hap_len + 1));
 
     // launches ordered by variant (largest footprint first); stable within a variant
     std::vector<uint32_t> gorder(groups.size());

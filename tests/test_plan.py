@@ -76,3 +76,18 @@ def test_rejects_malformed_jobs(built):
     with pytest.raises(engine.PmmError):
         engine.plan(empty_hap)
     assert len(engine.plan(good)) == 1
+
+
+def test_rare_variants_join_the_next_larger_launch(built):
+    """A few short reads do not get a kernel launch of their own; a large share of short reads does."""
+    from acc_genomics_b200 import engine
+    rng = np.random.Generator(np.random.PCG64(7))
+    haps = [450] * 40
+    few = [synth.region(rng, [151] * 90 + [70, 80, 90, 100, 101, 110, 120, 130, 140, 150], haps) for _ in range(4)]
+    tasks = engine.plan(few)
+    assert {(t["K"], t["W"]) for t in tasks} == {(19, 8)}
+    coverage(few, tasks)
+    half = [synth.region(rng, [151] * 52 + [101] * 48, haps) for _ in range(40)]
+    tasks = engine.plan(half)
+    assert {(t["K"], t["W"]) for t in tasks} == {(19, 8), (13, 8)}
+    coverage(half, tasks)
