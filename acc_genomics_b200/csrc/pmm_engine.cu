@@ -342,14 +342,17 @@ int stage_single_region(pmm_ctx* c, const JobSource& src)
 
 // Host worker threads for the per-result log10 (the one piece of the path that stays on the host so that it uses the
 // host libm like the reference).  Created once per process on first use; a fetch hands out chunks and takes part
-// itself, so small jobs never wait for a wake-up.  Calls from several contexts are serialised (each lasts tens of us).
+// itself, so small jobs never wait for a wake-up.  A call that finds the workers taken runs on its own thread.
 class HostWorkers {
  public:
     static HostWorkers& get() { static HostWorkers w; return w; }
     void run(uint64_t n, uint64_t grain, const std::function<void(uint64_t, uint64_t)>& f)
     {
         if (n <= grain || th_.empty()) { f(0, n); return; }
-        std::lock_guard<std::mutex> call(call_mu_);
+        // Workers busy with another context's results: the process is streaming jobs through several contexts, and
+        // the caller's own thread is the parallelism (24 feeder threads on an 8-GPU box) -- do not queue up behind them.
+        std::unique_lock<std::mutex> call(call_mu_, std::try_to_lock);
+        if (!call.owns_lock()) { f(0, n); return; }
         {
             std::lock_guard<std::mutex> lk(mu_);
             fn_ = &f; n_ = n; grain_ = grain; next_.store(0); busy_ = (int)th_.size(); ++gen_;

@@ -16,7 +16,7 @@ LIB = os.path.join(ROOT, "pairhmm", "lib")
 
 @pytest.fixture(scope="module")
 def host(built):
-    if not os.path.exists(os.path.join(BIN, "selftest")):
+    if not all(os.path.exists(os.path.join(BIN, b)) for b in ("selftest", "pairhmm_host_tb", "pairhmm_test")):
         subprocess.run(["make", "-C", os.path.join(ROOT, "pairhmm")], check=True, stdout=subprocess.DEVNULL)
     return BIN
 
@@ -132,3 +132,36 @@ def test_client_threads_share_the_manager(host, golden_folder):
     assert f"bit-identical {pairs} of {pairs}" in out
     used = [ln for ln in out.splitlines() if ln.startswith("env ") and not ln.endswith("tasks 0")]
     assert len(used) >= 2
+
+
+# ---- the standalone entry: class FalconPairHMM (reference: pairhmm/xlnx/host/FalconPairHMM.h) ------------------
+def test_falcon_entry_builds_and_refuses_to_run_without_a_gpu(host):
+    syms = subprocess.run(["nm", "-DC", "--defined-only", os.path.join(LIB, "libfalcon_pairhmm.so")], capture_output=True, text=True).stdout
+    for name in ("FalconPairHMM::computePairhmm(", "FalconPairHMM::computePairhmmFalcon(", "FalconPairHMM::get_kernel_time(",
+                 "worthFPGA(", "countCell("):
+        assert name in syms, name
+    import torch
+    if not torch.cuda.is_available():
+        out = run(os.path.join(host, "pairhmm_test"), "-", "--syn", "1", ok=(2,))
+        assert "no CPU fallback" in out
+
+
+@pytest.mark.gpu
+def test_falcon_entry_against_golden_folder(host, golden_folder):
+    folder, pairs = golden_folder
+    out = run(os.path.join(host, "pairhmm_test"), "-", "--real", folder)
+    assert f"bit-identical results: {pairs} of {pairs}" in out and "0 results with significant error" in out
+
+
+@pytest.mark.gpu
+def test_falcon_entry_synthetic_cases_checked_by_the_oracle(host, checker, tmp_path):
+    """The bench's own synthetic shapes (16(i+1) reads x (i+1) haplotypes, ragged lengths): invariants inside the bench,
+    values against the oracle here."""
+    out = run(os.path.join(host, "pairhmm_test"), "-", "--syn", "6", "--dump", str(tmp_path))
+    assert "invariant failures: 0" in out
+    for i in range(6):
+        b = fixtures.read_input(str(tmp_path / f"input{i}"))
+        assert b.num_read == 16 * (i + 1) and b.num_hap == i + 1
+        want = checker.batch(b, threads=8)[1]
+        got = fixtures.read_output(str(tmp_path / f"output{i}"))
+        assert np.array_equal(got.view(np.int64), np.asarray(want).view(np.int64)), i
