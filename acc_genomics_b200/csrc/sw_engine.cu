@@ -148,10 +148,10 @@ int sw_align_batch(sw_ctx* c, uint32_t n_pairs,
         uint64_t words = 0; const uint32_t first = k;
         while (k < n_pairs) {
             const uint32_t p = order[k];
-            const uint32_t stride = (seq2_len[p] + 7) / 8;
+            const uint32_t stride = (seq2_len[p] + 31 + 7) / 8;      // words per row: codes are indexed by step (l2 + 31 of them)
             const uint64_t w = (uint64_t)seq1_len[p] * stride;
             if (k > first && words + w > c->bt_budget_words) break;
-            hp[k] = PairDesc{seq1_start[p], seq1_len[p], seq2_start[p], seq2_len[p], words, stride, p};
+            hp[k] = PairDesc{seq1_start[p], seq1_len[p], seq2_start[p], seq2_len[p], words, stride, p, pick_rows_per_lane(seq1_len[p]), 0u};
             words += w; ++k;
         }
         chunks.emplace_back(first, k);
@@ -173,7 +173,7 @@ int sw_align_batch(sw_ctx* c, uint32_t n_pairs,
         a.n_elem = static_cast<int32_t*>(c->d_nelem.p); a.offset = static_cast<int32_t*>(c->d_off.p);
         a.score = static_cast<int32_t*>(c->d_score.p);
         a.max_l1 = 0; a.max_l2 = 0;
-        a.k_neg1 = -1; a.k_two = 2; a.k_four = 4; a.k_eight = 8;
+        a.k_neg1 = -1; a.k_one = 1;
         for (uint32_t k = ch.first; k < ch.second; ++k) { a.max_l1 = std::max(a.max_l1, hp[k].l1); a.max_l2 = std::max(a.max_l2, hp[k].l2); }
         SW_CUDA(c, cudaMemsetAsync(a.counter, 0, sizeof(uint32_t), s));
         SW_CUDA(c, launch_align(a, c->sm_count, s, nullptr));

@@ -62,18 +62,184 @@ __device__ __forceinline__ WarpSmem carve(char* base, uint32_t max_l1, uint32_t 
     return w;
 }
 
-template <int K>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) sw_align_kernel(const Args a)
+// Rows per lane available to the fill (a block of rows = 32 lanes x K rows).  The host picks K per pair so that the
+// pair's rows fill its blocks (pick_rows_per_lane): a 375-row matrix takes one block of K = 12 (384 rows) instead of
+// two of K = 8 (512 rows, and two fill/drain phases).
+#define SW_ROWS_PER_LANE(X) X(4) X(6) X(8) X(10) X(12) X(14)
+constexpr uint32_t kMaxRowsPerLane = 14;          // 16 rows per lane do not fit 128 registers (4 CTAs per SM) without spills
+
+struct FillCtx {
+    WarpSmem sm;
+    const uint8_t* s1;
+    uint32_t* B;
+    uint32_t stride;
+    int nrow, ncol, lane;
+    int match, mismatch, open, extend;
+    bool indel;
+    int neg1, one;
+};
+
+// CUTOFF: apply max(MATRIX_MIN_CUTOFF, .) to the diagonal term like the reference (PairWiseSW.h:31).  The host drops it
+// when the weights and lengths of the chunk cannot produce a score anywhere near -10^8 (see launch_align).
+template <int K, bool CUTOFF>
+__device__ __forceinline__ void fill_matrix(const FillCtx& c)
+{
+    const WarpSmem sm = c.sm;
+    const int nrow = c.nrow, ncol = c.ncol, lane = c.lane;
+    const int match = c.match, mismatch = c.mismatch, open = c.open, extend = c.extend;
+    const bool indel = c.indel;
+    const int neg1 = c.neg1;                       // -1, kept opaque to the compiler (see cells())
+#ifndef SW_FMA_ADDS
+#define SW_FMA_ADDS 0                              // bit 0: E/F adds, bit 1: diagonal add as multiply-adds (FMA pipe)
+#endif
+    const int one = c.one;
+    auto add_ef = [&](int x, int y) { return (SW_FMA_ADDS & 1) ? imad(x, one, y) : x + y; };
+    auto add_m = [&](int x, int y) { return (SW_FMA_ADDS & 2) ? imad(x, one, y) : x + y; };
+    {
+        const int nblk = (nrow + 32 * K - 1) / (32 * K);
+        #pragma unroll 1
+        for (int blk = 0; blk < nblk; ++blk) {
+            const int ifirst = blk * 32 * K + lane * K + 1;           // 1-based row of this lane's first row
+            int Hrow[K], E[K];
+            uint32_t acc[K];                                           // the last 8 steps' codes of each row, newest lowest
+            int c1[K];
+            #pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const int i = ifirst + k;
+                c1[k] = i <= nrow ? (int)c.s1[i - 1] : -1;
+                Hrow[k] = indel ? open + (i - 1) * extend : 0;       // H[i][0]
+                E[k] = kLowInit;
+                acc[k] = 0;
+            }
+            uint32_t* const brow0 = c.B + (size_t)(ifirst - 1) * c.stride;   // backtrack row of the lane's first row
+            const int nvalid = min(K, nrow - ifirst + 1);               // rows of this lane that exist (<= 0: none)
+            int prev_up = (ifirst - 1 == 0) ? 0 : (indel ? open + (ifirst - 2) * extend : 0);   // H[ifirst-1][0]
+            int lastF = kLowInit;
+            // the lane and row that hold the matrix's last row (for the end-cell search); -1 if not in this block
+            const int own_k = (nrow >= ifirst && nrow < ifirst + K) ? nrow - ifirst : -1;
+            const bool blk_has_owner = __any_sync(0xffffffffu, own_k >= 0);
+            const bool own_b0 = (own_k & 1) != 0, own_b1 = (own_k & 2) != 0, own_b2 = (own_k & 4) != 0, own_b3 = (own_k & 8) != 0;
+
+            // Column j of this lane's K rows.  MAIN_CODE (PairWiseSW.h:4-40): same comparisons, same order.
+            // Pipe balance: adds, min/max, compares, selects and shifts issue on the ALU pipe (half rate), multiply-adds
+            // with at most two register operands on the FMA pipe.  Each of the four tie-breaks of a cell is the sign of a
+            // difference (a multiply-add by a -1 ptxas cannot see through), and one funnel shift both extracts that sign
+            // and appends it to the row's code word: acc = (acc << 1) | (diff >> 31).  Eight steps fill a word, older
+            // codes fall off the top, nothing is ever reset or positioned.  (Differences cannot overflow:
+            // |values| <= 2^30 + 2^20.)  History: compare + select + multiply-add packing with a per-step flush test,
+            // 40 instructions per cell, 433 GCUPS; this form 24.
+            auto cells = [&](const int j, const int c2, int upH, int upF) {
+                int diag = prev_up;
+                prev_up = upH;
+                int hup = upH, fup = upF;
+                #pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const int hleft = Hrow[k];
+                    const int ext_h = add_ef(E[k], extend), open_h = add_ef(hleft, open);
+                    const int e11 = max(ext_h, open_h);
+                    const int d_ins_open = imad(open_h, neg1, ext_h);           // < 0: open_h > ext_h; ties extend
+                    const int ext_v = add_ef(fup, extend), open_v = add_ef(hup, open);
+                    const int f11 = max(ext_v, open_v);
+                    const int d_del_open = imad(open_v, neg1, ext_v);
+                    const int m11 = add_m(diag, c1[k] == c2 ? match : mismatch);
+                    const int h0 = CUTOFF ? max(kMinCutoff, m11) : m11;
+                    const int d_take_ins = imad(e11, neg1, h0);                 // < 0: e11 > h0
+                    const int h1 = max(h0, e11);
+                    const int d_take_del = imad(f11, neg1, h1);                 // < 0: f11 > h1
+                    const int h11 = max(h1, f11);
+                    uint32_t w = acc[k];
+                    w = __funnelshift_l((uint32_t)d_ins_open, w, 1);
+                    w = __funnelshift_l((uint32_t)d_del_open, w, 1);
+                    w = __funnelshift_l((uint32_t)d_take_ins, w, 1);
+                    w = __funnelshift_l((uint32_t)d_take_del, w, 1);
+                    acc[k] = w;
+                    diag = hleft;
+                    Hrow[k] = h11; E[k] = e11; hup = h11; fup = f11;
+                }
+                lastF = fup;
+                if (blk_has_owner) {                                    // warp-uniform: no reconvergence point in the loop
+                    // Hrow[own_k] by a select tree on the bits of own_k (loop-invariant predicates, no compares)
+                    int v[K];
+                    #pragma unroll
+                    for (int k = 0; k < K; ++k) v[k] = Hrow[k];
+                    #pragma unroll
+                    for (int bit = 0, n = K; n > 1; ++bit, n = (n + 1) / 2) {
+                        const bool b = bit == 0 ? own_b0 : bit == 1 ? own_b1 : bit == 2 ? own_b2 : own_b3;
+                        #pragma unroll
+                        for (int m = 0; 2 * m < n; ++m) v[m] = (2 * m + 1 < n && b) ? v[2 * m + 1] : v[2 * m];
+                    }
+                    if (own_k >= 0) sm.lastrow[j] = v[0];
+                }
+                if (lane == 31) { sm.carryH[j] = Hrow[K - 1]; sm.carryF[j] = lastF; }
+            };
+            auto store_words = [&](const int word, const int shift) {
+                #pragma unroll
+                for (int k = 0; k < K; ++k)
+                    if (k < nvalid) brow0[(size_t)k * c.stride + word] = acc[k] << shift;
+            };
+
+            // Backtrack words are indexed by step, not by column: the code of row i, column j sits in word t >> 3 of the
+            // row, nibble 7 - (t & 7), with t = j - 1 + (lane of row i).  All lanes then complete a word at the same
+            // step, and the steady loop needs no test at all.
+            const int steps = ncol + 31;
+            int t = 0;
+            // steps where some lanes have no column (fill, drain) or that do not line up with a word
+            auto ragged = [&](const int tend) {
+                #pragma unroll 1
+                for (; t < tend; ++t) {
+                    int upH = __shfl_up_sync(0xffffffffu, Hrow[K - 1], 1);
+                    int upF = __shfl_up_sync(0xffffffffu, lastF, 1);
+                    const int j = t - lane + 1;
+                    if (j >= 1 && j <= ncol) {
+                        if (lane == 0) { upH = sm.carryH[j]; upF = sm.carryF[j]; }
+                        cells(j, (int)sm.alt[j - 1], upH, upF);
+                        const int u = t & 7;
+                        if (u == 7 || j == ncol) store_words(t >> 3, 4 * (7 - u));   // a row's last word: left-aligned
+                    }
+                }
+            };
+            if (ncol >= 40) {
+                ragged(32);
+                // The step body is kept once in the instruction stream (the funnel-shift packing needs no position, so
+                // nothing forces an unroll): unrolled eight times it is 23 KB, streams through the instruction caches
+                // and "no instruction" becomes the top stall (ncu: 1.0 per issued instruction).  Branch-free: every lane
+                // reads the carry row at its own column and lane 0 keeps the value; the alternate base of the next
+                // step is fetched one step ahead.
+                const bool lane0 = lane == 0;
+                int c2 = (int)sm.alt[t - lane];                        // column t - lane + 1
+                #pragma unroll 1
+                for (; t + 8 <= ncol; t += 8) {
+                    #pragma unroll 1
+                    for (int u = 0; u < 8; ++u) {
+                        const int j = t + u - lane + 1;
+                        const int sH = __shfl_up_sync(0xffffffffu, Hrow[K - 1], 1);
+                        const int sF = __shfl_up_sync(0xffffffffu, lastF, 1);
+                        const int cH = sm.carryH[j], cF = sm.carryF[j];
+                        const int c2n = (int)sm.alt[j];                // next step's base (one slack byte past the end)
+                        cells(j, c2, lane0 ? cH : sH, lane0 ? cF : sF);
+                        c2 = c2n;
+                    }
+                    store_words(t >> 3, 0);
+                }
+            }
+            ragged(steps);
+            // H[i][ncol] of the lane's rows: still in registers, nothing touched them after the last column
+            #pragma unroll
+            for (int k = 0; k < K; ++k) if (ifirst + k <= nrow) sm.lastcol[ifirst + k] = Hrow[k];
+            __syncwarp();
+        }
+    }
+}
+
+template <bool CUTOFF>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 4) sw_align_kernel(const Args a)
 {
     extern __shared__ int4 smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t per_warp = per_warp_bytes(a.max_l1, a.max_l2);
     const WarpSmem sm = carve(reinterpret_cast<char*>(smem_raw) + warp * per_warp, a.max_l1, a.max_l2);
-    const int match = a.match, mismatch = a.mismatch, open = a.open, extend = a.extend, strategy = a.strategy;
+    const int open = a.open, extend = a.extend, strategy = a.strategy;
     const bool indel = strategy == kIndel || strategy == kLeadingIndel;
-    // multipliers the compiler must not know (see the step function): the host passes -1, 2, 4, 8
-    const int neg1 = a.k_neg1, two = a.k_two, four = a.k_four, eight = a.k_eight;
-    auto sign_of = [](int x) { return (unsigned)x >> 31; };
 
     for (;;) {
         uint32_t p = 0;
@@ -82,10 +248,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sw_align_kernel(const Args 
         if (p >= a.npairs) break;
         const PairDesc pd = a.pairs[p];
         const int nrow = (int)pd.l1, ncol = (int)pd.l2;
-        const uint8_t* s1 = a.seq1 + pd.s1;
         const uint8_t* s2 = a.seq2 + pd.s2;
         uint32_t* B = a.bt + pd.bt_off;
         const uint32_t stride = pd.bt_stride;
+        const int K = (int)pd.rows_per_lane;
+        const uint32_t kdiv = ((1u << 20) + K - 1) / K;                 // (x * kdiv) >> 20 == x / K for x < 4096
+        auto lane_of_row = [&](int row) { return (int)((((uint32_t)(row - 1) * kdiv) >> 20) & 31u); };
 
         __syncwarp();
         for (int x = lane; x < ncol; x += 32) sm.alt[x] = s2[x];
@@ -97,133 +265,50 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sw_align_kernel(const Args 
         __syncwarp();
 
         // ---- matrix fill -----------------------------------------------------------------------------------------
-        const int nblk = (nrow + 32 * K - 1) / (32 * K);
-        #pragma unroll 1
-        for (int blk = 0; blk < nblk; ++blk) {
-            const int ifirst = blk * 32 * K + lane * K + 1;           // 1-based row of this lane's first row
-            int Hrow[K], E[K];
-            uint32_t acc[K];
-            int c1[K];
-            uint32_t* brow[K];                                         // backtrack row of each of the lane's rows
-            #pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const int i = ifirst + k;
-                c1[k] = i <= nrow ? (int)s1[i - 1] : -1;
-                Hrow[k] = indel ? open + (i - 1) * extend : 0;       // H[i][0]
-                E[k] = kLowInit;
-                acc[k] = 0;
-                brow[k] = i <= nrow ? B + (size_t)(i - 1) * stride : nullptr;
+        {
+            const FillCtx fc{sm, a.seq1 + pd.s1, B, stride, nrow, ncol, lane, a.match, a.mismatch, open, extend, indel, a.k_neg1, a.k_one};
+            switch (K) {
+#define X(k) case k: fill_matrix<k, CUTOFF>(fc); break;
+                SW_ROWS_PER_LANE(X)
+#undef X
+                default: break;                                         // the host only hands out the values above
             }
-            int prev_up = (ifirst - 1 == 0) ? 0 : (indel ? open + (ifirst - 2) * extend : 0);   // H[ifirst-1][0]
-            int lastF = kLowInit;
-            // the lane and row that hold the matrix's last row (for the end-cell search); -1 if not in this block
-            const int own_k = (nrow >= ifirst && nrow < ifirst + K) ? nrow - ifirst : -1;
-
-            // one step: column j of this lane's K rows.  MAIN_CODE (PairWiseSW.h:4-40): same comparisons, same order.
-            // Pipe balance: compares, selects, min/max and shifts issue on the ALU pipe, multiply-adds on the FMA pipe, and
-            // the straightforward form of this update is 29 ALU instructions per cell.  Here each tie-break bit is the
-            // sign of a difference (a multiply-add by -1 that ptxas cannot see through, then one shift) instead of a
-            // compare plus a select, and the four bits are packed and appended to the row's word by multiply-adds.
-            // Measured on 16 640 pairs: 431 GCUPS against 406 for compare/select; moving the remaining adds and the
-            // sign extraction (mul.hi) to the FMA pipe as well was slower (366): three-register IMAD forms issue at half
-            // rate like three-register FFMA.  (Differences cannot overflow: |values| <= 2^30 + 2^20.)
-            auto step = [&](const int j, int upH, int upF) {
-                const int c2 = (int)sm.alt[j - 1];
-                int diag = prev_up;
-                prev_up = upH;
-                int hup = upH, fup = upF;
-                const int pw = 1 << (4 * ((j - 1) & 7));               // where this column's 4 bits go in the word
-                const bool flush = ((j - 1) & 7) == 7 || j == ncol;
-                #pragma unroll
-                for (int k = 0; k < K; ++k) {
-                    const int hleft = Hrow[k];
-                    const int ext_h = E[k] + extend, open_h = hleft + open;
-                    const int e11 = max(ext_h, open_h);
-                    const unsigned ins_open = sign_of(imad(open_h, neg1, ext_h));   // open_h > ext_h; ties extend
-                    const int ext_v = fup + extend, open_v = hup + open;
-                    const int f11 = max(ext_v, open_v);
-                    const unsigned del_open = sign_of(imad(open_v, neg1, ext_v));
-                    const int m11 = diag + (c1[k] == c2 ? match : mismatch);
-                    const int h0 = max(kMinCutoff, m11);
-                    const unsigned take_ins = sign_of(imad(e11, neg1, h0));          // e11 > h0
-                    const int h1 = max(h0, e11);
-                    const unsigned take_del = sign_of(imad(f11, neg1, h1));          // f11 > h1
-                    const int h11 = max(h1, f11);
-                    const int code = imad((int)take_del, eight, imad((int)take_ins, four, imad((int)del_open, two, (int)ins_open)));
-                    diag = hleft;
-                    Hrow[k] = h11; E[k] = e11; hup = h11; fup = f11;
-                    acc[k] = (uint32_t)imad(code, pw, (int)acc[k]);
-                    if (flush) {
-                        if (brow[k]) brow[k][(j - 1) >> 3] = acc[k];
-                        acc[k] = 0;
-                    }
-                }
-                lastF = fup;
-                if (own_k >= 0) {
-                    int v = Hrow[0];
-                    #pragma unroll
-                    for (int k = 1; k < K; ++k) v = own_k == k ? Hrow[k] : v;
-                    sm.lastrow[j] = v;
-                }
-                if (lane == 31) { sm.carryH[j] = Hrow[K - 1]; sm.carryF[j] = lastF; }
-            };
-
-            const int steps = ncol + 31;
-            int t = 0;
-            // fill: lanes join one per step
-            #pragma unroll 1
-            for (; t < min(31, steps); ++t) {
-                int upH = __shfl_up_sync(0xffffffffu, Hrow[K - 1], 1);
-                int upF = __shfl_up_sync(0xffffffffu, lastF, 1);
-                const int j = t - lane + 1;
-                if (j >= 1 && j <= ncol) {
-                    if (lane == 0) { upH = sm.carryH[j]; upF = sm.carryF[j]; }
-                    step(j, upH, upF);
-                }
-            }
-            // steady: every lane has a column
-            #pragma unroll 1
-            for (; t < ncol; ++t) {
-                int upH = __shfl_up_sync(0xffffffffu, Hrow[K - 1], 1);
-                int upF = __shfl_up_sync(0xffffffffu, lastF, 1);
-                const int j = t - lane + 1;
-                if (lane == 0) { upH = sm.carryH[j]; upF = sm.carryF[j]; }
-                step(j, upH, upF);
-            }
-            // drain
-            #pragma unroll 1
-            for (; t < steps; ++t) {
-                int upH = __shfl_up_sync(0xffffffffu, Hrow[K - 1], 1);
-                int upF = __shfl_up_sync(0xffffffffu, lastF, 1);
-                const int j = t - lane + 1;
-                if (j >= 1 && j <= ncol) {
-                    if (lane == 0) { upH = sm.carryH[j]; upF = sm.carryF[j]; }
-                    step(j, upH, upF);
-                }
-            }
-            // H[i][ncol] of the lane's rows: still in registers, nothing touched them after the last column
-            #pragma unroll
-            for (int k = 0; k < K; ++k) if (ifirst + k <= nrow) sm.lastcol[ifirst + k] = Hrow[k];
-            __syncwarp();
         }
 
         // ---- end cell (PairWiseSW.h:233-262): anti-diagonals ascending, last-row cell before last-column cell ----------
+        // The reference scans the candidates one by one and keeps the first cell of the best score unless a later one of
+        // the same score wins a tie-break against the cell held at that moment.  Cells below the final maximum can never
+        // influence the outcome (the first cell that reaches it replaces whatever is held), so: the maximum by a warp
+        // reduction, then only the cells that attain it, in the reference's order, 32 anti-diagonals per ballot.
         int ti = 0, tj = 0, seg = 0, best = INT32_MIN;
-        if (lane == 0) {
-            int max_i = 0, max_j = 0;
-            bool updated = false;
-            for (int ad = 1; ad <= nrow + ncol; ++ad) {
-                const int jj = ad - nrow;
-                if (jj >= 1 && jj <= ncol && (strategy == kSoftClip || strategy == kIgnore)) {
-                    const int s = sm.lastrow[jj];
-                    if (best < s || (best == s && abs(nrow - jj) < abs(max_i - max_j))) { best = s; max_i = nrow; max_j = jj; updated = true; }
-                }
-                const int ii = ad - ncol;
-                if (ii >= 1 && ii <= nrow) {
-                    const int s = sm.lastcol[ii];
-                    if (best < s || (best == s && (max_j == ncol || abs(ii - ncol) <= abs(max_i - max_j)))) { best = s; max_i = ii; max_j = ncol; updated = true; }
+        int max_i = 0, max_j = 0;
+        const bool updated = true;                 // some candidate is always taken: the last column has nrow >= 1 cells
+        {
+            const bool use_row = strategy == kSoftClip || strategy == kIgnore;
+            for (int x = lane + 1; x <= nrow; x += 32) best = max(best, sm.lastcol[x]);
+            if (use_row) for (int x = lane + 1; x <= ncol; x += 32) best = max(best, sm.lastrow[x]);
+            #pragma unroll
+            for (int d = 16; d; d >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, d));
+            bool have = false;                      // a cell of the maximal score is held (same on every lane)
+            for (int base = 1; base <= nrow + ncol; base += 32) {
+                const int ad = base + lane, jj = ad - nrow, ii = ad - ncol;
+                const bool rt = use_row && jj >= 1 && jj <= ncol && sm.lastrow[jj] == best;
+                const bool ct = ii >= 1 && ii <= nrow && sm.lastcol[ii] == best;
+                const unsigned rb = __ballot_sync(0xffffffffu, rt), cb = __ballot_sync(0xffffffffu, ct);
+                for (unsigned any = rb | cb; any; any &= any - 1) {
+                    const int l = __ffs((int)any) - 1, a2 = base + l;
+                    if ((rb >> l) & 1u) {                                  // last-row cell (nrow, a2 - nrow) comes first
+                        const int j2 = a2 - nrow;
+                        if (!have || abs(nrow - j2) < abs(max_i - max_j)) { max_i = nrow; max_j = j2; have = true; }
+                    }
+                    if ((cb >> l) & 1u) {                                  // then the last-column cell (a2 - ncol, ncol)
+                        const int i2 = a2 - ncol;
+                        if (!have || max_j == ncol || abs(i2 - ncol) <= abs(max_i - max_j)) { max_i = i2; max_j = ncol; have = true; }
+                    }
                 }
             }
+        }
+        if (lane == 0) {
             // start of the traceback (getCIGAR, :285-314)
             if (strategy == kIndel) { ti = nrow; tj = ncol; }
             else if (strategy == kLeadingIndel) { ti = max_i; tj = ncol; }
@@ -246,9 +331,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sw_align_kernel(const Args 
         for (;;) {
             const int ai = __shfl_sync(0xffffffffu, ti, 0), aj = __shfl_sync(0xffffffffu, tj, 0);
             if (!(ai > 0 && aj > 0)) break;
-            const int cw0 = max(0, ((aj - 1) >> 3) - 7);
+            // Each row's codes are indexed by step (t = j - 1 + lane of the row), so each row of the tile has its own
+            // window of 8 words ending at the word that holds column aj.
+            auto first_word = [&](int row) { return max(0, ((aj - 1 + lane_of_row(row)) >> 3) - 7); };
             {
                 const int row = ai - lane;
+                const int cw0 = row >= 1 ? first_word(row) : 0;
                 #pragma unroll
                 for (int w = 0; w < 8; ++w) {
                     uint32_t v = 0;
@@ -258,16 +346,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sw_align_kernel(const Args 
             }
             __syncwarp();
             if (lane == 0) {
-                while (ti > 0 && tj > 0 && ai - ti < 32 && ((tj - 1) >> 3) >= cw0) {
-                    const int btr = (int)((sm.tile[(((tj - 1) >> 3) - cw0) * 32 + (ai - ti)] >> (4 * ((tj - 1) & 7))) & 15u);
-                    // stored bits: 0 insertion opened (not an extension), 1 deletion opened, 2 insertion taken, 3 deletion
+                while (ti > 0 && tj > 0 && ai - ti < 32) {
+                    const int tt = tj - 1 + lane_of_row(ti), word = (tt >> 3) - first_word(ti);
+                    if (word < 0) break;
+                    const int btr = (int)((sm.tile[word * 32 + (ai - ti)] >> (4 * (7 - (tt & 7)))) & 15u);
+                    // stored bits: 3 insertion opened (not an extension), 2 deletion opened, 1 insertion taken, 0 deletion
                     // taken (it wins over the insertion); the reference's codes are move + "was an extension" flags
-                    const int ins_ext = (btr & 1) ? 0 : kInsertExt, del_ext = (btr & 2) ? 0 : kDeleteExt;
+                    const int ins_ext = (btr & 8) ? 0 : kInsertExt, del_ext = (btr & 4) ? 0 : kDeleteExt;
                     if (state == kInsertExt) { --tj; emit(kInsert, 1); state = ins_ext; }
                     else if (state == kDeleteExt) { --ti; emit(kDelete, 1); state = del_ext; }
                     else {
-                        if (btr & 8) { --ti; emit(kDelete, 1); state = del_ext; }
-                        else if (btr & 4) { --tj; emit(kInsert, 1); state = ins_ext; }
+                        if (btr & 1) { --ti; emit(kDelete, 1); state = del_ext; }
+                        else if (btr & 2) { --tj; emit(kInsert, 1); state = ins_ext; }
                         else { --ti; --tj; emit(0, (raw_ops == 0 && strategy == kIgnore) ? seg + 1 : 1); state = 0; }
                         ++raw_ops;
                     }
@@ -303,10 +393,25 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sw_align_kernel(const Args 
 
 size_t smem_bytes_per_warp(uint32_t max_l1, uint32_t max_l2) { return per_warp_bytes(max_l1, max_l2); }
 
-cudaError_t launch_align(const Args& a, int sm_count, cudaStream_t s, int* ctas_out)
+// Rows per lane for a matrix of l1 rows: as few blocks as the largest K allows, then the smallest instantiated K
+// whose blocks hold the rows (the unused rows of the last lanes are computed and thrown away).
+uint32_t pick_rows_per_lane(uint32_t l1)
+{
+    const uint32_t nblk = (l1 + 32 * kMaxRowsPerLane - 1) / (32 * kMaxRowsPerLane);
+    const uint32_t per_block = (l1 + nblk - 1) / nblk;
+    const uint32_t k = (per_block + 31) / 32;
+    uint32_t best = kMaxRowsPerLane;
+#define X(v) if (v >= k && v < best) best = v;
+    SW_ROWS_PER_LANE(X)
+#undef X
+    return best;
+}
+
+template <bool CUTOFF>
+static cudaError_t launch_align_t(const Args& a, int sm_count, cudaStream_t s, int* ctas_out)
 {
     const size_t smem = kWarpsPerCta * smem_bytes_per_warp(a.max_l1, a.max_l2);
-    auto kern = sw_align_kernel<kRowsPerLane>;
+    auto kern = sw_align_kernel<CUTOFF>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
@@ -318,6 +423,22 @@ cudaError_t launch_align(const Args& a, int sm_count, cudaStream_t s, int* ctas_
     if (ctas_out) *ctas_out = ctas;
     kern<<<ctas, kWarpsPerCta * 32, smem, s>>>(a);
     return cudaGetLastError();
+}
+
+cudaError_t launch_align(const Args& a, int sm_count, cudaStream_t s, int* ctas_out)
+{
+    // The reference clamps the diagonal term at MATRIX_MIN_CUTOFF = -10^8 (PairWiseSW.h:31).  Every H is at least the
+    // smallest boundary value plus min(i, j) diagonal steps, so with L = the longest sequence of the chunk no diagonal
+    // term is below  min(0, open, open + (L-1) extend) + (L+1) min(match, mismatch, 0);  when that is above the cutoff the
+    // clamp never acts and the kernel without it (one ALU instruction per cell fewer) gives identical results.
+    const long long L = (long long)(a.max_l1 > a.max_l2 ? a.max_l1 : a.max_l2);
+    long long bmin = 0;
+    if ((long long)a.open < bmin) bmin = a.open;
+    if ((long long)a.open + (L - 1) * a.extend < bmin) bmin = (long long)a.open + (L - 1) * a.extend;
+    long long step = a.match < a.mismatch ? a.match : a.mismatch;
+    if (step > 0) step = 0;
+    const bool clamp_can_act = bmin + (L + 1) * step <= (long long)kMinCutoff;
+    return clamp_can_act ? launch_align_t<true>(a, sm_count, s, ctas_out) : launch_align_t<false>(a, sm_count, s, ctas_out);
 }
 
 }  // namespace sw
