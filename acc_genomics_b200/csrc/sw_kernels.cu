@@ -37,7 +37,7 @@ __device__ __forceinline__ int imad(int a, int b, int c)
 }
 
 struct WarpSmem {
-    int* carryH; int* carryF; int* lastrow; int* lastcol; uint32_t* tile; uint8_t* alt;
+    int* carryH; int* carryF; int* lastrow; int* lastcol; uint32_t* tile; uint32_t* tmeta; uint8_t* alt;
 };
 
 __host__ __device__ inline size_t align4(size_t x) { return (x + 3) & ~(size_t)3; }
@@ -45,7 +45,7 @@ __host__ __device__ inline size_t align4(size_t x) { return (x + 3) & ~(size_t)3
 __host__ __device__ inline size_t per_warp_bytes(uint32_t max_l1, uint32_t max_l2)
 {
     const size_t c1 = align4(max_l2 + 1), r1 = align4(max_l1 + 1);
-    const size_t b = sizeof(int) * (3 * c1 + r1) + sizeof(uint32_t) * 32 * 8 + align4(max_l2 + 4);
+    const size_t b = sizeof(int) * (3 * c1 + r1) + sizeof(uint32_t) * 32 * 9 + align4(max_l2 + 4);
     return (b + 15) & ~(size_t)15;
 }
 
@@ -58,7 +58,8 @@ __device__ __forceinline__ WarpSmem carve(char* base, uint32_t max_l1, uint32_t 
     w.lastrow = w.carryF + c1;
     w.lastcol = w.lastrow + c1;
     w.tile = reinterpret_cast<uint32_t*>(w.lastcol + r1);
-    w.alt = reinterpret_cast<uint8_t*>(w.tile + 32 * 8);
+    w.tmeta = w.tile + 32 * 8;
+    w.alt = reinterpret_cast<uint8_t*>(w.tile + 32 * 9);
     return w;
 }
 
@@ -332,35 +333,38 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) sw_align_kernel(const Ar
             const int ai = __shfl_sync(0xffffffffu, ti, 0), aj = __shfl_sync(0xffffffffu, tj, 0);
             if (!(ai > 0 && aj > 0)) break;
             // Each row's codes are indexed by step (t = j - 1 + lane of the row), so each row of the tile has its own
-            // window of 8 words ending at the word that holds column aj.
-            auto first_word = [&](int row) { return max(0, ((aj - 1 + lane_of_row(row)) >> 3) - 7); };
+            // window of 8 words ending at the word that holds column aj; the walker finds a row's lane and first word in
+            // tmeta.
             {
                 const int row = ai - lane;
-                const int cw0 = row >= 1 ? first_word(row) : 0;
+                const int lr = row >= 1 ? lane_of_row(row) : 0;
+                const int cw0 = max(0, ((aj - 1 + lr) >> 3) - 7);
                 #pragma unroll
                 for (int w = 0; w < 8; ++w) {
                     uint32_t v = 0;
                     if (row >= 1 && (uint32_t)(cw0 + w) < stride) v = __ldcg(B + (size_t)(row - 1) * stride + cw0 + w);
                     sm.tile[w * 32 + lane] = v;
                 }
+                sm.tmeta[lane] = (uint32_t)lr | ((uint32_t)cw0 << 8);
             }
             __syncwarp();
             if (lane == 0) {
                 while (ti > 0 && tj > 0 && ai - ti < 32) {
-                    const int tt = tj - 1 + lane_of_row(ti), word = (tt >> 3) - first_word(ti);
+                    const uint32_t meta = sm.tmeta[ai - ti];
+                    const int tt = tj - 1 + (int)(meta & 31u), word = (tt >> 3) - (int)(meta >> 8);
                     if (word < 0) break;
-                    const int btr = (int)((sm.tile[word * 32 + (ai - ti)] >> (4 * (7 - (tt & 7)))) & 15u);
+                    const int btr = (int)((sm.tile[word * 32 + (ai - ti)] >> (28 - 4 * (tt & 7))) & 15u);
                     // stored bits: 3 insertion opened (not an extension), 2 deletion opened, 1 insertion taken, 0 deletion
                     // taken (it wins over the insertion); the reference's codes are move + "was an extension" flags
                     const int ins_ext = (btr & 8) ? 0 : kInsertExt, del_ext = (btr & 4) ? 0 : kDeleteExt;
-                    if (state == kInsertExt) { --tj; emit(kInsert, 1); state = ins_ext; }
-                    else if (state == kDeleteExt) { --ti; emit(kDelete, 1); state = del_ext; }
-                    else {
-                        if (btr & 1) { --ti; emit(kDelete, 1); state = del_ext; }
-                        else if (btr & 2) { --tj; emit(kInsert, 1); state = ins_ext; }
-                        else { --ti; --tj; emit(0, (raw_ops == 0 && strategy == kIgnore) ? seg + 1 : 1); state = 0; }
-                        ++raw_ops;
-                    }
+                    // one move: inside a gap the state decides, otherwise the cell's own comparison results do
+                    const bool in_ins = state == kInsertExt, in_del = state == kDeleteExt, fresh = !(in_ins || in_del);
+                    const bool del = in_del || (fresh && (btr & 1)), ins = !del && (in_ins || (btr & 2));
+                    const int len = (fresh && !del && !ins && raw_ops == 0 && strategy == kIgnore) ? seg + 1 : 1;
+                    ti -= ins ? 0 : 1; tj -= del ? 0 : 1;
+                    state = del ? del_ext : ins ? ins_ext : 0;
+                    raw_ops += fresh ? 1 : 0;
+                    emit(del ? kDelete : ins ? kInsert : 0, len);
                 }
             }
             __syncwarp();
