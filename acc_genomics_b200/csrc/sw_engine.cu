@@ -6,6 +6,8 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -36,7 +38,7 @@ struct sw_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     std::string err;
-    Buf d_seq1, d_seq2, d_pairs, d_bt, d_cigars, d_nelem, d_off, d_score, d_counter;
+    Buf d_seq1, d_seq2, d_pairs, d_bt, d_cigars, d_compact, d_first, d_nelem, d_off, d_score, d_counter;
     Buf h_stage, h_out;
     uint64_t bt_budget_words = (1ull << 30);      // 4 GiB of backtrack codes per chunk
     sw_stats_t stats{};
@@ -80,7 +82,7 @@ void sw_destroy(sw_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (Buf* b : {&c->d_seq1, &c->d_seq2, &c->d_pairs, &c->d_bt, &c->d_cigars, &c->d_nelem, &c->d_off, &c->d_score, &c->d_counter, &c->h_stage, &c->h_out}) b->release();
+    for (Buf* b : {&c->d_seq1, &c->d_seq2, &c->d_pairs, &c->d_bt, &c->d_cigars, &c->d_compact, &c->d_first, &c->d_nelem, &c->d_off, &c->d_score, &c->d_counter, &c->h_stage, &c->h_out}) b->release();
     cudaEventDestroy(c->ev[0]); cudaEventDestroy(c->ev[1]);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -108,6 +110,8 @@ int sw_align_batch(sw_ctx* c, uint32_t n_pairs,
     if (overhang_strategy < 0 || overhang_strategy > 3) return c->fail(SW_ERR_INVALID, "unknown overhang strategy");
     if (!cigar_cap) return c->fail(SW_ERR_INVALID, "cigar_cap must be positive");
     const auto t0 = std::chrono::steady_clock::now();
+    static const bool trace = getenv("SW_TRACE") != nullptr;
+    auto mark = [&](const char* what) { if (trace) fprintf(stderr, "[sw] %-10s %.3f ms\n", what, std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count()); };
     cudaSetDevice(c->device);
     cudaStream_t s = c->stream;
 
@@ -122,15 +126,21 @@ int sw_align_batch(sw_ctx* c, uint32_t n_pairs,
     if (ext1 >= (1ull << 31) || ext2 >= (1ull << 31)) return c->fail(SW_ERR_INVALID, "sequence blobs larger than 2 GiB");
 
     // largest pairs first: warps pull pairs in order, the tail of the launch is made of the small ones
+    // (one 64-bit key per pair: cells descending, then the caller's order)
+    std::vector<uint64_t> keys(n_pairs);
+    for (uint32_t p = 0; p < n_pairs; ++p)
+        keys[p] = (((1ull << 24) - (uint64_t)seq1_len[p] * seq2_len[p]) << 32) | p;      // lengths <= 4095: cells < 2^24
+    std::sort(keys.begin(), keys.end());
     std::vector<uint32_t> order(n_pairs);
-    std::iota(order.begin(), order.end(), 0u);
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
-        return (uint64_t)seq1_len[x] * seq2_len[x] > (uint64_t)seq1_len[y] * seq2_len[y]; });
+    for (uint32_t k = 0; k < n_pairs; ++k) order[k] = (uint32_t)keys[k];
 
+    mark("sorted");
     SW_CUDA(c, c->d_seq1.reserve(ext1)); SW_CUDA(c, c->d_seq2.reserve(ext2));
     SW_CUDA(c, c->h_stage.reserve(ext1 + ext2 + sizeof(PairDesc) * (size_t)n_pairs + 64));
     SW_CUDA(c, c->d_pairs.reserve(sizeof(PairDesc) * (size_t)n_pairs));
     SW_CUDA(c, c->d_cigars.reserve(sizeof(int2) * (size_t)n_pairs * cigar_cap));
+    SW_CUDA(c, c->d_compact.reserve(sizeof(int2) * (size_t)n_pairs * cigar_cap));
+    SW_CUDA(c, c->d_first.reserve(sizeof(uint32_t) * (size_t)n_pairs));
     SW_CUDA(c, c->d_nelem.reserve(sizeof(int32_t) * (size_t)n_pairs));
     SW_CUDA(c, c->d_off.reserve(sizeof(int32_t) * (size_t)n_pairs));
     SW_CUDA(c, c->d_score.reserve(sizeof(int32_t) * (size_t)n_pairs));
@@ -160,7 +170,10 @@ int sw_align_batch(sw_ctx* c, uint32_t n_pairs,
     SW_CUDA(c, c->d_bt.reserve(max_words * sizeof(uint32_t)));
     SW_CUDA(c, cudaMemcpyAsync(c->d_pairs.p, hp, sizeof(PairDesc) * (size_t)n_pairs, cudaMemcpyHostToDevice, s));
 
+    mark("staged");
     uint32_t launches = 0;
+    uint32_t* d_count = static_cast<uint32_t*>(c->d_counter.p) + 32;      // compact CIGAR cursor, its own 128-byte line
+    SW_CUDA(c, cudaMemsetAsync(d_count, 0, sizeof(uint32_t), s));
     SW_CUDA(c, cudaEventRecord(c->ev[0], s));
     for (const auto& ch : chunks) {
         Args a{};
@@ -170,6 +183,7 @@ int sw_align_batch(sw_ctx* c, uint32_t n_pairs,
         a.bt = static_cast<uint32_t*>(c->d_bt.p);
         a.match = w_match; a.mismatch = w_mismatch; a.open = w_open; a.extend = w_extend; a.strategy = overhang_strategy;
         a.cigar_cap = cigar_cap; a.cigars = static_cast<int2*>(c->d_cigars.p);
+        a.compact = static_cast<int2*>(c->d_compact.p); a.compact_count = d_count; a.compact_first = static_cast<uint32_t*>(c->d_first.p);
         a.n_elem = static_cast<int32_t*>(c->d_nelem.p); a.offset = static_cast<int32_t*>(c->d_off.p);
         a.score = static_cast<int32_t*>(c->d_score.p);
         a.max_l1 = 0; a.max_l2 = 0;
@@ -181,20 +195,37 @@ int sw_align_batch(sw_ctx* c, uint32_t n_pairs,
     }
     SW_CUDA(c, cudaEventRecord(c->ev[1], s));
 
-    const size_t sz_c = sizeof(int2) * (size_t)n_pairs * cigar_cap, sz_i = sizeof(int32_t) * (size_t)n_pairs;
-    SW_CUDA(c, c->h_out.reserve(sz_c + 3 * sz_i));
+    mark("launched");
+    // Results: the per-pair integers and the number of CIGAR elements first, then the compact CIGAR array (a few
+    // elements per pair, contiguous) which is scattered into the caller's rows of cigar_cap elements here.
+    const size_t sz_i = sizeof(int32_t) * (size_t)n_pairs;
+    SW_CUDA(c, c->h_out.reserve(4 * sz_i + 64 + sizeof(int2) * (size_t)n_pairs * cigar_cap));   // grow-only: worst case once
     char* ho = static_cast<char*>(c->h_out.p);
-    SW_CUDA(c, cudaMemcpyAsync(ho, c->d_cigars.p, sz_c, cudaMemcpyDeviceToHost, s));
-    SW_CUDA(c, cudaMemcpyAsync(ho + sz_c, c->d_nelem.p, sz_i, cudaMemcpyDeviceToHost, s));
-    SW_CUDA(c, cudaMemcpyAsync(ho + sz_c + sz_i, c->d_off.p, sz_i, cudaMemcpyDeviceToHost, s));
-    SW_CUDA(c, cudaMemcpyAsync(ho + sz_c + 2 * sz_i, c->d_score.p, sz_i, cudaMemcpyDeviceToHost, s));
+    SW_CUDA(c, cudaMemcpyAsync(ho, c->d_nelem.p, sz_i, cudaMemcpyDeviceToHost, s));
+    SW_CUDA(c, cudaMemcpyAsync(ho + sz_i, c->d_off.p, sz_i, cudaMemcpyDeviceToHost, s));
+    SW_CUDA(c, cudaMemcpyAsync(ho + 2 * sz_i, c->d_score.p, sz_i, cudaMemcpyDeviceToHost, s));
+    SW_CUDA(c, cudaMemcpyAsync(ho + 3 * sz_i, c->d_first.p, sz_i, cudaMemcpyDeviceToHost, s));
+    SW_CUDA(c, cudaMemcpyAsync(ho + 4 * sz_i, d_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     SW_CUDA(c, cudaStreamSynchronize(s));
+    mark("synced");
+    memcpy(n_elem, ho, sz_i);
+    memcpy(alignment_offset, ho + sz_i, sz_i);
+    if (score) memcpy(score, ho + 2 * sz_i, sz_i);
     static_assert(sizeof(sw_cigar_elem_t) == sizeof(int2), "cigar element layout");
-    memcpy(cigars, ho, sz_c);
-    memcpy(n_elem, ho + sz_c, sz_i);
-    memcpy(alignment_offset, ho + sz_c + sz_i, sz_i);
-    if (score) memcpy(score, ho + sz_c + 2 * sz_i, sz_i);
+    uint32_t total = 0;
+    memcpy(&total, ho + 4 * sz_i, sizeof total);
+    if (total) {
+        const int2* hc = reinterpret_cast<const int2*>(ho + 4 * sz_i + 64);
+        SW_CUDA(c, cudaMemcpyAsync(const_cast<int2*>(hc), c->d_compact.p, sizeof(int2) * (size_t)total, cudaMemcpyDeviceToHost, s));
+        SW_CUDA(c, cudaStreamSynchronize(s));
+        const uint32_t* first = reinterpret_cast<const uint32_t*>(ho + 3 * sz_i);
+        for (uint32_t p = 0; p < n_pairs; ++p) {
+            const uint32_t stored = std::min<uint32_t>(cigar_cap, (uint32_t)std::max(0, n_elem[p]));
+            memcpy(cigars + (size_t)p * cigar_cap, hc + first[p], sizeof(int2) * (size_t)stored);
+        }
+    }
 
+    mark("scattered");
     c->stats = sw_stats_t{};
     c->stats.pairs = n_pairs; c->stats.cells = cells; c->stats.bytes_backtrack = max_words * sizeof(uint32_t);
     c->stats.kernel_launches = launches; c->stats.chunks = (uint32_t)chunks.size();

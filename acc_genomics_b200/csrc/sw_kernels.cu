@@ -383,9 +383,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) sw_align_kernel(const Ar
                 off = 0;
             }
             if (cur_state >= 0) { if ((uint32_t)n < a.cigar_cap) out[n] = make_int2(cur_len, cur_state); ++n; }
-            // forward order
+            // forward order, appended to the batch's compact CIGAR array (what the host reads back: a few elements per
+            // pair instead of cigar_cap); `out` was the scratch row of the backward pass
             const int stored = min(n, (int)a.cigar_cap);
-            for (int x = 0, y = stored - 1; x < y; ++x, --y) { const int2 u = out[x]; out[x] = out[y]; out[y] = u; }
+            const uint32_t first = atomicAdd(a.compact_count, (uint32_t)stored);
+            for (int x = 0; x < stored; ++x) a.compact[first + x] = out[stored - 1 - x];
+            a.compact_first[pd.index] = first;
             a.n_elem[pd.index] = n;
             a.offset[pd.index] = off;
             if (a.score) a.score[pd.index] = best;
