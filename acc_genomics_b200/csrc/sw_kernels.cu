@@ -14,7 +14,8 @@
 //     (for the end-cell search) and the traceback tile live in shared memory too.
 //   * Backtrack codes are packed 8 cells per 32-bit word per row (row-major), so a lane stores one word every 8 steps
 //     and the traceback can fetch a 32-row x 64-column tile with one 32-byte segment per lane.
-//   * The traceback is inherently serial (each step depends on the cell before): lane 0 walks, all lanes fetch tiles.
+//   * The traceback is a pointer chase, but most of it is runs of diagonal moves: all lanes fetch a tile of codes, lane r
+//     looks r cells down the diagonal and a ballot finds how far the run goes (one iteration per run or gap cell).
 #include "sw_kernels.cuh"
 
 #include <climits>
@@ -37,7 +38,7 @@ __device__ __forceinline__ int imad(int a, int b, int c)
 }
 
 struct WarpSmem {
-    int* carryH; int* carryF; int* lastrow; int* lastcol; uint32_t* tile; uint32_t* tmeta; uint8_t* alt;
+    int* carryH; int* carryF; int* lastrow; int* lastcol; uint32_t* tile; uint8_t* alt;
 };
 
 __host__ __device__ inline size_t align4(size_t x) { return (x + 3) & ~(size_t)3; }
@@ -45,7 +46,7 @@ __host__ __device__ inline size_t align4(size_t x) { return (x + 3) & ~(size_t)3
 __host__ __device__ inline size_t per_warp_bytes(uint32_t max_l1, uint32_t max_l2)
 {
     const size_t c1 = align4(max_l2 + 1), r1 = align4(max_l1 + 1);
-    const size_t b = sizeof(int) * (3 * c1 + r1) + sizeof(uint32_t) * 32 * 9 + align4(max_l2 + 4);
+    const size_t b = sizeof(int) * (3 * c1 + r1) + sizeof(uint32_t) * 32 * 8 + align4(max_l2 + 4);
     return (b + 15) & ~(size_t)15;
 }
 
@@ -58,8 +59,7 @@ __device__ __forceinline__ WarpSmem carve(char* base, uint32_t max_l1, uint32_t 
     w.lastrow = w.carryF + c1;
     w.lastcol = w.lastrow + c1;
     w.tile = reinterpret_cast<uint32_t*>(w.lastcol + r1);
-    w.tmeta = w.tile + 32 * 8;
-    w.alt = reinterpret_cast<uint8_t*>(w.tile + 32 * 9);
+    w.alt = reinterpret_cast<uint8_t*>(w.tile + 32 * 8);
     return w;
 }
 
@@ -67,7 +67,7 @@ __device__ __forceinline__ WarpSmem carve(char* base, uint32_t max_l1, uint32_t 
 // pair's rows fill its blocks (pick_rows_per_lane): a 375-row matrix takes one block of K = 12 (384 rows) instead of
 // two of K = 8 (512 rows, and two fill/drain phases).
 #define SW_ROWS_PER_LANE(X) X(4) X(6) X(8) X(10) X(12) X(14)
-constexpr uint32_t kMaxRowsPerLane = 14;          // 16 rows per lane do not fit 128 registers (4 CTAs per SM) without spills
+constexpr uint32_t kMaxRowsPerLane = 14;          // measured: 16 rows per lane are slower (501 vs 670 GCUPS), as are caps of 8..12
 
 struct FillCtx {
     WarpSmem sm;
@@ -232,8 +232,11 @@ __device__ __forceinline__ void fill_matrix(const FillCtx& c)
     }
 }
 
+// Occupancy: three CTAs (12 warps) per SM with up to 168 registers beat four with 128 -- 670 against 510 GCUPS on 16 640
+// pairs, 243 against 211 on one 260-pair batch (ptxas schedules the dependent chains better with the extra registers, and
+// a fourth fill warp per SMSP only adds contention for the half-rate ALU pipe); two CTAs with 200 registers: 662.
 template <bool CUTOFF>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 4) sw_align_kernel(const Args a)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 3) sw_align_kernel(const Args a)
 {
     extern __shared__ int4 smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -309,15 +312,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) sw_align_kernel(const Ar
                 }
             }
         }
-        if (lane == 0) {
-            // start of the traceback (getCIGAR, :285-314)
-            if (strategy == kIndel) { ti = nrow; tj = ncol; }
-            else if (strategy == kLeadingIndel) { ti = max_i; tj = ncol; }
-            else { ti = max_i; tj = max_j; }
-            if (strategy == kIgnore && updated && tj != ncol) { ti = nrow; seg = ncol - max_j; }
-        }
+        // start of the traceback (getCIGAR, :285-314); the walk's state is kept identical on all lanes
+        if (strategy == kIndel) { ti = nrow; tj = ncol; }
+        else if (strategy == kLeadingIndel) { ti = max_i; tj = ncol; }
+        else { ti = max_i; tj = max_j; }
+        if (strategy == kIgnore && updated && tj != ncol) { ti = nrow; seg = ncol - max_j; }
 
-        // ---- traceback: lane 0 walks, all lanes fetch 32-row x 64-column tiles of backtrack codes -----------------------
+        // ---- traceback ------------------------------------------------------------------------------------------------------
+        // A walk is a pointer chase (each move depends on the cell before), but most of it is runs of diagonal moves.  All
+        // lanes fetch a 32-row x 64-column tile of codes, realigned from step-indexed words to column-indexed ones; then
+        // lane r looks at the r-th cell down the diagonal from the current one and a ballot finds how far the diagonal run
+        // goes -- one iteration per run or per gap cell instead of one per move (a 400-move walk: ~25 iterations).
         int2* out = a.cigars + (size_t)pd.index * a.cigar_cap;
         int n = 0;                         // elements written (run-length encoded, still in backward order)
         int cur_state = -1, cur_len = 0;   // the open run
@@ -325,51 +330,57 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) sw_align_kernel(const Ar
         int state = 0;
         auto emit = [&](int st, int len) {
             if (st == cur_state) { cur_len += len; return; }
-            if (cur_state >= 0) { if ((uint32_t)n < a.cigar_cap) out[n] = make_int2(cur_len, cur_state); ++n; }
+            if (cur_state >= 0) { if (lane == 0 && (uint32_t)n < a.cigar_cap) out[n] = make_int2(cur_len, cur_state); ++n; }
             cur_state = st; cur_len = len;
         };
-        if (lane == 0 && tj < ncol && strategy == kSoftClip) { emit(kStateClip, ncol - tj); ++raw_ops; }
-        for (;;) {
-            const int ai = __shfl_sync(0xffffffffu, ti, 0), aj = __shfl_sync(0xffffffffu, tj, 0);
-            if (!(ai > 0 && aj > 0)) break;
-            // Each row's codes are indexed by step (t = j - 1 + lane of the row), so each row of the tile has its own
-            // window of 8 words ending at the word that holds column aj; the walker finds a row's lane and first word in
-            // tmeta.
+        if (tj < ncol && strategy == kSoftClip) { emit(kStateClip, ncol - tj); ++raw_ops; }
+        while (ti > 0 && tj > 0) {
+            const int ai = ti, aj = tj;
+            const int cw0 = max(0, ((aj - 1) >> 3) - 7);               // first column-indexed word of the tile
             {
+                // row ai - lane: nine step-indexed words starting at cw0 + (lane of the row) / 8, shifted left by
+                // (lane of the row) % 8 codes, give the eight column-indexed words cw0 .. cw0 + 7
                 const int row = ai - lane;
                 const int lr = row >= 1 ? lane_of_row(row) : 0;
-                const int cw0 = max(0, ((aj - 1 + lr) >> 3) - 7);
+                const uint32_t* src = B + (size_t)max(row - 1, 0) * stride;
+                const int w0 = cw0 + (lr >> 3), sh = 4 * (lr & 7);
+                uint32_t raw[9];
                 #pragma unroll
-                for (int w = 0; w < 8; ++w) {
-                    uint32_t v = 0;
-                    if (row >= 1 && (uint32_t)(cw0 + w) < stride) v = __ldcg(B + (size_t)(row - 1) * stride + cw0 + w);
-                    sm.tile[w * 32 + lane] = v;
-                }
-                sm.tmeta[lane] = (uint32_t)lr | ((uint32_t)cw0 << 8);
+                for (int w = 0; w < 9; ++w) raw[w] = (row >= 1 && (uint32_t)(w0 + w) < stride) ? __ldcg(src + w0 + w) : 0u;
+                #pragma unroll
+                for (int w = 0; w < 8; ++w) sm.tile[w * 32 + lane] = __funnelshift_l(raw[w + 1], raw[w], sh);
             }
             __syncwarp();
-            if (lane == 0) {
-                while (ti > 0 && tj > 0 && ai - ti < 32) {
-                    const uint32_t meta = sm.tmeta[ai - ti];
-                    const int tt = tj - 1 + (int)(meta & 31u), word = (tt >> 3) - (int)(meta >> 8);
-                    if (word < 0) break;
-                    const int btr = (int)((sm.tile[word * 32 + (ai - ti)] >> (28 - 4 * (tt & 7))) & 15u);
-                    // stored bits: 3 insertion opened (not an extension), 2 deletion opened, 1 insertion taken, 0 deletion
-                    // taken (it wins over the insertion); the reference's codes are move + "was an extension" flags
-                    const int ins_ext = (btr & 8) ? 0 : kInsertExt, del_ext = (btr & 4) ? 0 : kDeleteExt;
+            for (;;) {
+                // lane r: the cell r steps down the diagonal from (ti, tj), if the tile holds it
+                const int ri = ti - lane, rj = tj - lane, wc = ((rj - 1) >> 3) - cw0;
+                const bool held = ri >= 1 && rj >= 1 && ai - ri < 32 && wc >= 0;
+                const int btr = held ? (int)((sm.tile[wc * 32 + (ai - ri)] >> (28 - 4 * ((rj - 1) & 7))) & 15u) : 3;
+                const unsigned held0 = __ballot_sync(0xffffffffu, held) & 1u;
+                if (!held0) break;                                      // the current cell is outside the tile (or the walk is over)
+                // stored bits: 3 insertion opened (not an extension), 2 deletion opened, 1 insertion taken, 0 deletion
+                // taken (it wins over the insertion); the reference's codes are move + "was an extension" flags
+                const int b0 = __shfl_sync(0xffffffffu, btr, 0);
+                if (state == 0 && (b0 & 3) == 0) {
+                    // diagonal run: every leading lane whose cell also moves diagonally
+                    const unsigned nd = __ballot_sync(0xffffffffu, !(held && (btr & 3) == 0));
+                    const int run = nd ? __ffs((int)nd) - 1 : 32;
+                    emit(0, run + ((raw_ops == 0 && strategy == kIgnore) ? seg : 0));
+                    ti -= run; tj -= run; raw_ops += run;
+                } else {
+                    const int ins_ext = (b0 & 8) ? 0 : kInsertExt, del_ext = (b0 & 4) ? 0 : kDeleteExt;
                     // one move: inside a gap the state decides, otherwise the cell's own comparison results do
                     const bool in_ins = state == kInsertExt, in_del = state == kDeleteExt, fresh = !(in_ins || in_del);
-                    const bool del = in_del || (fresh && (btr & 1)), ins = !del && (in_ins || (btr & 2));
-                    const int len = (fresh && !del && !ins && raw_ops == 0 && strategy == kIgnore) ? seg + 1 : 1;
+                    const bool del = in_del || (fresh && (b0 & 1)), ins = !del && (in_ins || (b0 & 2));
                     ti -= ins ? 0 : 1; tj -= del ? 0 : 1;
                     state = del ? del_ext : ins ? ins_ext : 0;
                     raw_ops += fresh ? 1 : 0;
-                    emit(del ? kDelete : ins ? kInsert : 0, len);
+                    emit(del ? kDelete : kInsert, 1);
                 }
             }
             __syncwarp();
         }
-        if (lane == 0) {
+        {
             int off;
             if (strategy == kSoftClip) {
                 if (tj > 0) emit(kStateClip, tj);
@@ -382,16 +393,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) sw_align_kernel(const Ar
                 else if (tj > 0) emit(kInsert, tj);
                 off = 0;
             }
-            if (cur_state >= 0) { if ((uint32_t)n < a.cigar_cap) out[n] = make_int2(cur_len, cur_state); ++n; }
-            // forward order, appended to the batch's compact CIGAR array (what the host reads back: a few elements per
-            // pair instead of cigar_cap); `out` was the scratch row of the backward pass
-            const int stored = min(n, (int)a.cigar_cap);
-            const uint32_t first = atomicAdd(a.compact_count, (uint32_t)stored);
-            for (int x = 0; x < stored; ++x) a.compact[first + x] = out[stored - 1 - x];
-            a.compact_first[pd.index] = first;
-            a.n_elem[pd.index] = n;
-            a.offset[pd.index] = off;
-            if (a.score) a.score[pd.index] = best;
+            if (cur_state >= 0) { if (lane == 0 && (uint32_t)n < a.cigar_cap) out[n] = make_int2(cur_len, cur_state); ++n; }
+            if (lane == 0) {
+                // forward order, appended to the batch's compact CIGAR array (what the host reads back: a few elements per
+                // pair instead of cigar_cap); `out` was the scratch row of the backward pass
+                const int stored = min(n, (int)a.cigar_cap);
+                const uint32_t first = atomicAdd(a.compact_count, (uint32_t)stored);
+                for (int x = 0; x < stored; ++x) a.compact[first + x] = out[stored - 1 - x];
+                a.compact_first[pd.index] = first;
+                a.n_elem[pd.index] = n;
+                a.offset[pd.index] = off;
+                if (a.score) a.score[pd.index] = best;
+            }
         }
     }
 }
