@@ -164,4 +164,4 @@ def test_falcon_entry_synthetic_cases_checked_by_the_oracle(host, checker, tmp_p
         assert b.num_read == 16 * (i + 1) and b.num_hap == i + 1
         want = checker.batch(b, threads=8)[1]
         got = fixtures.read_output(str(tmp_path / f"output{i}"))
-        assert np.array_equal(got.view(np.int64), np.asarray(want).view(np.int64)), i
+        assert np.array_equal(got.view(np.int64), np.asarray(want).ravel().view(np.int64)), i
