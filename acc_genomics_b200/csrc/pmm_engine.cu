@@ -72,6 +72,8 @@ struct pmm_ctx {
     int sm_count = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_block = nullptr;     // "sync" = "block": waits sleep on this event instead of spinning on the stream
+    bool block_sync = false;
     std::string err;
     int tasks_per_warp = 16;
     bool fast = false;                  // "mode" option: fast = contracted float kernels + exact re-check near the threshold
@@ -454,6 +456,7 @@ int pmm_create(int device, pmm_ctx** out)
     }
     c->stream = c->own_stream;
     for (auto& ev : c->ev) cudaEventCreate(&ev);
+    cudaEventCreateWithFlags(&c->ev_block, cudaEventBlockingSync | cudaEventDisableTiming);
     *out = c;
     return PMM_OK;
 }
@@ -467,6 +470,7 @@ void pmm_destroy(pmm_ctx* c)
                       &c->d_tiny_tasks, &c->d_dres, &c->d_ctrl, &c->d_scratch, &c->d_probe}) b->release();
     c->h_in.release(); c->h_out.release();
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+    if (c->ev_block) cudaEventDestroy(c->ev_block);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -500,6 +504,12 @@ int pmm_set_option(pmm_ctx* c, const char* key, const char* value)
         const float g = (float)atof(value);
         if (!(g >= 0.0f && g < 1.0f)) return c->fail(PMM_ERR_INVALID, "guard must be in [0, 1)");
         c->guard = g;
+        return PMM_OK;
+    }
+    if (k == "sync") {
+        const std::string v = value;
+        if (v != "spin" && v != "block") return c->fail(PMM_ERR_INVALID, "sync is \"spin\" or \"block\"");
+        c->block_sync = v == "block";
         return PMM_OK;
     }
     if (k == "force_variant") {
@@ -616,6 +626,16 @@ int pmm_sync(pmm_ctx* c)
     return PMM_OK;
 }
 
+// Wait for everything queued on the context's stream.  A caller with one context per core spins (lowest latency); the
+// pool, which runs several contexts per GPU from as many host threads, sleeps on a blocking event so that the waiting
+// threads do not take the cores the packing and log10 work of the other contexts needs.
+static cudaError_t wait_stream(pmm_ctx* c)
+{
+    if (!c->block_sync) return cudaStreamSynchronize(c->stream);
+    cudaError_t e = cudaEventRecord(c->ev_block, c->stream);
+    return e != cudaSuccess ? e : cudaEventSynchronize(c->ev_block);
+}
+
 static int fetch_common(pmm_ctx* c, bool want_lists, uint32_t* nfb_out, uint32_t* ntiny_out)
 {
     if (!c->launched) return c->fail(PMM_ERR_STATE, "fetch before pmm_launch");
@@ -635,13 +655,13 @@ static int fetch_common(pmm_ctx* c, bool want_lists, uint32_t* nfb_out, uint32_t
         PMM_CUDA(c, cudaMemcpyAsync(hidx, c->d_fb_idx.p, sizeof(uint32_t) * spec, cudaMemcpyDeviceToHost, s));
         PMM_CUDA(c, cudaMemcpyAsync(hd, c->d_dres.p, sizeof(double) * spec, cudaMemcpyDeviceToHost, s));
     }
-    PMM_CUDA(c, cudaStreamSynchronize(s));
+    PMM_CUDA(c, wait_stream(c));
     const uint32_t nfb = hctrl[0], ntiny = hctrl[1];
     uint64_t d2h = 12 + sizeof(float) * c->pairs + (sizeof(uint32_t) + sizeof(double)) * spec;
     if (want_lists && nfb > spec) {
         PMM_CUDA(c, cudaMemcpyAsync(hidx + spec, static_cast<uint32_t*>(c->d_fb_idx.p) + spec, sizeof(uint32_t) * (nfb - spec), cudaMemcpyDeviceToHost, s));
         PMM_CUDA(c, cudaMemcpyAsync(hd + spec, static_cast<double*>(c->d_dres.p) + spec, sizeof(double) * (nfb - spec), cudaMemcpyDeviceToHost, s));
-        PMM_CUDA(c, cudaStreamSynchronize(s));
+        PMM_CUDA(c, wait_stream(c));
         d2h += (sizeof(uint32_t) + sizeof(double)) * (nfb - spec);
     }
     c->stats.fallback_pairs = nfb; c->stats.flush_pairs = ntiny; c->stats.recheck_pairs = hctrl[2]; c->stats.d2h_bytes = d2h;

@@ -79,7 +79,11 @@ int  pmm_device_count(void);
  *                       double decision is taken, so that decision stays identical to the reference's
  *   "guard"           = relative half-width of that band (default 0.0078125 = 2^-7)
  *   "force_variant"   = "K,W": rows per lane and lanes per read of the float kernel for every read that fits
- *                       (tuning sweeps, tools/sweep_variants.py); "0,0" gives the choice back to the planner   */
+ *                       (tuning sweeps, tools/sweep_variants.py); "0,0" gives the choice back to the planner,
+ *                       "-1,0" keeps every variant in a launch of its own (no consolidation of rare ones)
+ *   "sync"            = "spin" (default): waits poll the stream, lowest latency for one context per core; "block":
+ *                       waits sleep on a blocking event (for hosts with fewer cores than waiting threads; the pool takes
+ *                       it from the environment variable PMM_POOL_SYNC=block)                                      */
 int  pmm_set_option(pmm_ctx* ctx, const char* key, const char* value);
 
 /* ---- one-shot calls, host buffers in, host buffers out --------------------------------------------------
