@@ -27,6 +27,7 @@
 //   * Work is pulled by warps from a global queue (atomicAdd), grid = SMs x resident CTAs.
 #include "pmm_kernels.cuh"
 
+#include <atomic>
 #include <cfloat>
 #include <type_traits>
 
@@ -505,26 +506,45 @@ __global__ void __launch_bounds__(256) fp32_probe_kernel(float* sink, int iters)
 // ---------------------------------------------------------------------------------------------------------
 // Variant table
 // ---------------------------------------------------------------------------------------------------------
+// The shared-memory attribute and the occupancy of a variant are per device and never change: looked up once per
+// (variant, device) instead of on every launch (runtime calls that take the driver's locks, which feeder threads of
+// eight GPUs in one process would otherwise contend for several times per job).
+constexpr int kMaxDevices = 64;
+inline int current_device() { int d = 0; if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) d = -1; return d; }
+
+template <typename T, int K, int W, bool STRIPED, int F>
+cudaError_t prepare_variant()
+{
+    static std::atomic<bool> ready[kMaxDevices];
+    const int dev = current_device();
+    if (dev >= 0 && ready[dev].load(std::memory_order_acquire)) return cudaSuccess;
+    constexpr int smem = kWarpsPerCta * wtab_elems<T, K>() * (int)sizeof(T);
+    const cudaError_t e = cudaFuncSetAttribute(pmm_forward_kernel<T, K, W, STRIPED, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess && dev >= 0) ready[dev].store(true, std::memory_order_release);
+    return e;
+}
+
 template <typename T, int K, int W, bool STRIPED, int F>
 cudaError_t launch_variant(const ForwardArgs& a, const FallbackQueue& fq, int ctas, cudaStream_t s)
 {
     constexpr int smem = kWarpsPerCta * wtab_elems<T, K>() * (int)sizeof(T);
-    auto kern = pmm_forward_kernel<T, K, W, STRIPED, F>;
-    // per device, cheap: the context may live on any GPU of the box
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const cudaError_t e = prepare_variant<T, K, W, STRIPED, F>();
     if (e != cudaSuccess) return e;
-    kern<<<ctas, kWarpsPerCta * 32, smem, s>>>(a, fq);
+    pmm_forward_kernel<T, K, W, STRIPED, F><<<ctas, kWarpsPerCta * 32, smem, s>>>(a, fq);
     return cudaGetLastError();
 }
 
 template <typename T, int K, int W, bool STRIPED, int F>
 int variant_ctas_per_sm()
 {
+    static std::atomic<int> cached[kMaxDevices];               // occupancy + 1; 0 = not looked up yet
+    const int dev = current_device();
+    if (dev >= 0) { const int v = cached[dev].load(std::memory_order_relaxed); if (v) return v - 1; }
     constexpr int smem = kWarpsPerCta * wtab_elems<T, K>() * (int)sizeof(T);
-    auto kern = pmm_forward_kernel<T, K, W, STRIPED, F>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (prepare_variant<T, K, W, STRIPED, F>() != cudaSuccess) return 0;
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kWarpsPerCta * 32, smem) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, pmm_forward_kernel<T, K, W, STRIPED, F>, kWarpsPerCta * 32, smem) != cudaSuccess) return 0;
+    if (dev >= 0) cached[dev].store(n + 1, std::memory_order_relaxed);
     return n;
 }
 
