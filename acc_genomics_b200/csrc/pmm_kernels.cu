@@ -86,9 +86,17 @@ __host__ __device__ constexpr int wtab_elems() { return 5 * ((K + Arith<T>::kVec
 // ---------------------------------------------------------------------------------------------------------
 // Resident CTAs per SM the register allocator must leave room for: the state of a lane is 8 registers per row
 // (5 parameters + M, X, Y), so K decides the occupancy step (64K registers / 128 threads).
+// Measured (tools/occ_check.py): 15 and 16 rows per lane at two CTAs per SM (up to 255 registers) beat three CTAs at 168
+// registers by 5.6 % (config 4, K = 16 / W = 16: 2 343 -> 2 475 GCUPS); for K <= 14 the difference is within 2 %.
 template <typename T, int K> __host__ __device__ constexpr int min_ctas()
 {
-    return sizeof(T) == 8 ? (K <= 6 ? 3 : 2) : K <= 11 ? 4 : K <= 16 ? 3 : 2;
+#ifndef PMM_F32_4CTA_MAXK
+#define PMM_F32_4CTA_MAXK 11
+#endif
+#ifndef PMM_F32_3CTA_MAXK
+#define PMM_F32_3CTA_MAXK 14
+#endif
+    return sizeof(T) == 8 ? (K <= 6 ? 3 : 2) : K <= PMM_F32_4CTA_MAXK ? 4 : K <= PMM_F32_3CTA_MAXK ? 3 : 2;
 }
 
 // ---- fallback list: the float pass appends the pairs whose result is below 1e-28f the moment the result exists ----
