@@ -49,7 +49,8 @@ const char* sw_last_error(const sw_ctx* ctx);     /* ctx may be NULL: last error
 
 /* Align n_pairs pairs.  Pair p is seq1_bytes[seq1_start[p] .. +seq1_len[p]) against seq2_bytes[seq2_start[p] .. +seq2_len[p])
  * (several pairs may name the same reference bytes).  Outputs, all caller-owned host memory:
- *   cigars[p * cigar_cap .. ]  the CIGAR elements of pair p in forward order, at most cigar_cap of them
+ *   cigars[p * cigar_cap .. ]  the CIGAR elements of pair p in forward order, at most cigar_cap of them; only the first
+ *                              min(n_elem[p], cigar_cap) elements of a row are written, the rest is left as it was
  *   n_elem[p]                  how many elements the CIGAR has (if > cigar_cap the stored CIGAR is truncated: retry larger)
  *   alignment_offset[p]        the value runSWOnePairBT returns / SWPairwiseAlignmentOneBatch stores
  *   score[p]                   (optional, may be NULL) score of the end cell
