@@ -409,7 +409,25 @@ def _main(args, real_stdout):
                 one = cpu_reference_pass(lib, [batches[0].slice_reads(0, max(1, batches[0].num_read // 16))], 1)[0]
                 line["cpu_baseline"] = {"value": cells / best * 1e-9, "unit": UNIT, "cores": threads, "kind": kind,
                                         "sample": "the full workload (all pairs incl. double re-run and log10), best of 3 passes",
-                                        "one_thread_gcups": cells_of([batches[0].slice_reads(0, max(1, batches[0].num_read // 16))]) / one * 1e-9}
+                                        "one_thread_gcups": cells_of([batches[0].slice_reads(0, max(1, batches[0].num_read // 16))]) / one * 1e-9,
+                                        "build": "g++ -O3 -mavx -ffp-contract=off (the arithmetic of Intel GKL's AVX build: no FMA contraction)"}
+                # the build the reference's own Makefile makes (-march=native => FMA contraction, different low bits)
+                try:
+                    with open("/proc/cpuinfo") as f:
+                        flags = f.read()
+                except OSError:
+                    flags = ""
+                fma = oracle.reference(fma=True) if kind == "reference" and " fma" in flags and " avx2" in flags else None
+                if fma is not None:
+                    cpu_reference_pass(fma, batches, threads)
+                    tf = min(cpu_reference_pass(fma, batches, threads)[0] for _ in range(3))
+                    line["cpu_baseline"]["fma_contracted_build_gcups"] = cells / tf * 1e-9   # -mavx2 -mfma: what -march=native yields here
+                try:
+                    with open("/proc/cpuinfo") as f:
+                        model = [ln.split(":", 1)[1].strip() for ln in f if ln.startswith("model name")]
+                    line["cpu_baseline"]["cpu_model"] = model[0] if model else None
+                except OSError:
+                    pass
             except Exception as e:  # the baseline is a report, never a reason to lose the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)}
         log("cpu baseline done")
