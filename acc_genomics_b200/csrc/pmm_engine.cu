@@ -11,7 +11,6 @@
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
-#include <memory>
 #include <mutex>
 #include <chrono>
 #include <cmath>
@@ -344,23 +343,18 @@ int stage_single_region(pmm_ctx* c, const JobSource& src)
 }
 
 // Host worker threads for the per-result log10 (the one piece of the path that stays on the host so that it uses the
-// host libm like the reference).  Created once per process on first use, in teams of up to seven threads (one team on a
-// 16-core host, three on a 32-core box).  A fetch takes a free team, hands out chunks and takes part itself, so small jobs
-// never wait for a wake-up; several contexts finishing together each find a team; a call that finds every team taken
-// runs on its own thread (the process is then streaming jobs through many contexts and has parallelism enough).
-class WorkerTeam {
+// host libm like the reference).  Created once per process on first use; a fetch hands out chunks and takes part
+// itself, so small jobs never wait for a wake-up.  A call that finds the workers taken runs on its own thread.
+class HostWorkers {
  public:
-    explicit WorkerTeam(unsigned n) { for (unsigned k = 0; k < n; ++k) th_.emplace_back([this] { loop(); }); }
-    ~WorkerTeam()
+    static HostWorkers& get() { static HostWorkers w; return w; }
+    void run(uint64_t n, uint64_t grain, const std::function<void(uint64_t, uint64_t)>& f)
     {
-        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
-        cv_work_.notify_all();
-        for (auto& t : th_) t.join();
-    }
-    bool try_run(uint64_t n, uint64_t grain, const std::function<void(uint64_t, uint64_t)>& f)
-    {
+        if (n <= grain || th_.empty()) { f(0, n); return; }
+        // Workers busy with another context's results: the process is streaming jobs through several contexts, and
+        // the caller's own thread is the parallelism (24 feeder threads on an 8-GPU box) -- do not queue up behind them.
         std::unique_lock<std::mutex> call(call_mu_, std::try_to_lock);
-        if (!call.owns_lock()) return false;
+        if (!call.owns_lock()) { f(0, n); return; }
         {
             std::lock_guard<std::mutex> lk(mu_);
             fn_ = &f; n_ = n; grain_ = grain; next_.store(0); busy_ = (int)th_.size(); ++gen_;
@@ -370,10 +364,21 @@ class WorkerTeam {
         std::unique_lock<std::mutex> lk(mu_);
         cv_done_.wait(lk, [&] { return busy_ == 0; });
         fn_ = nullptr;
-        return true;
     }
 
  private:
+    HostWorkers()
+    {
+        const unsigned hw = std::thread::hardware_concurrency();
+        const unsigned n = hw > 1 ? std::min(hw - 1, 7u) : 0;
+        for (unsigned k = 0; k < n; ++k) th_.emplace_back([this] { loop(); });
+    }
+    ~HostWorkers()
+    {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+        cv_work_.notify_all();
+        for (auto& t : th_) t.join();
+    }
     void work()
     {
         for (;;) {
@@ -405,28 +410,6 @@ class WorkerTeam {
     std::atomic<uint64_t> next_{0};
     int busy_ = 0;
     bool stop_ = false;
-};
-
-class HostWorkers {
- public:
-    static HostWorkers& get() { static HostWorkers w; return w; }
-    void run(uint64_t n, uint64_t grain, const std::function<void(uint64_t, uint64_t)>& f)
-    {
-        if (n > grain)
-            for (auto& t : teams_) if (t->try_run(n, grain, f)) return;
-        f(0, n);
-    }
-
- private:
-    HostWorkers()
-    {
-        const unsigned hw = std::thread::hardware_concurrency();
-        const unsigned spare = hw > 1 ? hw - 1 : 0;                      // threads besides the caller's
-        if (spare <= 7) { if (spare) teams_.emplace_back(new WorkerTeam(spare)); return; }
-        const unsigned nteams = std::max(1u, std::min(3u, spare / 8));  // 16 cores: one team of 7; 32 cores: three
-        for (unsigned k = 0; k < nteams; ++k) teams_.emplace_back(new WorkerTeam(7));
-    }
-    std::vector<std::unique_ptr<WorkerTeam>> teams_;
 };
 
 void parallel_for(uint64_t n, uint64_t grain, const std::function<void(uint64_t, uint64_t)>& f)
