@@ -430,18 +430,27 @@ uint32_t pick_rows_per_lane(uint32_t l1)
 template <bool CUTOFF>
 static cudaError_t launch_align_t(const Args& a, int sm_count, cudaStream_t s, int* ctas_out)
 {
-    const size_t smem = kWarpsPerCta * smem_bytes_per_warp(a.max_l1, a.max_l2);
+    // Warps per CTA: four, fewer when the chunk's longest sequences make four warps' shared memory (~70 KB per warp at
+    // 4 095 bases) exceed what a CTA may have.  The kernel carves shared memory by warp index and works with any count.
+    int dev = 0, max_smem = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e != cudaSuccess) return e;
+    const size_t per_warp = smem_bytes_per_warp(a.max_l1, a.max_l2);
+    int warps = kWarpsPerCta;
+    while (warps > 1 && warps * per_warp > (size_t)max_smem) --warps;
+    const size_t smem = warps * per_warp;
     auto kern = sw_align_kernel<CUTOFF>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWarpsPerCta * 32, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
-    const int want = (int)((a.npairs + kWarpsPerCta - 1) / kWarpsPerCta);
+    const int want = (int)((a.npairs + warps - 1) / warps);
     const int ctas = want < sm_count * per_sm ? want : sm_count * per_sm;
     if (ctas_out) *ctas_out = ctas;
-    kern<<<ctas, kWarpsPerCta * 32, smem, s>>>(a);
+    kern<<<ctas, warps * 32, smem, s>>>(a);
     return cudaGetLastError();
 }
 

@@ -57,10 +57,10 @@ def test_all_small_lengths(aligner, sw_checker, strategy):
 
 
 def test_block_boundaries_and_long_sequences(aligner, sw_checker):
-    """Row counts around the 128- and 256-row blocks (32 lanes x 4 or 8 rows), column counts around the 8-cell backtrack word and the
-    64-column traceback tile, and the reference's maximum (1536)."""
+    """Row counts around the row blocks (32 lanes x 4, 6, .. 14 rows per lane, chosen per pair: 128 .. 448 rows, then two blocks),
+    column counts around the 8-cell backtrack word and the 64-column traceback tile, and the reference's maximum (1536)."""
     pairs = []
-    for n1 in (127, 128, 129, 255, 256, 257):
+    for n1 in (127, 128, 129, 191, 192, 193, 255, 256, 257, 319, 320, 321, 447, 448, 449, 895, 896, 897):
         for n2 in (7, 8, 9, 63, 64, 65, 130):
             pairs += sw.haplotype_pairs(n1 * 131 + n2, 1, ref_len=n1, per_ref=1, trim=0.0)
             r, a = pairs[-1]
@@ -72,6 +72,10 @@ def test_block_boundaries_and_long_sequences(aligner, sw_checker):
     long = sw.haplotype_pairs(98, 2, ref_len=(2500, 3000), per_ref=2)
     check(aligner, oracle.sw_port(), long, 0)
     check(aligner, oracle.sw_port(), long, 3)
+    # the longest the C ABI accepts: four warps' shared memory no longer fits a CTA, the launch uses fewer warps per CTA
+    longest = [(r[:4095], a[:4095]) for r, a in sw.haplotype_pairs(99, 3, ref_len=(4095, 4200), per_ref=3)]
+    assert max(len(r) for r, _ in longest) == 4095
+    check(aligner, oracle.sw_port(), longest, 0)
 
 
 def test_repeats_and_ties(aligner, sw_checker):
