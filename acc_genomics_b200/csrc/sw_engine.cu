@@ -125,14 +125,18 @@ int sw_align_batch(sw_ctx* c, uint32_t n_pairs,
     }
     if (ext1 >= (1ull << 31) || ext2 >= (1ull << 31)) return c->fail(SW_ERR_INVALID, "sequence blobs larger than 2 GiB");
 
-    // largest pairs first: warps pull pairs in order, the tail of the launch is made of the small ones
-    // (one 64-bit key per pair: cells descending, then the caller's order)
-    std::vector<uint64_t> keys(n_pairs);
-    for (uint32_t p = 0; p < n_pairs; ++p)
-        keys[p] = (((1ull << 24) - (uint64_t)seq1_len[p] * seq2_len[p]) << 32) | p;      // lengths <= 4095: cells < 2^24
-    std::sort(keys.begin(), keys.end());
+    // largest pairs first: warps pull pairs in order, the tail of the launch is made of the small ones.  A stable
+    // counting sort on 4096 size classes (cells / 4096), linear in the number of pairs: the order inside a class does
+    // not matter for the tail.
     std::vector<uint32_t> order(n_pairs);
-    for (uint32_t k = 0; k < n_pairs; ++k) order[k] = (uint32_t)keys[k];
+    {
+        constexpr uint32_t kClasses = 4096;                              // cells < 2^24
+        std::vector<uint32_t> first(kClasses + 1, 0);
+        auto cls = [&](uint32_t p) { return kClasses - 1 - (uint32_t)(((uint64_t)seq1_len[p] * seq2_len[p]) >> 12); };
+        for (uint32_t p = 0; p < n_pairs; ++p) ++first[cls(p) + 1];
+        for (uint32_t k = 0; k < kClasses; ++k) first[k + 1] += first[k];
+        for (uint32_t p = 0; p < n_pairs; ++p) order[first[cls(p)]++] = p;
+    }
 
     mark("sorted");
     SW_CUDA(c, c->d_seq1.reserve(ext1)); SW_CUDA(c, c->d_seq2.reserve(ext2));
