@@ -418,6 +418,9 @@ void parallel_for(uint64_t n, uint64_t grain, const std::function<void(uint64_t,
 }
 }  // namespace
 
+// the same workers for the other engine of this library (sw_engine.cu: staging and CIGAR scatter)
+namespace pmm { void host_parallel_for(uint64_t n, uint64_t grain, const std::function<void(uint64_t, uint64_t)>& f) { parallel_for(n, grain, f); } }
+
 // =========================================================================================================
 extern "C" {
 

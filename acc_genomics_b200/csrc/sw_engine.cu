@@ -9,11 +9,15 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <numeric>
 #include <string>
 #include <vector>
 
 using namespace sw;
+
+// host worker threads shared with the PairHMM engine (pmm_engine.cu)
+namespace pmm { void host_parallel_for(uint64_t n, uint64_t grain, const std::function<void(uint64_t, uint64_t)>& f); }
 
 namespace {
 std::string g_sw_create_error;
@@ -150,7 +154,10 @@ int sw_align_batch(sw_ctx* c, uint32_t n_pairs,
     SW_CUDA(c, c->d_score.reserve(sizeof(int32_t) * (size_t)n_pairs));
     SW_CUDA(c, c->d_counter.reserve(256));
     char* hs = static_cast<char*>(c->h_stage.p);
-    memcpy(hs, seq1_bytes, ext1); memcpy(hs + ext1, seq2_bytes, ext2);
+    auto copy_in = [&](char* dst, const uint8_t* src, uint64_t n) {       // into pinned memory, by the host workers
+        pmm::host_parallel_for(n, 1 << 18, [&](uint64_t b0, uint64_t b1) { memcpy(dst + b0, src + b0, b1 - b0); });
+    };
+    copy_in(hs, seq1_bytes, ext1); copy_in(hs + ext1, seq2_bytes, ext2);
     SW_CUDA(c, cudaMemcpyAsync(c->d_seq1.p, hs, ext1, cudaMemcpyHostToDevice, s));
     SW_CUDA(c, cudaMemcpyAsync(c->d_seq2.p, hs + ext1, ext2, cudaMemcpyHostToDevice, s));
 
@@ -223,10 +230,12 @@ int sw_align_batch(sw_ctx* c, uint32_t n_pairs,
         SW_CUDA(c, cudaMemcpyAsync(const_cast<int2*>(hc), c->d_compact.p, sizeof(int2) * (size_t)total, cudaMemcpyDeviceToHost, s));
         SW_CUDA(c, cudaStreamSynchronize(s));
         const uint32_t* first = reinterpret_cast<const uint32_t*>(ho + 3 * sz_i);
-        for (uint32_t p = 0; p < n_pairs; ++p) {
-            const uint32_t stored = std::min<uint32_t>(cigar_cap, (uint32_t)std::max(0, n_elem[p]));
-            memcpy(cigars + (size_t)p * cigar_cap, hc + first[p], sizeof(int2) * (size_t)stored);
-        }
+        pmm::host_parallel_for(n_pairs, 1024, [&](uint64_t p0, uint64_t p1) {
+            for (uint64_t p = p0; p < p1; ++p) {
+                const uint32_t stored = std::min<uint32_t>(cigar_cap, (uint32_t)std::max(0, n_elem[p]));
+                memcpy(cigars + (size_t)p * cigar_cap, hc + first[p], sizeof(int2) * (size_t)stored);
+            }
+        });
     }
 
     mark("scattered");
