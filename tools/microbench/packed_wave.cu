@@ -24,6 +24,18 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
     asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(y));
     return *reinterpret_cast<float2*>(&r);
 }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    unsigned long long r, x = *reinterpret_cast<unsigned long long*>(&a), y = *reinterpret_cast<unsigned long long*>(&b), z = *reinterpret_cast<unsigned long long*>(&c);
+    asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(x), "l"(y), "l"(z));
+    return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 pmul2(float2 a, float2 b) {     // plain packed multiply (free to be contracted: fast mode)
+    unsigned long long r, x = *reinterpret_cast<unsigned long long*>(&a), y = *reinterpret_cast<unsigned long long*>(&b);
+    asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(y));
+    return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float fma2(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ float pmul2(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float mul2(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float add2(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float shfl_up(float v, int w) { return __shfl_up_sync(0xffffffffu, v, 1, w); }
@@ -34,7 +46,7 @@ template <> struct Vec<2> { using T = float2; };
 
 constexpr int kStream = 4096;
 
-template <int K, int W, int PACK>
+template <int K, int W, int PACK, bool FUSED>
 __global__ void __launch_bounds__(128, 2) wave(const float* __restrict__ params, const unsigned char* __restrict__ stream,
                                                float* __restrict__ out, int steps)
 {
@@ -73,15 +85,21 @@ __global__ void __launch_bounds__(128, 2) wave(const float* __restrict__ params,
             const T md = j ? M[j - 1] : dM, xd = j ? X[j - 1] : dX, yd = j ? Y[j - 1] : dY;
             T w;
             if constexpr (PACK == 2) w = make_float2(wf[2 * j], wf[2 * j + 1]); else w = wf[j];
+            if constexpr (FUSED) {       // the fast mode's contraction: FMUL + 2 FFMA + FMUL, FMUL + FFMA
+                const T t5 = fma2(yd, pG[j], fma2(xd, pG[j], pmul2(md, pMM[j])));
+                Mn[j] = pmul2(t5, w);
+                Yn[j] = fma2(Y[j], pC[j], pmul2(M[j], pMY[j]));
+            } else {
             const T t3 = add2(mul2(md, pMM[j]), mul2(xd, pG[j]));
             const T t5 = add2(t3, mul2(yd, pG[j]));
             Mn[j] = mul2(t5, w);
             Yn[j] = add2(mul2(M[j], pMY[j]), mul2(Y[j], pC[j]));
+            }
         }
         #pragma unroll
         for (int j = 0; j < K; ++j) {
             const T mu = j ? Mn[j - 1] : inM, xu = j ? Xn[j - 1] : inX;
-            Xn[j] = add2(mul2(mu, pMX[j]), mul2(xu, pC[j]));
+            if constexpr (FUSED) Xn[j] = fma2(xu, pC[j], pmul2(mu, pMX[j])); else Xn[j] = add2(mul2(mu, pMX[j]), mul2(xu, pC[j]));
         }
         #pragma unroll
         for (int j = 0; j < K; ++j) { M[j] = Mn[j]; X[j] = Xn[j]; Y[j] = Yn[j]; }
@@ -106,7 +124,7 @@ __global__ void __launch_bounds__(128, 2) wave(const float* __restrict__ params,
     out[blockIdx.x * 128 + threadIdx.x] = r;
 }
 
-template <int K, int W, int PACK> void run(const char* name, int nsm, double peak)
+template <int K, int W, int PACK, bool FUSED = false> void run(const char* name, int nsm, double peak)
 {
     constexpr int E = K * PACK, KQ = (E + 3) / 4, smem = 4 * 5 * KQ * 32 * 4 * (int)sizeof(float);
     const int blocks = nsm * 2, steps = 40000;
@@ -118,7 +136,7 @@ template <int K, int W, int PACK> void run(const char* name, int nsm, double pea
     CK(cudaMalloc(&params, hp.size() * 4)); CK(cudaMemcpy(params, hp.data(), hp.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&stream, hs.size())); CK(cudaMemcpy(stream, hs.data(), hs.size(), cudaMemcpyHostToDevice));
     CK(cudaMalloc(&out, (size_t)blocks * 128 * 4));
-    auto kern = wave<K, W, PACK>;
+    auto kern = wave<K, W, PACK, FUSED>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, smem));
     cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kern));
@@ -133,7 +151,7 @@ template <int K, int W, int PACK> void run(const char* name, int nsm, double pea
     const double rate = cells / (best * 1e-3);
     printf("{\"bench\":\"%s\",\"K\":%d,\"W\":%d,\"pack\":%d,\"regs\":%d,\"ctas_per_sm\":%d,\"ms\":%.3f,\"lane_cells_per_s\":%.4e,\"tcups_at_full_rows\":%.3f,"
            "\"frac_of_fp32_issue_peak\":%.4f,\"cycles_per_step_at_1965\":%.1f}\n",
-           name, K, W, PACK, fa.numRegs, occ, best, rate, rate * 1e-12, rate * 12 / peak,
+           name, K, W, PACK, fa.numRegs, occ, best, rate, rate * 1e-12, rate * (FUSED ? 8 : 12) / peak,
            best * 1e-3 * 1.965e9 / steps * 1.0);
     CK(cudaFree(params)); CK(cudaFree(stream)); CK(cudaFree(out));
 }
@@ -171,5 +189,9 @@ int main()
     run<10, 16, 2>("packed_K10_W16", nsm, peak);
     run<12, 16, 2>("packed_K12_W16", nsm, peak);
     run<8, 32, 2>("packed_K8_W32", nsm, peak);
+    // fast mode (contracted): fraction is against 8 instructions per cell
+    run<19, 8, 1, true>("fused_scalar_K19_W8", nsm, peak);
+    run<10, 16, 2, true>("fused_packed_K10_W16", nsm, peak);
+    run<12, 16, 2, true>("fused_packed_K12_W16", nsm, peak);
     return 0;
 }
