@@ -80,6 +80,8 @@ struct pmm_ctx {
     float guard = 0.0078125f;           // "guard" option: relative half-width of the re-check band around 1e-28f (2^-7)
     int f64_rows = kF64K;               // rows per lane of the double kernel for the staged job (pick_f64_rows)
     Variant force{0, 0, false};         // "force_variant" option (tuning sweeps): K,W of the float kernel
+    int f64_tasks_per_warp = 4;         // "f64_tasks_per_warp": tasks the double re-run aims at per resident warp ...
+    int f64_max_run = 16;               // "f64_max_run": ... and the most haplotypes it puts into one task
 
     // device-resident tables
     DevBuf tables;
@@ -87,11 +89,11 @@ struct pmm_ctx {
 
     // job state
     PinBuf h_in;  DevBuf d_in;          // one arena: read blob | descs | hap blob | descs | spos | tasks | regions
-    DevBuf d_params, d_stream, d_iyf, d_iyd, d_raw, d_fb_tasks, d_fb_idx, d_tiny_tasks, d_dres, d_ctrl, d_scratch, d_probe;
+    DevBuf d_params, d_stream, d_iyf, d_iyd, d_raw, d_fb_tasks, d_fb_idx, d_fb_hap, d_tiny_tasks, d_dres, d_ctrl, d_scratch, d_probe;
     PinBuf h_out;                       // raw floats | fb idx | dres
     size_t off_rblob = 0, off_rdesc = 0, off_hblob = 0, off_hdesc = 0, off_spos = 0, off_tasks = 0, off_regions = 0, off_groups = 0;
     uint32_t num_groups = 0;
-    uint32_t num_read = 0, num_hap = 0, num_region = 0, num_tasks = 0;
+    uint32_t num_read = 0, num_hap = 0, num_region = 0, num_tasks = 0, num_rows = 0;
     uint64_t pairs = 0, cells = 0;
     uint32_t max_hap_len = 0;
     std::vector<LaunchSeg> segs;
@@ -221,8 +223,9 @@ int stage_common(pmm_ctx* c, uint32_t num_read, const uint32_t* read_off, uint32
     PMM_CUDA(c, c->d_iyd.reserve(sizeof(double) * num_hap));
     PMM_CUDA(c, c->d_raw.reserve(sizeof(float) * pairs));
     PMM_CUDA(c, c->d_fb_tasks.reserve(sizeof(Task) * pairs));
-    PMM_CUDA(c, c->d_tiny_tasks.reserve(sizeof(Task) * pairs));
+    if (c->fast) PMM_CUDA(c, c->d_tiny_tasks.reserve(sizeof(Task) * pairs));     // re-check list of the guard band
     PMM_CUDA(c, c->d_fb_idx.reserve(sizeof(uint32_t) * pairs));
+    PMM_CUDA(c, c->d_fb_hap.reserve(sizeof(uint32_t) * pairs));
     PMM_CUDA(c, c->d_dres.reserve(sizeof(double) * pairs));
     PMM_CUDA(c, c->d_ctrl.reserve(sizeof(uint32_t) * kCtrlWords));
     PMM_CUDA(c, c->h_out.reserve(256 + align_up(sizeof(float) * pairs) + align_up(sizeof(uint32_t) * pairs) + sizeof(double) * pairs + 256));
@@ -248,6 +251,7 @@ int stage_common(pmm_ctx* c, uint32_t num_read, const uint32_t* read_off, uint32
                                     static_cast<float*>(c->d_iyf.p), static_cast<double*>(c->d_iyd.p), ht.ic_f, ht.ic_d, s));
 
     c->num_read = num_read; c->num_hap = num_hap; c->num_region = num_region; c->num_tasks = (uint32_t)plan.num_tasks;
+    c->num_rows = (uint32_t)plan.rows;
     c->pairs = pairs; c->cells = cells;
     c->regions.assign(regions, regions + num_region);
     c->stats = pmm_stats_t{};
@@ -470,7 +474,7 @@ void pmm_destroy(pmm_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->tables, &c->d_in, &c->d_params, &c->d_stream, &c->d_iyf, &c->d_iyd, &c->d_raw, &c->d_fb_tasks, &c->d_fb_idx,
-                      &c->d_tiny_tasks, &c->d_dres, &c->d_ctrl, &c->d_scratch, &c->d_probe}) b->release();
+                      &c->d_fb_hap, &c->d_tiny_tasks, &c->d_dres, &c->d_ctrl, &c->d_scratch, &c->d_probe}) b->release();
     c->h_in.release(); c->h_out.release();
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     if (c->ev_block) cudaEventDestroy(c->ev_block);
@@ -495,6 +499,12 @@ int pmm_set_option(pmm_ctx* c, const char* key, const char* value)
         const int v = atoi(value);
         if (v < 1 || v > 64) return c->fail(PMM_ERR_INVALID, "tasks_per_warp out of range");
         c->tasks_per_warp = v;
+        return PMM_OK;
+    }
+    if (k == "f64_tasks_per_warp" || k == "f64_max_run") {
+        const int v = atoi(value);
+        if (v < 1 || v > 64) return c->fail(PMM_ERR_INVALID, k + " out of range (1..64)");
+        (k == "f64_max_run" ? c->f64_max_run : c->f64_tasks_per_warp) = v;
         return PMM_OK;
     }
     if (k == "mode") {
@@ -547,11 +557,12 @@ int pmm_launch(pmm_ctx* c)
 {
     if (!c) return PMM_ERR_INVALID;
     if (!c->staged) return c->fail(PMM_ERR_STATE, "pmm_launch before pmm_stage_*");
+    if (c->fast && c->d_tiny_tasks.cap < sizeof(Task) * c->pairs) return c->fail(PMM_ERR_STATE, "mode changed to fast after pmm_stage_*: stage the job again");
     cudaSetDevice(c->device);
     cudaStream_t s = c->stream;
     char* db = static_cast<char*>(c->d_in.p);
-    // control words, hot ones on their own 128-byte lines: [0] fallback count, [1] flush count,
-    // [kCtrlCursors + 32 k] work-queue cursor of launch k
+    // control words, hot ones on their own 128-byte lines: [0] fallback count, [1] flush count, [2] re-check count,
+    // [3] tasks of the double re-run, [4] fallback slots handed out, [kCtrlCursors + 32 k] work-queue cursor of launch k
     uint32_t* ctrl = static_cast<uint32_t*>(c->d_ctrl.p);
     uint32_t launches = 0;
     PMM_CUDA(c, cudaEventRecord(c->ev[0], s));
@@ -578,9 +589,9 @@ int pmm_launch(pmm_ctx* c)
     // fast mode: results within the guard band around the threshold are re-run by an exact kernel before the decision
     // is taken, so the decision (and the float value of those pairs) is the reference's, bit for bit
     const float thr = 1e-28f;
-    FallbackQueue fq{static_cast<Task*>(c->d_fb_tasks.p), static_cast<uint32_t*>(c->d_fb_idx.p), ctrl + 0, (uint32_t)c->pairs,
+    FallbackQueue fq{ctrl + 0, (uint32_t)c->pairs,
                      c->fast ? thr * (1.0f - c->guard) : thr, c->fast ? thr * (1.0f + c->guard) : thr,
-                     static_cast<Task*>(c->d_tiny_tasks.p) /* free until the double pass is over */, ctrl + 2};
+                     static_cast<Task*>(c->d_tiny_tasks.p), ctrl + 2};
     uint32_t cursor = kCtrlCursors;
     for (const LaunchSeg& seg : c->segs) {
         a.inity = c->d_iyf.p;
@@ -604,12 +615,30 @@ int pmm_launch(pmm_ctx* c)
     }
     PMM_CUDA(c, cudaEventRecord(c->ev[1], s));
 
-    // ---- double re-run of the fallback list (count read from device memory) -----------------------------------------
-    a.inity = c->d_iyd.p; a.out = c->d_dres.p; a.tasks = static_cast<Task*>(c->d_fb_tasks.p);
-    a.ntasks = 0; a.ntasks_dev = ctrl + 0; a.counter = ctrl + cursor; cursor += 32;
+    // ---- double re-run (PairHMMWorker.cpp:176-184): the results below the threshold become tasks, the failing haplotypes
+    //      of a read together; their number is only known on the device ------------------------------------------------
     const int KD = c->f64_rows;
+    const int f64_ctas = c->sm_count * std::max(1, forward_f64_ctas_per_sm(KD));
+    FallbackBuild fb{};
+    fb.raw = static_cast<float*>(c->d_raw.p);
+    fb.regions = reinterpret_cast<RegionDesc*>(db + c->off_regions);
+    fb.reads = a.reads;
+    fb.num_region = c->num_region; fb.num_rows = c->num_rows;
+    fb.threshold = thr;
+    fb.ctrl = ctrl;
+    fb.tasks = static_cast<Task*>(c->d_fb_tasks.p);
+    fb.out_index = static_cast<uint32_t*>(c->d_fb_idx.p);
+    fb.hap_list = static_cast<uint32_t*>(c->d_fb_hap.p);
+    fb.capacity = (uint32_t)c->pairs;
+    fb.single_stripe_rows = 32u * (uint32_t)KD;
+    fb.target_tasks = (uint32_t)(f64_ctas * kWarpsPerCta * c->f64_tasks_per_warp);
+    fb.max_run = (uint32_t)c->f64_max_run;
+    PMM_CUDA(c, launch_build_fallback(fb, c->sm_count, s));
+    ++launches;
+    a.inity = c->d_iyd.p; a.out = c->d_dres.p; a.tasks = fb.tasks; a.hap_list = fb.hap_list;
+    a.ntasks = 0; a.ntasks_dev = ctrl + 3; a.counter = ctrl + cursor; cursor += 32;
     a.tiny_threshold = ldexp(1.0, -800); a.tiny_count = ctrl + 1;
-    PMM_CUDA(c, launch_forward_f64(KD, a, c->sm_count * std::max(1, forward_f64_ctas_per_sm(KD)), s));
+    PMM_CUDA(c, launch_forward_f64(KD, a, f64_ctas, s));
     ++launches;
     PMM_CUDA(c, cudaEventRecord(c->ev[2], s));
     c->stats.kernel_launches = launches;
@@ -922,6 +951,31 @@ int pmm_measure_fp32_peak(pmm_ctx* c, double* lane_instr_per_s, double* sm_mhz)
     }
     *lane_instr_per_s = best;
     if (sm_mhz) *sm_mhz = best / ((double)c->sm_count * 128.0) * 1e-6;   // lower bound: assumes 128 lanes/clk/SM fully used
+    return PMM_OK;
+}
+
+int pmm_measure_fp64_peak(pmm_ctx* c, double* lane_instr_per_s)
+{
+    if (!c || !lane_instr_per_s) return PMM_ERR_INVALID;
+    cudaSetDevice(c->device);
+    const int ctas = c->sm_count * 8, iters = 60;
+    PMM_CUDA(c, c->d_probe.reserve(sizeof(double) * ctas * 256));
+    cudaStream_t s = c->stream;
+    PMM_CUDA(c, launch_fp64_probe(static_cast<double*>(c->d_probe.p), 5, ctas, s));
+    double best = 0;
+    cudaEvent_t e1;
+    PMM_CUDA(c, cudaEventCreate(&e1));
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(c->ev[3], s);
+        cudaError_t e = launch_fp64_probe(static_cast<double*>(c->d_probe.p), iters, ctas, s);
+        if (e == cudaSuccess) e = cudaEventRecord(e1, s);
+        if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) { cudaEventDestroy(e1); return c->fail_cuda(e, "fp64 probe"); }
+        float ms = 0; cudaEventElapsedTime(&ms, c->ev[3], e1);
+        best = std::max(best, (double)ctas * 256 * iters * 512.0 / (ms * 1e-3));
+    }
+    cudaEventDestroy(e1);
+    *lane_instr_per_s = best;
     return PMM_OK;
 }
 

@@ -27,6 +27,7 @@
 //   * Work is pulled by warps from a global queue (atomicAdd), grid = SMs x resident CTAs.
 #include "pmm_kernels.cuh"
 
+#include <algorithm>
 #include <atomic>
 #include <cfloat>
 #include <type_traits>
@@ -99,25 +100,20 @@ template <typename T, int K> __host__ __device__ constexpr int min_ctas()
     return sizeof(T) == 8 ? (K <= 6 ? 3 : 2) : K <= PMM_F32_4CTA_MAXK ? 4 : K <= PMM_F32_3CTA_MAXK ? 3 : 2;
 }
 
-// ---- fallback list: the float pass appends the pairs whose result is below 1e-28f the moment the result exists ----
-// (Tried and measured on B200, see DESIGN.md section 4.4: also *consuming* the list inside the float kernel, so that the
+// ---- fallback count: the float pass counts the pairs whose result is below 1e-28f the moment the result exists ----
+// (Tried and measured on B200, see DESIGN.md section 4.5: *consuming* a fallback list inside the float kernel, so that the
 // double re-run overlaps the float pass, is slower than a separate double launch -- the two loop bodies evict each
 // other from the instruction caches and the double tasks run at the float kernel's lower occupancy.)
-__device__ __forceinline__ void push_fallback(const FallbackQueue& fq, uint32_t read, uint32_t hap, uint32_t out_index)
+__device__ __forceinline__ void count_fallback(const FallbackQueue& fq)
 {
-    const uint32_t slot = atomicAdd(fq.reserve, 1u);
-    if (slot >= fq.capacity) return;              // cannot happen: capacity = pairs of the job
-    Task t;
-    t.read[0] = read; t.read[1] = t.read[2] = t.read[3] = 0;
-    t.out_base[0] = slot; t.out_base[1] = t.out_base[2] = t.out_base[3] = 0;
-    t.hap_first = hap; t.nhaps = 1; t.nreads = 1; t.param_off = 0;
-    fq.tasks[slot] = t;
-    fq.out_index[slot] = out_index;
+    // The pair itself is found again by build_fallback_kernel's scan of the results (which groups the failing pairs of
+    // a read into one task); the float pass only keeps the total, which sizes those tasks.
+    atomicAdd(fq.reserve, 1u);
 }
 
 // Fast mode: a result too close to 1e-28f to trust the decision.  The re-check task writes the exact float result
-// over the fast one (out_base = the pair's own result index) and, being an exact kernel with kPush, appends the
-// pair to the fallback list if that is what the reference would do.
+// over the fast one (out_base = the pair's own result index) and, being an exact kernel with kPush, counts the
+// pair as a fallback if that is what the reference would do.
 __device__ __forceinline__ void push_recheck(const FallbackQueue& fq, uint32_t read, uint32_t hap, uint32_t out_index)
 {
     const uint32_t slot = atomicAdd(fq.recheck_count, 1u);
@@ -138,9 +134,13 @@ __device__ __forceinline__ void push_recheck(const FallbackQueue& fq, uint32_t r
 // kInline: compute the float row parameters in the kernel instead of reading read_params_kernel's planes (single-pair
 // re-check tasks have no parameter block).
 constexpr int kFlush = 1, kPush = 2, kFast = 4, kInline = 8;
-// kRetry (kernel level, double only): a single-pair task whose result is below tiny_threshold is run again at once with
+// kRetry (kernel level, double only): a pair whose result is below tiny_threshold is run again at once with
 // kFlush -- the case where x86 flush-to-zero of intermediate products may have changed the reference's result.
 constexpr int kRetry = 16;
+// kList (double re-run): the task's haplotypes are not a run of consecutive ones but entries hap_first .. hap_first +
+// nhaps - 1 of a.hap_list (the failing haplotypes of one read, build_fallback_kernel).  The wavefront still flows from
+// one haplotype into the next; a lane re-points its stream pointer when it crosses a separator.
+constexpr int kList = 32;
 
 template <typename T, int K, int W, bool STRIPED, int F>
 __device__ __forceinline__ void run_task(const ForwardArgs& a, const Task* tk, T* wtab, const int lane,
@@ -148,6 +148,7 @@ __device__ __forceinline__ void run_task(const ForwardArgs& a, const Task* tk, T
 {
     using A = Arith<T>;
     constexpr bool FLUSH = (F & kFlush) != 0, PUSH = (F & kPush) != 0, FAST = (F & kFast) != 0, INLINE = (F & kInline) != 0;
+    constexpr bool LIST = (F & kList) != 0;
     constexpr bool kIsFloat = std::is_same<T, float>::value;
     static_assert(kIsFloat || !(FAST || PUSH || INLINE), "float-only flags");
     constexpr int VEC = A::kVec;
@@ -169,10 +170,22 @@ __device__ __forceinline__ void run_task(const ForwardArgs& a, const Task* tk, T
     const int nstripes = STRIPED ? (R + W * K) / (W * K) : 1;       // ceil((R + 1) / (W*K))
     const int pad = nstripes * W * K - R;                            // >= 1 boundary rows at the top
 
-    const uint32_t s0 = a.spos[hap_first];
-    const int Lc = (int)(a.spos[hap_first + nhaps] - s0) + 1;        // elements incl. the terminal separator
+    // haplotype n of the task, as an index into spos / inity
+    auto hap_at = [&](uint32_t n) -> uint32_t { return LIST ? __ldg(a.hap_list + hap_first + n) : hap_first + n; };
+    const uint32_t s0 = a.spos[hap_at(0)];
+    int Lc;                                                          // elements incl. the terminal separator
+    if constexpr (LIST) {
+        // the task's haplotypes lie anywhere in the stream: add up their lengths (+ one separator each)
+        static_assert(!LIST || W == 32, "list tasks: one read per warp");
+        uint32_t len = 0;
+        for (uint32_t n = lane; n < nhaps; n += 32) { const uint32_t h = hap_at(n); len += a.spos[h + 1] - a.spos[h]; }
+        #pragma unroll
+        for (int o = 16; o; o >>= 1) len += __shfl_xor_sync(0xffffffffu, len, o);
+        Lc = (int)len + 1;
+    } else {
+        Lc = (int)(a.spos[hap_first + nhaps] - s0) + 1;
+    }
     const int Tsteps = Lc + W - 1;
-    const uint8_t* sp = a.stream + s0 - l;                           // this lane's element at step t is sp[t]
 
     T* scM = nullptr; T* scX = nullptr; T* scY = nullptr;
     if (STRIPED) {
@@ -182,6 +195,7 @@ __device__ __forceinline__ void run_task(const ForwardArgs& a, const Task* tk, T
 
     #pragma unroll 1
     for (int stripe = 0; stripe < nstripes; ++stripe) {
+        const uint8_t* sp = a.stream + s0 - l;                       // this lane's element at step t is sp[t]
         // ---- per-row parameters (avx-pairhmm-template.h:108-127, :155-158) --------------------------
         T pMM[K], pG[K], pMX[K], pMY[K], pC[K];       // pXX == pYY == ph2pr[c] (:119-121)
         T pX0 = (T)0;                                                // pC[0] as the X update of row 0 sees it
@@ -302,7 +316,8 @@ __device__ __forceinline__ void run_task(const ForwardArgs& a, const Task* tk, T
         };
 
         // Step with every check: separators, fill/drain, stripe carries.
-        auto checked_step = [&](int t, unsigned e) {
+        auto checked_step = [&](int t, unsigned e) -> bool {
+            bool repointed = false;
             T inM = __shfl_up_sync(0xffffffffu, M[K - 1], 1, W);
             T inX = __shfl_up_sync(0xffffffffu, X[K - 1], 1, W);
             T inY = __shfl_up_sync(0xffffffffu, Y[K - 1], 1, W);
@@ -319,13 +334,22 @@ __device__ __forceinline__ void run_task(const ForwardArgs& a, const Task* tk, T
                                 // (PairHMMWorker.cpp:176; NaN -> false).  Fast kernels: results in [lo, hi) are too close
                                 // to the threshold to decide and go to the exact re-check list instead.
                                 if (res < fq.hi) {
-                                    if (res < fq.lo) push_fallback(fq, tk->read[g], hap_first + nsep - 1, out_base + nsep - 1);
+                                    if (res < fq.lo) count_fallback(fq);
                                     else push_recheck(fq, tk->read[g], hap_first + nsep - 1, out_base + nsep - 1);
                                 }
                             }
                         }
                     done = nsep == (int)nhaps;
-                    const T iy = done ? (T)0 : inity[hap_first + nsep];
+                    T iy = (T)0;
+                    if (!done) {
+                        const uint32_t h = hap_at((uint32_t)nsep);
+                        iy = inity[h];
+                        if constexpr (LIST) {
+                            // this separator stands at step t for this lane; from here on the lane reads haplotype h
+                            sp = a.stream + a.spos[h] - t;
+                            repointed = true;
+                        }
+                    }
                     ++nsep;
                     #pragma unroll
                     for (int j = 0; j < K; ++j) { M[j] = (T)0; X[j] = (T)0; Y[j] = (padmask >> j) & 1 ? iy : (T)0; }
@@ -336,6 +360,7 @@ __device__ __forceinline__ void run_task(const ForwardArgs& a, const Task* tk, T
                 }
                 if (carry_out) { scM[p] = M[K - 1]; scX[p] = X[K - 1]; scY[p] = Y[K - 1]; }
             }
+            return repointed;
         };
 
         // Branch-free step: every lane is inside the bases of a haplotype.
@@ -361,13 +386,30 @@ __device__ __forceinline__ void run_task(const ForwardArgs& a, const Task* tk, T
             // checked window: lane l meets the separator at step next_sep + l
             int wend = next_sep + W;
             if (wend > Tsteps) wend = Tsteps;
-            for (; t < wend; ++t) {
-                const unsigned en = sp[t + 1];
-                checked_step(t, e);
-                e = en;
+            if constexpr (LIST) {
+                // what a lane reads right after re-pointing at the separator of haplotype hn: that haplotype's first
+                // base, the same for every lane -- loaded ahead of the window so that its latency is not exposed
+                unsigned first = 0;
+                uint32_t hlen = 0;
+                if (hn < nhaps) { const uint32_t h = hap_at(hn); const uint32_t ps = a.spos[h]; first = a.stream[ps + 1]; hlen = a.spos[h + 1] - ps; }
+                for (; t < wend; ++t) {
+                    const unsigned en = sp[t + 1];
+                    // (a haplotype shorter than the warp lets a lane cross a second separator inside this window:
+                    // that one's first base is fetched on the spot)
+                    if (checked_step(t, e)) e = nsep - 1 == (int)hn ? first : sp[t + 1];
+                    else e = en;
+                }
+                ++hn;
+                next_sep = hn <= nhaps ? next_sep + (int)hlen : Tsteps + W;
+            } else {
+                for (; t < wend; ++t) {
+                    const unsigned en = sp[t + 1];
+                    checked_step(t, e);
+                    e = en;
+                }
+                ++hn;
+                next_sep = hn <= nhaps ? (int)(a.spos[hap_first + hn] - s0) : Tsteps + W;
             }
-            ++hn;
-            next_sep = hn <= nhaps ? (int)(a.spos[hap_first + hn] - s0) : Tsteps + W;
             int send = next_sep < Tsteps ? next_sep : Tsteps;
             // kSteadyUnroll steps per trip: the element loads use one pointer with immediate offsets
             const uint8_t* q = sp + t;
@@ -408,15 +450,81 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, min_ctas<T, K>()) pmm_forwa
         if constexpr ((F & kRetry) != 0) {
             // Intermediate products below DBL_MIN are flushed to zero on the reference's x86 (FTZ on); they can only
             // influence results that are themselves tiny.  Everything below tiny_threshold (2^-800, scaled by 2^1020) is
-            // recomputed with the flush emulated after every product; above it the two arithmetics agree.
-            static_assert(std::is_same<T, double>::value && W == 32, "retry is for the single-pair double tasks");
+            // recomputed, one pair at a time, with the flush emulated after every product; above it the two
+            // arithmetics agree.
+            static_assert(std::is_same<T, double>::value && W == 32, "retry is for the one-read double tasks");
             __syncwarp();
-            const uint32_t slot = a.tasks[ti].out_base[0];
-            const double r = __ldcg(static_cast<const double*>(a.out) + slot);       // written by lane 31 a moment ago
-            if (r < a.tiny_threshold) {
-                if (lane == 0) atomicAdd(a.tiny_count, 1u);
-                run_task<T, K, W, STRIPED, (F & ~kRetry) | kFlush>(a, a.tasks + ti, wtab, lane, gwarp, fq);
+            const Task tk = a.tasks[ti];
+            for (uint32_t n0 = 0; n0 < tk.nhaps; n0 += 32) {
+                double r = 1.0;                                                      // written by lane 31 a moment ago
+                if (n0 + lane < tk.nhaps) r = __ldcg(static_cast<const double*>(a.out) + tk.out_base[0] + n0 + lane);
+                unsigned m = __ballot_sync(0xffffffffu, r < a.tiny_threshold);
+                while (m) {
+                    const uint32_t n = n0 + (uint32_t)__ffs(m) - 1;
+                    m &= m - 1;
+                    Task one = tk;
+                    one.hap_first = tk.hap_first + n; one.nhaps = 1; one.out_base[0] = tk.out_base[0] + n;
+                    if (lane == 0) atomicAdd(a.tiny_count, 1u);
+                    run_task<T, K, W, STRIPED, (F & ~kRetry) | kFlush>(a, &one, wtab, lane, gwarp, fq);
+                }
             }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Fallback tasks of the double re-run: one warp per result row (one read against the haplotypes of its region).
+// ---------------------------------------------------------------------------------------------------------
+// The reference re-runs every pair with raw < 1e-28f in double, one pair at a time (PairHMMWorker.cpp:176-184).  Here
+// the failing haplotypes of a read become tasks of `run` haplotypes each, so that the wavefront bubble, the row
+// parameters (a double division per row) and the shared-memory weight table are paid once per task, not once per
+// pair.  `run` follows from the number of failing pairs the float pass counted: enough tasks to keep every resident
+// warp of the double kernel supplied, never more than max_run.  Slot k of the fallback list (out_index[k], hap_list[k],
+// and the double result the kernel writes to dres[k]) belongs to one pair; a task owns consecutive slots.
+__global__ void __launch_bounds__(256) build_fallback_kernel(const FallbackBuild b)
+{
+    const uint32_t total = b.ctrl[0];
+    if (total == 0) return;
+    const uint32_t run_cap = max(1u, min(b.max_run, total / max(1u, b.target_tasks)));
+    const uint32_t lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    for (uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < b.num_rows; row += warps) {
+        uint32_t lo = 0, hi = b.num_region;                       // last region with row_first <= row
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (b.regions[mid].row_first <= row) lo = mid; else hi = mid; }
+        const RegionDesc rg = b.regions[lo];
+        const uint32_t r = row - rg.row_first, read = rg.read_first + r, base = rg.out_first + r * rg.nhaps;
+        const float* raw = b.raw + base;
+        uint32_t n = 0;
+        for (uint32_t h0 = 0; h0 < rg.nhaps; h0 += 32) {
+            const bool fail = h0 + lane < rg.nhaps && raw[h0 + lane] < b.threshold;      // NaN -> false, like the reference
+            n += __popc(__ballot_sync(0xffffffffu, fail));
+        }
+        if (n == 0) continue;
+        // reads longer than one stripe of the double kernel carry rows through scratch sized for one haplotype
+        const uint32_t run = b.reads[read].len + 1 > b.single_stripe_rows ? 1u : run_cap;
+        const uint32_t ntask = (n + run - 1) / run;
+        uint32_t slot = 0, tfirst = 0;
+        if (lane == 0) { slot = atomicAdd(b.ctrl + 4, n); tfirst = atomicAdd(b.ctrl + 3, ntask); }
+        slot = __shfl_sync(0xffffffffu, slot, 0); tfirst = __shfl_sync(0xffffffffu, tfirst, 0);
+        if (slot + n > b.capacity) continue;                       // cannot happen: capacity = pairs of the job
+        uint32_t k = slot;
+        for (uint32_t h0 = 0; h0 < rg.nhaps; h0 += 32) {
+            const bool fail = h0 + lane < rg.nhaps && raw[h0 + lane] < b.threshold;
+            const unsigned m = __ballot_sync(0xffffffffu, fail);
+            if (fail) {
+                const uint32_t pos = k + __popc(m & lt);
+                b.out_index[pos] = base + h0 + lane;
+                b.hap_list[pos] = rg.hap_first + h0 + lane;
+            }
+            k += __popc(m);
+        }
+        for (uint32_t t = lane; t < ntask; t += 32) {
+            const uint32_t k0 = (uint32_t)((uint64_t)n * t / ntask), k1 = (uint32_t)((uint64_t)n * (t + 1) / ntask);
+            Task tk;
+            tk.read[0] = read; tk.read[1] = tk.read[2] = tk.read[3] = 0;
+            tk.out_base[0] = slot + k0; tk.out_base[1] = tk.out_base[2] = tk.out_base[3] = 0;
+            tk.hap_first = slot + k0; tk.nhaps = k1 - k0; tk.nreads = 1; tk.param_off = 0;
+            b.tasks[tfirst + t] = tk;
         }
     }
 }
@@ -511,6 +619,26 @@ __global__ void __launch_bounds__(256) fp32_probe_kernel(float* sink, int iters)
     sink[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// The same for the FP64 pipe (roofline denominator of the double re-run): independent DMUL/DADD chains.
+__global__ void __launch_bounds__(256) fp64_probe_kernel(double* sink, int iters)
+{
+    double x[8];
+    #pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = 1.0 + threadIdx.x * 1e-3 + i;
+    const double m = 0.99999, c = 1e-6;
+    for (int it = 0; it < iters; ++it) {
+        #pragma unroll
+        for (int rep = 0; rep < 64; ++rep) {
+            #pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = (rep & 1) ? __dadd_rn(x[i], c) : __dmul_rn(x[i], m);
+        }
+    }
+    double s = 0;
+    #pragma unroll
+    for (int i = 0; i < 8; ++i) s += x[i];
+    sink[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Variant table
 // ---------------------------------------------------------------------------------------------------------
@@ -599,7 +727,7 @@ int recheck_f32_ctas_per_sm() { return variant_ctas_per_sm<float, kStripedK, 32,
 cudaError_t launch_forward_f64(int K, const ForwardArgs& a, int ctas, cudaStream_t s)
 {
     const FallbackQueue none{};
-#define X(k) if (K == k) return launch_variant<double, k, 32, true, kRetry>(a, none, ctas, s);
+#define X(k) if (K == k) return launch_variant<double, k, 32, true, kRetry | kList>(a, none, ctas, s);
     PMM_F64_ROWS(X)
 #undef X
     return cudaErrorInvalidValue;
@@ -607,7 +735,7 @@ cudaError_t launch_forward_f64(int K, const ForwardArgs& a, int ctas, cudaStream
 
 int forward_f64_ctas_per_sm(int K)
 {
-#define X(k) if (K == k) return variant_ctas_per_sm<double, k, 32, true, kRetry>();
+#define X(k) if (K == k) return variant_ctas_per_sm<double, k, 32, true, kRetry | kList>();
     PMM_F64_ROWS(X)
 #undef X
     return 0;
@@ -624,6 +752,14 @@ int pick_f64_rows(uint32_t max_read_len)
         if (!best || padded <= best_padded) { best = k; best_padded = padded; }
     }
     return best;
+}
+
+cudaError_t launch_build_fallback(const FallbackBuild& b, int sm_count, cudaStream_t s)
+{
+    if (b.num_rows == 0) return cudaSuccess;
+    const int ctas = (int)std::min<uint64_t>(((uint64_t)b.num_rows + 7) / 8, (uint64_t)sm_count * 8);
+    build_fallback_kernel<<<ctas, 256, 0, s>>>(b);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_build_stream(const uint8_t* hap_blob, const HapDesc* haps, const uint32_t* spos, uint32_t num_hap,
@@ -646,6 +782,12 @@ cudaError_t launch_read_params(const uint8_t* read_blob, const ReadDesc* reads, 
 cudaError_t launch_fp32_probe(float* sink, int iters, int ctas, cudaStream_t s)
 {
     fp32_probe_kernel<<<ctas, 256, 0, s>>>(sink, iters);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fp64_probe(double* sink, int iters, int ctas, cudaStream_t s)
+{
+    fp64_probe_kernel<<<ctas, 256, 0, s>>>(sink, iters);
     return cudaGetLastError();
 }
 

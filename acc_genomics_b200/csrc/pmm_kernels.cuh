@@ -42,6 +42,7 @@ struct ForwardArgs {
     const uint8_t*  stream;        // points at stream[0]; kStreamFrontPad readable bytes precede it
     const uint32_t* spos;          // [num_hap + 1]; spos[num_hap] = position of the final SEP
     const void*     inity;         // float* or double* [num_hap]
+    const uint32_t* hap_list;      // double re-run: the tasks' haplotypes (Task::hap_first indexes this list)
     const Task*     tasks;
     const uint32_t* ntasks_dev;    // if non-null the task count is read from device memory (fallback list)
     uint32_t        ntasks;
@@ -54,18 +55,37 @@ struct ForwardArgs {
     DeviceTables    tab;
 };
 
-// Fallback list: the float pass appends one single-pair task per result below 1e-28f (PairHMMWorker.cpp:176).
+// What the float pass reports about results below 1e-28f (PairHMMWorker.cpp:176): their number (the pairs themselves
+// are found again by build_fallback_kernel) and, in fast mode, the pairs too close to the threshold to decide.
 struct FallbackQueue {
-    Task*     tasks;
-    uint32_t* out_index;     // position of the pair in the job's result
-    uint32_t* reserve;       // entries appended so far (== fallback count when the float pass is done)
-    uint32_t  capacity;
+    uint32_t* reserve;       // results below `lo` so far (== fallback count when the float pass is done)
+    uint32_t  capacity;      // room in recheck_tasks
     // Thresholds of the float pass: result < lo -> fallback list; lo <= result < hi -> exact re-check list.  Exact
     // kernels run with lo == hi == 1e-28f (the reference's test, PairHMMWorker.cpp:176); fast kernels with a guard band.
     float     lo, hi;
     Task*     recheck_tasks;
     uint32_t* recheck_count;
 };
+
+// Input of build_fallback_kernel: turns the results below the threshold into tasks for the double kernel, the failing
+// haplotypes of one read together.  ctrl: [0] number of failing pairs (counted by the float pass), [3] tasks written,
+// [4] slots handed out.
+struct FallbackBuild {
+    const float*      raw;
+    const RegionDesc* regions;
+    const ReadDesc*   reads;
+    uint32_t          num_region, num_rows;
+    float             threshold;
+    uint32_t*         ctrl;
+    Task*             tasks;
+    uint32_t*         out_index;           // [slot] position of the pair in the job's result
+    uint32_t*         hap_list;            // [slot] its haplotype
+    uint32_t          capacity;            // slots available (= pairs of the job)
+    uint32_t          single_stripe_rows;  // 32 * K of the double kernel: longer reads get single-pair tasks
+    uint32_t          target_tasks;        // tasks wanted: haplotypes per task = failing pairs / target_tasks ...
+    uint32_t          max_run;             // ... but at most this many
+};
+cudaError_t launch_build_fallback(const FallbackBuild& b, int sm_count, cudaStream_t s);
 
 // Launch helpers implemented in pmm_kernels.cu -------------------------------------------------------------
 
@@ -76,8 +96,8 @@ cudaError_t launch_forward_f32(int K, int W, bool striped, bool fast, const Forw
 // Exact float re-run of the single-pair tasks on the re-check list (fast mode), overwriting their results.
 cudaError_t launch_recheck_f32(const ForwardArgs& a, const FallbackQueue& fq, int ctas, cudaStream_t s);
 int recheck_f32_ctas_per_sm();
-// Double re-run (fallback list), K in {4, 5, 6, 8} rows per lane from pick_f64_rows().  Results below a.tiny_threshold are
-// recomputed in the same kernel with x86 flush-to-zero emulated on every product.
+// Double re-run of build_fallback_kernel's tasks, K in {4, 5, 6, 8} rows per lane from pick_f64_rows().  Results below
+// a.tiny_threshold are recomputed in the same kernel with x86 flush-to-zero emulated on every product.
 cudaError_t launch_forward_f64(int K, const ForwardArgs& a, int ctas, cudaStream_t s);
 int pick_f64_rows(uint32_t max_read_len);
 // CTAs per SM the given variant reaches.
@@ -94,5 +114,7 @@ cudaError_t launch_read_params(const uint8_t* read_blob, const ReadDesc* reads, 
 
 // FP32 issue-rate probe used for the roofline denominator (dependent-free FMUL/FADD streams).
 cudaError_t launch_fp32_probe(float* sink, int iters, int ctas, cudaStream_t s);
+// The same for the FP64 pipe (independent DMUL/DADD streams): denominator of the double re-run's roofline.
+cudaError_t launch_fp64_probe(double* sink, int iters, int ctas, cudaStream_t s);
 
 }  // namespace pmm

@@ -105,16 +105,19 @@ int plan_job(uint32_t num_read, const uint32_t* read_off, uint32_t num_hap, cons
 
     // ---- regions, result offsets, the reference's cell count (host/main.cpp:305-313) -------------------------
     plan.regions.resize(num_region);
+    uint64_t rows = 0;
     for (uint32_t g = 0; g < num_region; ++g) {
         const pmm_region_t& r = regions[g];
         if (!r.num_read || !r.num_hap || (uint64_t)r.read_first + r.num_read > num_read ||
             (uint64_t)r.hap_first + r.num_hap > num_hap) { err = "region out of range"; return PMM_ERR_INVALID; }
-        plan.regions[g] = RegionDesc{r.read_first, r.num_read, r.hap_first, r.num_hap, (uint32_t)plan.pairs};
+        plan.regions[g] = RegionDesc{r.read_first, r.num_read, r.hap_first, r.num_hap, (uint32_t)plan.pairs, (uint32_t)rows};
+        rows += r.num_read;
         plan.pairs += (uint64_t)r.num_read * r.num_hap;
         plan.cells += (uint64_t)(read_off[r.read_first + r.num_read] - read_off[r.read_first]) *
                       (uint64_t)(hap_off[r.hap_first + r.num_hap] - hap_off[r.hap_first]);
         if (plan.pairs >= (1ull << 31)) { err = "more than 2^31 pairs in one job: split it"; return PMM_ERR_INVALID; }
     }
+    plan.rows = rows;
 
     // ---- read groups --------------------------------------------------------------------------------------------
     // Reads of a region are sorted by length (longest first); the longest unassigned read picks the (K, W)

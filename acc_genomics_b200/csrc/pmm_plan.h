@@ -19,7 +19,7 @@ struct Plan {
     std::vector<Task> tasks;            // grouped by variant, see segs (empty when the caller supplied the destination)
     uint64_t num_tasks = 0;
     std::vector<LaunchSeg> segs;        // one kernel launch each, largest footprint first
-    uint64_t pairs = 0, cells = 0;
+    uint64_t pairs = 0, cells = 0, rows = 0;   // rows: result rows = reads summed over regions
     uint32_t max_hap_len = 0, max_read_len = 0;
     uint32_t haps_per_task = 0;
 };

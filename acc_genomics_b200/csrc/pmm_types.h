@@ -12,7 +12,7 @@ constexpr int kStripedK = 8;            // rows per lane of the striped float ke
 
 struct ReadDesc { uint32_t off, stride, len; };
 struct HapDesc  { uint32_t off, len; };
-struct RegionDesc { uint32_t read_first, nreads, hap_first, nhaps, out_first; };
+struct RegionDesc { uint32_t read_first, nreads, hap_first, nhaps, out_first, row_first; };   // row_first: reads of earlier regions
 
 // One unit of work for one warp.  Group g (lanes g*W .. g*W+W-1) owns read[g]; all groups walk the same run of
 // haplotypes [hap_first, hap_first + nhaps).  The result for (read[g], hap_first + n) goes to out[out_base[g] + n].

@@ -22,7 +22,7 @@ EXPORTS = [
     "pmm_create", "pmm_destroy", "pmm_last_error", "pmm_device_count", "pmm_set_option",
     "pmm_forward_raw_serialized", "pmm_forward_log10", "pmm_forward_log10_serialized",
     "pmm_stage_flat", "pmm_stage_serialized", "pmm_fetch_fallback", "pmm_fetch_log10_indexed", "pmm_launch", "pmm_sync", "pmm_fetch_raw", "pmm_fetch_log10", "pmm_fetch_fallback_mask",
-    "pmm_get_stats", "pmm_measure_fp32_peak", "pmm_plan_flat", "pmm_host_table", "pmm_host_finish_log10",
+    "pmm_get_stats", "pmm_measure_fp32_peak", "pmm_measure_fp64_peak", "pmm_plan_flat", "pmm_host_table", "pmm_host_finish_log10",
     "pmm_pool_create", "pmm_pool_destroy", "pmm_pool_last_error", "pmm_pool_num_devices", "pmm_pool_submit_flat",
     "pmm_pool_wait", "pmm_pool_device_load", "pmm_pool_set_merge",
 ]
@@ -89,6 +89,7 @@ def load_library() -> C.CDLL:
         L.pmm_fetch_fallback_mask.argtypes = [vp, vp, u64]
         L.pmm_get_stats.argtypes = [vp, C.POINTER(PmmStats)]
         L.pmm_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.pmm_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double)]
         L.pmm_plan_flat.argtypes = [u32, vp, u32, vp, u32, vp, C.c_int, C.c_int, vp, u64, C.POINTER(u64)]
         L.pmm_host_table.argtypes = [C.c_int, vp, u64]
         L.pmm_host_finish_log10.argtypes = [vp, u64, vp, vp, u64, vp]
@@ -238,6 +239,11 @@ class PairHMMEngine:
         r, mhz = C.c_double(), C.c_double()
         self._ck(self.lib.pmm_measure_fp32_peak(self.h, C.byref(r), C.byref(mhz)))
         return r.value, mhz.value
+
+    def measure_fp64_peak(self) -> float:
+        r = C.c_double()
+        self._ck(self.lib.pmm_measure_fp64_peak(self.h, C.byref(r)))
+        return r.value
 
     # ---- one-shot paths ---------------------------------------------------------------------------------
     def forward(self, b: Batch):

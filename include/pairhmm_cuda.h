@@ -81,6 +81,8 @@ int  pmm_device_count(void);
  *   "force_variant"   = "K,W": rows per lane and lanes per read of the float kernel for every read that fits
  *                       (tuning sweeps, tools/sweep_variants.py); "0,0" gives the choice back to the planner,
  *                       "-1,0" keeps every variant in a launch of its own (no consolidation of rare ones)
+ *   "f64_tasks_per_warp", "f64_max_run" = how the double re-run cuts a read's failing haplotypes into tasks: about
+ *                       f64_tasks_per_warp tasks per resident warp (default 4), at most f64_max_run haplotypes each (16)
  *   "sync"            = "spin" (default): waits poll the stream, lowest latency for one context per core; "block":
  *                       waits sleep on a blocking event (for hosts with fewer cores than waiting threads; the pool takes
  *                       it from the environment variable PMM_POOL_SYNC=block)                                      */
@@ -194,6 +196,8 @@ int  pmm_host_finish_log10(const float* raw, uint64_t n, const uint32_t* fb_inde
 /* Measured FP32 instruction issue rate of this GPU in lane-instructions per second (the roofline denominator of
  * SURVEY.md section 8d; an independent FMUL/FADD stream, ~20 ms).  Also returns the SM clock seen while measuring. */
 int  pmm_measure_fp32_peak(pmm_ctx* ctx, double* lane_instr_per_s, double* sm_mhz);
+/* The same for the FP64 pipe (independent DMUL/DADD streams): the denominator of the double re-run's roofline. */
+int  pmm_measure_fp64_peak(pmm_ctx* ctx, double* lane_instr_per_s);
 
 #ifdef __cplusplus
 }

@@ -1,5 +1,7 @@
-"""BASELINE.json's full sizes through size-independent properties (the oracle would take minutes there), plus an
-oracle check on a random sample of pairs."""
+"""BASELINE.json's full sizes: every pair of configs 2, 3 and 4 and a tenth of config 5 against the oracle, bit for bit
+(the checker runs the whole batch on all host cores in about a second), plus size-independent properties."""
+import os
+
 import numpy as np
 import pytest
 
@@ -37,25 +39,32 @@ def test_full_config_properties(engine, checker, cfg):
     raw3 = engine.fetch_raw().reshape(b.num_read, b.num_hap)
     assert_bits_equal(raw3, raw, "region split invariance")
 
-    # (3) a random sample of pairs against the oracle, bit for bit
-    for _ in range(48):
-        i, j = int(rng.integers(b.num_read)), int(rng.integers(b.num_hap))
-        f = checker.f32(*b.read(i), b.haplotype(j))
-        assert np.float32(f).view(np.uint32) == raw[i, j].view(np.uint32)
-        if mask[i, j]:
-            d = checker.f64(*b.read(i), b.haplotype(j))
-            lic = checker.log10_ic()[1]
-            assert np.float64(np.log10(d) - lic).view(np.uint64) == out[i, j].view(np.uint64) or (d == 0 and np.isinf(out[i, j]))
+    # (3) every pair of the configuration against the oracle, bit for bit: raw floats, the float-versus-double decision
+    #     and the final log10 (the contract of FalconPairHMM::computePairhmmAVX, xlnx/host/FalconPairHMM.cpp:69-95)
+    raw_r, out_r, fb_r = checker.batch(b, threads=os.cpu_count() or 1)
+    assert_bits_equal(raw, raw_r, f"cfg{cfg} raw, all {b.num_pairs} pairs")
+    assert np.array_equal(mask, fb_r), f"cfg{cfg} fallback decision"
+    assert_bits_equal(out, out_r, f"cfg{cfg} log10, all {b.num_pairs} pairs")
 
 
-def test_config5_stream_sample(engine, checker):
-    """A 2 % slice of the 10^7-pair stream (50 regions) as one job; three regions checked in full against the oracle."""
-    regs = synth.config(5, scale=0.02)
-    j = engine.stage(regs); engine.launch()
-    raw = engine.fetch_raw(); out, nfb = engine.fetch_log10()
-    assert j["pairs"] == 50 * 4000 and np.isfinite(raw).all()
-    offs = np.cumsum([0] + [r.num_pairs for r in regs])
-    for k in (0, 17, 49):
-        raw_r, out_r, fb_r = checker.batch(regs[k], threads=8)
-        assert_bits_equal(raw[offs[k]:offs[k + 1]].reshape(raw_r.shape), raw_r, f"region {k} raw")
-        assert_bits_equal(out[offs[k]:offs[k + 1]].reshape(out_r.shape), out_r, f"region {k} log10")
+def test_config5_stream_tenth(engine, checker):
+    """A tenth of the 10^7-pair stream (250 regions, 10^6 pairs) as jobs of 25 regions; every region checked in full
+    against the oracle."""
+    regs = synth.config(5, scale=0.1)
+    assert len(regs) == 250
+    threads = os.cpu_count() or 1
+    nfb_total = 0
+    for j0 in range(0, len(regs), 25):
+        job = regs[j0:j0 + 25]
+        j = engine.stage(job); engine.launch()
+        raw = engine.fetch_raw(); out, nfb = engine.fetch_log10()
+        mask = engine.fetch_fallback_mask()
+        assert j["pairs"] == 25 * 4000
+        offs = np.cumsum([0] + [r.num_pairs for r in job])
+        for k, r in enumerate(job):
+            raw_r, out_r, fb_r = checker.batch(r, threads=threads)
+            assert_bits_equal(raw[offs[k]:offs[k + 1]].reshape(raw_r.shape), raw_r, f"region {j0 + k} raw")
+            assert np.array_equal(mask[offs[k]:offs[k + 1]].reshape(fb_r.shape), fb_r), f"region {j0 + k} decision"
+            assert_bits_equal(out[offs[k]:offs[k + 1]].reshape(out_r.shape), out_r, f"region {j0 + k} log10")
+        nfb_total += nfb
+    assert nfb_total > 0

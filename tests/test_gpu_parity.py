@@ -154,3 +154,37 @@ def test_repeat_launch_is_idempotent(engine):
     engine.launch(); engine.launch()
     c = engine.fetch_raw(); oc, _ = engine.fetch_log10()
     assert_bits_equal(a, c, "raw after relaunch"); assert_bits_equal(oa, oc, "log10 after relaunch")
+
+
+@pytest.mark.parametrize("tasks_per_warp,max_run", [(1, 64), (64, 1), (2, 3), (4, 16)])
+def test_double_rerun_task_shapes(engine, checker, golden, tasks_per_warp, max_run):
+    """The double re-run groups the failing haplotypes of a read into tasks (a list of haplotypes, not a run of
+    neighbours).  However the list is cut -- everything in one task, one pair per task, odd runs -- the results are the
+    reference's: haplotypes shorter than the warp (a lane crosses two separators in one window), results deep enough for
+    the flush-to-zero repeat inside a multi-haplotype task, reads of more than one stripe, failing and passing
+    haplotypes interleaved."""
+    engine.set_option("f64_tasks_per_warp", tasks_per_warp)
+    engine.set_option("f64_max_run", max_run)
+    try:
+        rng = np.random.Generator(np.random.PCG64(31))
+        # unrelated reads against random haplotypes with expensive gaps (deep underflow, some results exactly 0) ...
+        hl = list(range(1, 41, 3)) + [64, 65, 300, 500, 7, 2, 450, 33]
+        w = synth.region(rng, [20, 60, 120, 140, 151, 151, 159, 160, 175, 200, 250, 300], hl)
+        w.hap[:] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=w.hap.size)]
+        w.q[:] = 60
+        w.i[:] = 90; w.d[:] = 90; w.c[:] = 90
+        raw, out, mask = check(engine, checker, w, "deep underflow, ragged haplotypes")
+        assert mask.sum() > w.num_pairs // 2 and engine.stats()["flush_pairs"] > 0
+        # ... and a region where about half of the haplotypes of every read fail, interleaved with the ones that pass
+        b = synth.config(3, seed=41, scale=0.05)[0]
+        hp = rng.permutation(b.num_hap)
+        b = Batch.from_lists([b.read(k) for k in range(b.num_read)], [b.haplotype(int(k)) for k in hp])
+        raw, out, mask = check(engine, checker, b, "interleaved failing haplotypes")
+        assert 0.3 < mask.mean() < 0.7
+        cases, _ = golden
+        gb, raw_bits, log10_bits, gmask = cases["deep_underflow"]
+        raw, out, m = engine.forward(gb)
+        assert_bits_equal(out, log10_bits.view(np.float64), "golden deep_underflow log10")
+    finally:
+        engine.set_option("f64_tasks_per_warp", 4)
+        engine.set_option("f64_max_run", 16)
