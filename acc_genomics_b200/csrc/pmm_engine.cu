@@ -30,7 +30,7 @@ namespace {
 std::string g_create_error;
 
 constexpr size_t kAlign = 256;
-constexpr uint32_t kCtrlCursors = 64, kCtrlWords = 64 + 32 * 104;
+constexpr uint32_t kCtrlWords = kCtrlCursors + 32 * 104;
 inline size_t align_up(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
 
 struct DevBuf {
@@ -79,9 +79,10 @@ struct pmm_ctx {
     bool fast = false;                  // "mode" option: fast = contracted float kernels + exact re-check near the threshold
     float guard = 0.0078125f;           // "guard" option: relative half-width of the re-check band around 1e-28f (2^-7)
     int f64_rows = kF64K;               // rows per lane of the double kernel for the staged job (pick_f64_rows)
+    bool f64_striped = true;            // ... and whether its longest read needs more than one stripe of 32 x rows
     Variant force{0, 0, false};         // "force_variant" option (tuning sweeps): K,W of the float kernel
-    int f64_tasks_per_warp = 4;         // "f64_tasks_per_warp": tasks the double re-run aims at per resident warp ...
-    int f64_max_run = 16;               // "f64_max_run": ... and the most haplotypes it puts into one task
+    int f64_tasks_per_warp = 6;         // "f64_tasks_per_warp": tasks the double re-run aims at per resident warp ...
+    int f64_max_run = 6;                // "f64_max_run": ... and the most haplotypes it puts into one task (tools/f64_sweep.py)
 
     // device-resident tables
     DevBuf tables;
@@ -89,7 +90,7 @@ struct pmm_ctx {
 
     // job state
     PinBuf h_in;  DevBuf d_in;          // one arena: read blob | descs | hap blob | descs | spos | tasks | regions
-    DevBuf d_params, d_stream, d_iyf, d_iyd, d_raw, d_fb_tasks, d_fb_idx, d_fb_hap, d_tiny_tasks, d_dres, d_ctrl, d_scratch, d_probe;
+    DevBuf d_params, d_stream, d_iyf, d_iyd, d_raw, d_fb_tasks, d_fb_idx, d_fb_hap, d_fb_rows, d_tiny_tasks, d_dres, d_ctrl, d_scratch, d_probe;
     PinBuf h_out;                       // raw floats | fb idx | dres
     size_t off_rblob = 0, off_rdesc = 0, off_hblob = 0, off_hdesc = 0, off_spos = 0, off_tasks = 0, off_regions = 0, off_groups = 0;
     uint32_t num_groups = 0;
@@ -195,6 +196,7 @@ int stage_common(pmm_ctx* c, uint32_t num_read, const uint32_t* read_off, uint32
     const std::vector<RegionDesc>& rdesc = plan.regions;
     c->max_hap_len = max_hap;
     c->f64_rows = pick_f64_rows(plan.max_read_len);
+    c->f64_striped = plan.max_read_len + 1 > 32u * (uint32_t)c->f64_rows;
     c->segs = plan.segs;
 
     // ---- pack the rest of the input arena ---------------------------------------------------------------------
@@ -226,13 +228,14 @@ int stage_common(pmm_ctx* c, uint32_t num_read, const uint32_t* read_off, uint32
     if (c->fast) PMM_CUDA(c, c->d_tiny_tasks.reserve(sizeof(Task) * pairs));     // re-check list of the guard band
     PMM_CUDA(c, c->d_fb_idx.reserve(sizeof(uint32_t) * pairs));
     PMM_CUDA(c, c->d_fb_hap.reserve(sizeof(uint32_t) * pairs));
+    PMM_CUDA(c, c->d_fb_rows.reserve(sizeof(uint32_t) * 2 * plan.rows));
     PMM_CUDA(c, c->d_dres.reserve(sizeof(double) * pairs));
     PMM_CUDA(c, c->d_ctrl.reserve(sizeof(uint32_t) * kCtrlWords));
     PMM_CUDA(c, c->h_out.reserve(256 + align_up(sizeof(float) * pairs) + align_up(sizeof(uint32_t) * pairs) + sizeof(double) * pairs + 256));
     // carry rows of the striped kernels: one haplotype (+2 separators) per warp, three rows of doubles
     {
         int ctas64 = 1;
-        for (int k : {4, 5, 6, 8}) ctas64 = std::max(ctas64, forward_f64_ctas_per_sm(k));
+        for (int k : {4, 5, 6, 8}) ctas64 = std::max(ctas64, forward_f64_ctas_per_sm(k, true));
         const int ctas32 = std::max(std::max(forward_f32_ctas_per_sm(kStripedK, 32, true, false), forward_f32_ctas_per_sm(kStripedK, 32, true, true)),
                                     recheck_f32_ctas_per_sm());
         const size_t warps = (size_t)c->sm_count * std::max(ctas64, ctas32) * kWarpsPerCta;
@@ -474,7 +477,7 @@ void pmm_destroy(pmm_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->tables, &c->d_in, &c->d_params, &c->d_stream, &c->d_iyf, &c->d_iyd, &c->d_raw, &c->d_fb_tasks, &c->d_fb_idx,
-                      &c->d_fb_hap, &c->d_tiny_tasks, &c->d_dres, &c->d_ctrl, &c->d_scratch, &c->d_probe}) b->release();
+                      &c->d_fb_hap, &c->d_fb_rows, &c->d_tiny_tasks, &c->d_dres, &c->d_ctrl, &c->d_scratch, &c->d_probe}) b->release();
     c->h_in.release(); c->h_out.release();
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     if (c->ev_block) cudaEventDestroy(c->ev_block);
@@ -562,7 +565,8 @@ int pmm_launch(pmm_ctx* c)
     cudaStream_t s = c->stream;
     char* db = static_cast<char*>(c->d_in.p);
     // control words, hot ones on their own 128-byte lines: [0] fallback count, [1] flush count, [2] re-check count,
-    // [3] tasks of the double re-run, [4] fallback slots handed out, [kCtrlCursors + 32 k] work-queue cursor of launch k
+    // [3] tasks of the double re-run, [4] fallback slots handed out, [kCtrlHist ..) and [kCtrlClassCursor ..) the counting
+    // sort of those tasks, [kCtrlCursors + 32 k] work-queue cursor of launch k
     uint32_t* ctrl = static_cast<uint32_t*>(c->d_ctrl.p);
     uint32_t launches = 0;
     PMM_CUDA(c, cudaEventRecord(c->ev[0], s));
@@ -618,7 +622,7 @@ int pmm_launch(pmm_ctx* c)
     // ---- double re-run (PairHMMWorker.cpp:176-184): the results below the threshold become tasks, the failing haplotypes
     //      of a read together; their number is only known on the device ------------------------------------------------
     const int KD = c->f64_rows;
-    const int f64_ctas = c->sm_count * std::max(1, forward_f64_ctas_per_sm(KD));
+    const int f64_ctas = c->sm_count * std::max(1, forward_f64_ctas_per_sm(KD, c->f64_striped));
     FallbackBuild fb{};
     fb.raw = static_cast<float*>(c->d_raw.p);
     fb.regions = reinterpret_cast<RegionDesc*>(db + c->off_regions);
@@ -629,16 +633,19 @@ int pmm_launch(pmm_ctx* c)
     fb.tasks = static_cast<Task*>(c->d_fb_tasks.p);
     fb.out_index = static_cast<uint32_t*>(c->d_fb_idx.p);
     fb.hap_list = static_cast<uint32_t*>(c->d_fb_hap.p);
+    fb.row_slot = static_cast<uint32_t*>(c->d_fb_rows.p);
+    fb.spos = a.spos;
+    fb.max_hap_len = c->max_hap_len;
     fb.capacity = (uint32_t)c->pairs;
     fb.single_stripe_rows = 32u * (uint32_t)KD;
     fb.target_tasks = (uint32_t)(f64_ctas * kWarpsPerCta * c->f64_tasks_per_warp);
     fb.max_run = (uint32_t)c->f64_max_run;
     PMM_CUDA(c, launch_build_fallback(fb, c->sm_count, s));
-    ++launches;
+    launches += 2;
     a.inity = c->d_iyd.p; a.out = c->d_dres.p; a.tasks = fb.tasks; a.hap_list = fb.hap_list;
     a.ntasks = 0; a.ntasks_dev = ctrl + 3; a.counter = ctrl + cursor; cursor += 32;
     a.tiny_threshold = ldexp(1.0, -800); a.tiny_count = ctrl + 1;
-    PMM_CUDA(c, launch_forward_f64(KD, a, f64_ctas, s));
+    PMM_CUDA(c, launch_forward_f64(KD, c->f64_striped, a, f64_ctas, s));
     ++launches;
     PMM_CUDA(c, cudaEventRecord(c->ev[2], s));
     c->stats.kernel_launches = launches;

@@ -315,6 +315,23 @@ __device__ __forceinline__ void run_task(const ForwardArgs& a, const Task* tk, T
             dM = inM; dX = inX; dY = inY;
         };
 
+        // What a lane needs when it crosses the separator in front of haplotype hn -- its initial Y value and, for list
+        // tasks, where its bases are and the first of them.  The same for every lane, so it is loaded once per window
+        // and a whole haplotype ahead (fetch_hap below), not by each lane in the middle of its separator step where a
+        // chain of dependent loads would stall the warp 32 times per haplotype.
+        uint32_t hn = 0;                      // index (within the task) of the next separator lane 0 will meet
+        T w_iy = (T)0;
+        uint32_t w_ps = 0, w_len = 0;
+        unsigned w_first = 0;
+        auto fetch_hap = [&](uint32_t n) {
+            w_iy = (T)0; w_len = 0; w_first = 0;
+            if (n < nhaps) {
+                const uint32_t h = hap_at(n);
+                w_iy = inity[h];
+                if constexpr (LIST) { w_ps = a.spos[h]; w_len = a.spos[h + 1] - w_ps; w_first = a.stream[w_ps + 1]; }
+            }
+        };
+
         // Step with every check: separators, fill/drain, stripe carries.
         auto checked_step = [&](int t, unsigned e) -> bool {
             bool repointed = false;
@@ -342,13 +359,18 @@ __device__ __forceinline__ void run_task(const ForwardArgs& a, const Task* tk, T
                     done = nsep == (int)nhaps;
                     T iy = (T)0;
                     if (!done) {
-                        const uint32_t h = hap_at((uint32_t)nsep);
-                        iy = inity[h];
-                        if constexpr (LIST) {
-                            // this separator stands at step t for this lane; from here on the lane reads haplotype h
-                            sp = a.stream + a.spos[h] - t;
-                            repointed = true;
+                        // this separator stands at step t for this lane; from here on a list task's lane reads the
+                        // haplotype that starts here
+                        if (nsep == (int)hn) {
+                            iy = w_iy;
+                            if constexpr (LIST) sp = a.stream + w_ps - t;
+                        } else {
+                            // a haplotype shorter than the warp: this lane crosses a second separator inside the window
+                            const uint32_t h = hap_at((uint32_t)nsep);
+                            iy = inity[h];
+                            if constexpr (LIST) sp = a.stream + a.spos[h] - t;
                         }
+                        repointed = LIST;
                     }
                     ++nsep;
                     #pragma unroll
@@ -379,28 +401,23 @@ __device__ __forceinline__ void run_task(const ForwardArgs& a, const Task* tk, T
         };
 
         int t = 0;
-        uint32_t hn = 0;                      // index (within the task) of the next separator lane 0 will meet
-        int next_sep = 0;                     // step at which lane 0 meets it
+        int next_sep = 0;                     // step at which lane 0 meets separator hn
         unsigned e = sp[0];
+        fetch_hap(0);
         while (t < Tsteps) {
             // checked window: lane l meets the separator at step next_sep + l
             int wend = next_sep + W;
             if (wend > Tsteps) wend = Tsteps;
             if constexpr (LIST) {
-                // what a lane reads right after re-pointing at the separator of haplotype hn: that haplotype's first
-                // base, the same for every lane -- loaded ahead of the window so that its latency is not exposed
-                unsigned first = 0;
-                uint32_t hlen = 0;
-                if (hn < nhaps) { const uint32_t h = hap_at(hn); const uint32_t ps = a.spos[h]; first = a.stream[ps + 1]; hlen = a.spos[h + 1] - ps; }
                 for (; t < wend; ++t) {
                     const unsigned en = sp[t + 1];
-                    // (a haplotype shorter than the warp lets a lane cross a second separator inside this window:
-                    // that one's first base is fetched on the spot)
-                    if (checked_step(t, e)) e = nsep - 1 == (int)hn ? first : sp[t + 1];
+                    // a lane that re-pointed reads the first base of its new haplotype next, not what follows the
+                    // separator in memory
+                    if (checked_step(t, e)) e = nsep - 1 == (int)hn ? w_first : sp[t + 1];
                     else e = en;
                 }
                 ++hn;
-                next_sep = hn <= nhaps ? next_sep + (int)hlen : Tsteps + W;
+                next_sep = hn <= nhaps ? next_sep + (int)w_len : Tsteps + W;
             } else {
                 for (; t < wend; ++t) {
                     const unsigned en = sp[t + 1];
@@ -410,6 +427,7 @@ __device__ __forceinline__ void run_task(const ForwardArgs& a, const Task* tk, T
                 ++hn;
                 next_sep = hn <= nhaps ? (int)(a.spos[hap_first + hn] - s0) : Tsteps + W;
             }
+            fetch_hap(hn);                    // for the next window, a whole haplotype from now
             int send = next_sep < Tsteps ? next_sep : Tsteps;
             // kSteadyUnroll steps per trip: the element loads use one pointer with immediate offsets
             const uint8_t* q = sp + t;
@@ -481,32 +499,63 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, min_ctas<T, K>()) pmm_forwa
 // pair.  `run` follows from the number of failing pairs the float pass counted: enough tasks to keep every resident
 // warp of the double kernel supplied, never more than max_run.  Slot k of the fallback list (out_index[k], hap_list[k],
 // and the double result the kernel writes to dres[k]) belongs to one pair; a task owns consecutive slots.
-__global__ void __launch_bounds__(256) build_fallback_kernel(const FallbackBuild b)
+// Two launches: the scan finds the failing pairs, fills the slots and counts the tasks per cost class; the second
+// writes the tasks longest first (a counting sort on kCostClasses classes), because warps pull tasks in order and the
+// double pass of a typical job is only two or three tasks deep per warp -- its tail is what the order decides
+// (measured on config 2: 0.31 ms longest-first, 0.38 ms in row order).
+struct RowCut { uint32_t run, ntask; };
+
+__device__ __forceinline__ uint32_t fallback_run_cap(const FallbackBuild& b, uint32_t total)
+{
+    return max(1u, min(b.max_run, total / max(1u, b.target_tasks)));
+}
+// reads longer than one stripe of the double kernel carry rows through scratch sized for one haplotype: one pair per task
+__device__ __forceinline__ RowCut cut_row(const FallbackBuild& b, uint32_t read, uint32_t n, uint32_t run_cap)
+{
+    const uint32_t run = b.reads[read].len + 1 > b.single_stripe_rows ? 1u : run_cap;
+    return RowCut{run, (n + run - 1) / run};
+}
+// wavefront steps of task t of a row (haplotype bases + one separator each) and its cost class, 0 = the longest
+__device__ __forceinline__ uint32_t task_class(const FallbackBuild& b, uint32_t slot, uint32_t n, uint32_t ntask, uint32_t t, uint32_t run_cap)
+{
+    const uint32_t k0 = (uint32_t)((uint64_t)n * t / ntask), k1 = (uint32_t)((uint64_t)n * (t + 1) / ntask);
+    uint32_t cost = 0;
+    for (uint32_t k = k0; k < k1; ++k) { const uint32_t h = b.hap_list[slot + k]; cost += b.spos[h + 1] - b.spos[h]; }
+    const uint32_t cmax = run_cap * (b.max_hap_len + 1);
+    return (kCostClasses - 1) - min((uint32_t)(kCostClasses - 1), (uint32_t)((uint64_t)cost * (kCostClasses - 1) / cmax));
+}
+
+__device__ __forceinline__ void row_of(const FallbackBuild& b, uint32_t row, RegionDesc& rg, uint32_t& read, uint32_t& base)
+{
+    uint32_t lo = 0, hi = b.num_region;                       // last region with row_first <= row
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (b.regions[mid].row_first <= row) lo = mid; else hi = mid; }
+    rg = b.regions[lo];
+    const uint32_t r = row - rg.row_first;
+    read = rg.read_first + r; base = rg.out_first + r * rg.nhaps;
+}
+
+__global__ void __launch_bounds__(256) fallback_scan_kernel(const FallbackBuild b)
 {
     const uint32_t total = b.ctrl[0];
     if (total == 0) return;
-    const uint32_t run_cap = max(1u, min(b.max_run, total / max(1u, b.target_tasks)));
+    const uint32_t run_cap = fallback_run_cap(b, total);
     const uint32_t lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
     const unsigned lt = (1u << lane) - 1u;
     for (uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < b.num_rows; row += warps) {
-        uint32_t lo = 0, hi = b.num_region;                       // last region with row_first <= row
-        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (b.regions[mid].row_first <= row) lo = mid; else hi = mid; }
-        const RegionDesc rg = b.regions[lo];
-        const uint32_t r = row - rg.row_first, read = rg.read_first + r, base = rg.out_first + r * rg.nhaps;
+        RegionDesc rg; uint32_t read, base;
+        row_of(b, row, rg, read, base);
         const float* raw = b.raw + base;
         uint32_t n = 0;
         for (uint32_t h0 = 0; h0 < rg.nhaps; h0 += 32) {
             const bool fail = h0 + lane < rg.nhaps && raw[h0 + lane] < b.threshold;      // NaN -> false, like the reference
             n += __popc(__ballot_sync(0xffffffffu, fail));
         }
+        uint32_t slot = 0;
+        if (n && lane == 0) slot = atomicAdd(b.ctrl + 4, n);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        if (slot + n > b.capacity) n = 0;                          // cannot happen: capacity = pairs of the job
+        if (lane == 0) { b.row_slot[2 * row] = slot; b.row_slot[2 * row + 1] = n; }
         if (n == 0) continue;
-        // reads longer than one stripe of the double kernel carry rows through scratch sized for one haplotype
-        const uint32_t run = b.reads[read].len + 1 > b.single_stripe_rows ? 1u : run_cap;
-        const uint32_t ntask = (n + run - 1) / run;
-        uint32_t slot = 0, tfirst = 0;
-        if (lane == 0) { slot = atomicAdd(b.ctrl + 4, n); tfirst = atomicAdd(b.ctrl + 3, ntask); }
-        slot = __shfl_sync(0xffffffffu, slot, 0); tfirst = __shfl_sync(0xffffffffu, tfirst, 0);
-        if (slot + n > b.capacity) continue;                       // cannot happen: capacity = pairs of the job
         uint32_t k = slot;
         for (uint32_t h0 = 0; h0 < rg.nhaps; h0 += 32) {
             const bool fail = h0 + lane < rg.nhaps && raw[h0 + lane] < b.threshold;
@@ -518,13 +567,44 @@ __global__ void __launch_bounds__(256) build_fallback_kernel(const FallbackBuild
             }
             k += __popc(m);
         }
-        for (uint32_t t = lane; t < ntask; t += 32) {
-            const uint32_t k0 = (uint32_t)((uint64_t)n * t / ntask), k1 = (uint32_t)((uint64_t)n * (t + 1) / ntask);
+        __syncwarp();                                              // hap_list of this row is read back below
+        const RowCut rc = cut_row(b, read, n, run_cap);
+        for (uint32_t t = lane; t < rc.ntask; t += 32) atomicAdd(b.ctrl + kCtrlHist + task_class(b, slot, n, rc.ntask, t, run_cap), 1u);
+    }
+}
+
+__global__ void __launch_bounds__(256) fallback_tasks_kernel(const FallbackBuild b)
+{
+    const uint32_t total = b.ctrl[0];
+    if (total == 0) return;
+    __shared__ uint32_t first[kCostClasses];                       // position of each class's first task
+    if (threadIdx.x < 32) {
+        static_assert(kCostClasses == 64, "two classes per lane");
+        const uint32_t c0 = b.ctrl[kCtrlHist + 2 * threadIdx.x], c1 = b.ctrl[kCtrlHist + 2 * threadIdx.x + 1];
+        uint32_t incl = c0 + c1;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if ((int)threadIdx.x >= o) incl += v; }
+        first[2 * threadIdx.x] = incl - c0 - c1; first[2 * threadIdx.x + 1] = incl - c1;
+        if (blockIdx.x == 0 && threadIdx.x == 31) b.ctrl[3] = incl;   // number of tasks, read by the double kernel
+    }
+    __syncthreads();
+    const uint32_t run_cap = fallback_run_cap(b, total);
+    const uint32_t lane = threadIdx.x & 31, warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < b.num_rows; row += warps) {
+        const uint32_t slot = b.row_slot[2 * row], n = b.row_slot[2 * row + 1];
+        if (n == 0) continue;
+        RegionDesc rg; uint32_t read, base;
+        row_of(b, row, rg, read, base);
+        const RowCut rc = cut_row(b, read, n, run_cap);
+        for (uint32_t t = lane; t < rc.ntask; t += 32) {
+            const uint32_t cls = task_class(b, slot, n, rc.ntask, t, run_cap);
+            const uint32_t pos = first[cls] + atomicAdd(b.ctrl + kCtrlClassCursor + cls, 1u);
+            const uint32_t k0 = (uint32_t)((uint64_t)n * t / rc.ntask), k1 = (uint32_t)((uint64_t)n * (t + 1) / rc.ntask);
             Task tk;
             tk.read[0] = read; tk.read[1] = tk.read[2] = tk.read[3] = 0;
             tk.out_base[0] = slot + k0; tk.out_base[1] = tk.out_base[2] = tk.out_base[3] = 0;
             tk.hap_first = slot + k0; tk.nhaps = k1 - k0; tk.nreads = 1; tk.param_off = 0;
-            b.tasks[tfirst + t] = tk;
+            b.tasks[pos] = tk;
         }
     }
 }
@@ -724,18 +804,23 @@ int recheck_f32_ctas_per_sm() { return variant_ctas_per_sm<float, kStripedK, 32,
 // Double re-run: rows per lane K in {4, 5, 6, 8} (W = 32, multi-stripe capable); see pick_f64_rows().
 #define PMM_F64_ROWS(X) X(4) X(5) X(6) X(8)
 
-cudaError_t launch_forward_f64(int K, const ForwardArgs& a, int ctas, cudaStream_t s)
+// striped = false: every read of the job fits one stripe (32 K - 1 bases), the common case; the loop then carries no
+// row through scratch memory (in the striped variant those loads, stores and their branches are a fifth of the
+// steady loop's non-DP instructions).
+cudaError_t launch_forward_f64(int K, bool striped, const ForwardArgs& a, int ctas, cudaStream_t s)
 {
     const FallbackQueue none{};
-#define X(k) if (K == k) return launch_variant<double, k, 32, true, kRetry | kList>(a, none, ctas, s);
+#define X(k) if (K == k) return striped ? launch_variant<double, k, 32, true, kRetry | kList>(a, none, ctas, s) \
+                                        : launch_variant<double, k, 32, false, kRetry | kList>(a, none, ctas, s);
     PMM_F64_ROWS(X)
 #undef X
     return cudaErrorInvalidValue;
 }
 
-int forward_f64_ctas_per_sm(int K)
+int forward_f64_ctas_per_sm(int K, bool striped)
 {
-#define X(k) if (K == k) return variant_ctas_per_sm<double, k, 32, true, kRetry | kList>();
+#define X(k) if (K == k) return striped ? variant_ctas_per_sm<double, k, 32, true, kRetry | kList>() \
+                                        : variant_ctas_per_sm<double, k, 32, false, kRetry | kList>();
     PMM_F64_ROWS(X)
 #undef X
     return 0;
@@ -758,7 +843,8 @@ cudaError_t launch_build_fallback(const FallbackBuild& b, int sm_count, cudaStre
 {
     if (b.num_rows == 0) return cudaSuccess;
     const int ctas = (int)std::min<uint64_t>(((uint64_t)b.num_rows + 7) / 8, (uint64_t)sm_count * 8);
-    build_fallback_kernel<<<ctas, 256, 0, s>>>(b);
+    fallback_scan_kernel<<<ctas, 256, 0, s>>>(b);
+    fallback_tasks_kernel<<<ctas, 256, 0, s>>>(b);
     return cudaGetLastError();
 }
 

@@ -67,9 +67,12 @@ struct FallbackQueue {
     uint32_t* recheck_count;
 };
 
-// Input of build_fallback_kernel: turns the results below the threshold into tasks for the double kernel, the failing
-// haplotypes of one read together.  ctrl: [0] number of failing pairs (counted by the float pass), [3] tasks written,
-// [4] slots handed out.
+// Input of the two fallback-building kernels: they turn the results below the threshold into tasks for the double
+// kernel, the failing haplotypes of one read together, longest tasks first.  ctrl: [0] number of failing pairs (counted
+// by the float pass), [3] tasks written, [4] slots handed out, [kCtrlHist ..) tasks per cost class,
+// [kCtrlClassCursor ..) write cursor of each class.
+constexpr int kCostClasses = 64;
+constexpr int kCtrlHist = 64, kCtrlClassCursor = 128, kCtrlCursors = 256;   // kCtrlCursors + 32 k: work-queue cursor of launch k
 struct FallbackBuild {
     const float*      raw;
     const RegionDesc* regions;
@@ -80,12 +83,15 @@ struct FallbackBuild {
     Task*             tasks;
     uint32_t*         out_index;           // [slot] position of the pair in the job's result
     uint32_t*         hap_list;            // [slot] its haplotype
+    uint32_t*         row_slot;            // [2 row] first slot and number of failing pairs of the row (scan -> tasks)
+    const uint32_t*   spos;                // haplotype stream positions (lengths, for the task cost)
+    uint32_t          max_hap_len;
     uint32_t          capacity;            // slots available (= pairs of the job)
     uint32_t          single_stripe_rows;  // 32 * K of the double kernel: longer reads get single-pair tasks
     uint32_t          target_tasks;        // tasks wanted: haplotypes per task = failing pairs / target_tasks ...
     uint32_t          max_run;             // ... but at most this many
 };
-cudaError_t launch_build_fallback(const FallbackBuild& b, int sm_count, cudaStream_t s);
+cudaError_t launch_build_fallback(const FallbackBuild& b, int sm_count, cudaStream_t s);   // two launches
 
 // Launch helpers implemented in pmm_kernels.cu -------------------------------------------------------------
 
@@ -98,11 +104,11 @@ cudaError_t launch_recheck_f32(const ForwardArgs& a, const FallbackQueue& fq, in
 int recheck_f32_ctas_per_sm();
 // Double re-run of build_fallback_kernel's tasks, K in {4, 5, 6, 8} rows per lane from pick_f64_rows().  Results below
 // a.tiny_threshold are recomputed in the same kernel with x86 flush-to-zero emulated on every product.
-cudaError_t launch_forward_f64(int K, const ForwardArgs& a, int ctas, cudaStream_t s);
+cudaError_t launch_forward_f64(int K, bool striped, const ForwardArgs& a, int ctas, cudaStream_t s);
 int pick_f64_rows(uint32_t max_read_len);
 // CTAs per SM the given variant reaches.
 int forward_f32_ctas_per_sm(int K, int W, bool striped, bool fast = false);
-int forward_f64_ctas_per_sm(int K);
+int forward_f64_ctas_per_sm(int K, bool striped);
 
 cudaError_t launch_build_stream(const uint8_t* hap_blob, const HapDesc* haps, const uint32_t* spos, uint32_t num_hap,
                                 uint8_t* stream, float* inity_f, double* inity_d, float ic_f, double ic_d,

@@ -82,7 +82,7 @@ int  pmm_device_count(void);
  *                       (tuning sweeps, tools/sweep_variants.py); "0,0" gives the choice back to the planner,
  *                       "-1,0" keeps every variant in a launch of its own (no consolidation of rare ones)
  *   "f64_tasks_per_warp", "f64_max_run" = how the double re-run cuts a read's failing haplotypes into tasks: about
- *                       f64_tasks_per_warp tasks per resident warp (default 4), at most f64_max_run haplotypes each (16)
+ *                       f64_tasks_per_warp tasks per resident warp (default 6), at most f64_max_run haplotypes each (6)
  *   "sync"            = "spin" (default): waits poll the stream, lowest latency for one context per core; "block":
  *                       waits sleep on a blocking event (for hosts with fewer cores than waiting threads; the pool takes
  *                       it from the environment variable PMM_POOL_SYNC=block)                                      */

@@ -156,7 +156,7 @@ def test_repeat_launch_is_idempotent(engine):
     assert_bits_equal(a, c, "raw after relaunch"); assert_bits_equal(oa, oc, "log10 after relaunch")
 
 
-@pytest.mark.parametrize("tasks_per_warp,max_run", [(1, 64), (64, 1), (2, 3), (4, 16)])
+@pytest.mark.parametrize("tasks_per_warp,max_run", [(1, 64), (64, 1), (2, 3), (6, 6)])
 def test_double_rerun_task_shapes(engine, checker, golden, tasks_per_warp, max_run):
     """The double re-run groups the failing haplotypes of a read into tasks (a list of haplotypes, not a run of
     neighbours).  However the list is cut -- everything in one task, one pair per task, odd runs -- the results are the
@@ -186,5 +186,5 @@ def test_double_rerun_task_shapes(engine, checker, golden, tasks_per_warp, max_r
         raw, out, m = engine.forward(gb)
         assert_bits_equal(out, log10_bits.view(np.float64), "golden deep_underflow log10")
     finally:
-        engine.set_option("f64_tasks_per_warp", 4)
-        engine.set_option("f64_max_run", 16)
+        engine.set_option("f64_tasks_per_warp", 6)
+        engine.set_option("f64_max_run", 6)
