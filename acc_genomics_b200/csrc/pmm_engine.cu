@@ -27,7 +27,7 @@ using namespace pmm;
 
 namespace {
 
-std::string g_create_error;
+thread_local std::string g_create_error;      // last error of the calls that have no context (pmm_create, pmm_plan_flat), per thread
 
 constexpr size_t kAlign = 256;
 constexpr uint32_t kCtrlWords = kCtrlCursors + 32 * 104;
@@ -71,6 +71,12 @@ struct pmm_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t copy_stream = nullptr; // D2H of the raw floats as soon as the float pass is over, under the double pass
+    cudaEvent_t ev_raw = nullptr;       // ... recorded after that copy; the next launch's float pass waits for it
+    cudaEvent_t ev_h2d = nullptr;       // recorded after the input arena's H2D copy; the next stage waits before repacking
+    bool h2d_pending = false;
+    cudaEvent_t ev_ref = nullptr;       // recorded and waited for in pmm_create: origin of the context's device timeline ...
+    double ref_host_s = 0;              // ... and the host's steady clock at that moment (pmm_get_timeline)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_block = nullptr;     // "sync" = "block": waits sleep on this event instead of spinning on the stream
     bool block_sync = false;
@@ -100,6 +106,8 @@ struct pmm_ctx {
     std::vector<LaunchSeg> segs;
     std::vector<pmm_region_t> regions;
     bool staged = false, launched = false;
+    bool have_raw = false, have_lists = false;   // what of the last launch's results is already in h_out
+    uint32_t spec = 0;                           // fallback entries copied back speculatively by pmm_launch
     pmm_stats_t stats{};
 
     // scratch reused by the one-shot calls
@@ -155,6 +163,9 @@ int stage_common(pmm_ctx* c, uint32_t num_read, const uint32_t* read_off, uint32
 {
     auto t0 = std::chrono::steady_clock::now();
     c->staged = false; c->launched = false;
+    // the pinned input arena is about to be repacked: the previous job's H2D copy out of it must be over
+    // (stage, launch, stage with no fetch in between)
+    if (c->h2d_pending) { PMM_CUDA(c, cudaEventSynchronize(c->ev_h2d)); c->h2d_pending = false; }
     int rc = ensure_tables(c);
     if (rc) return rc;
 
@@ -244,6 +255,8 @@ int stage_common(pmm_ctx* c, uint32_t num_read, const uint32_t* read_off, uint32
 
     cudaStream_t s = c->stream;
     PMM_CUDA(c, cudaMemcpyAsync(c->d_in.p, c->h_in.p, arena, cudaMemcpyHostToDevice, s));
+    PMM_CUDA(c, cudaEventRecord(c->ev_h2d, s));
+    c->h2d_pending = true;
     PMM_CUDA(c, cudaMemsetAsync(c->d_stream.p, 0, kStreamFrontPad, s));
     PMM_CUDA(c, cudaMemsetAsync(static_cast<char*>(c->d_stream.p) + kStreamFrontPad + pos + 1, 0, kStreamTailPad, s));
     char* db = static_cast<char*>(c->d_in.p);
@@ -271,6 +284,7 @@ bool scan_reads(const uint8_t* p, uint64_t n, std::vector<uint32_t>& off, std::v
     int32_t num; memcpy(&num, p, 4);
     if (num < 0) return false;
     uint64_t pos = 4;
+    if ((uint64_t)num > (n - 4) / 4) return false;          // every read takes at least its length word
     off.resize(num); len.resize(num);
     for (int32_t i = 0; i < num; ++i) {
         if (pos + 4 > n) return false;
@@ -287,6 +301,7 @@ bool scan_haps(const uint8_t* p, uint64_t n, std::vector<uint32_t>& off, std::ve
     int32_t num; memcpy(&num, p, 4);
     if (num < 0) return false;
     uint64_t pos = 4;
+    if ((uint64_t)num > (n - 4) / 4) return false;
     off.resize(num); len.resize(num);
     for (int32_t i = 0; i < num; ++i) {
         if (pos + 4 > n) return false;
@@ -428,6 +443,21 @@ void parallel_for(uint64_t n, uint64_t grain, const std::function<void(uint64_t,
 // the same workers for the other engine of this library (sw_engine.cu: staging and CIGAR scatter)
 namespace pmm { void host_parallel_for(uint64_t n, uint64_t grain, const std::function<void(uint64_t, uint64_t)>& f) { parallel_for(n, grain, f); } }
 
+// No exception crosses the C boundary (include/pairhmm_cuda.h): allocation failures of the host-side vectors and
+// anything else thrown below an entry point become a status code and a message.
+template <class F> static int guarded(pmm_ctx* c, F&& f)
+{
+    try { return f(); }
+    catch (const std::bad_alloc&) {
+        if (c) return c->fail(PMM_ERR_INVALID, "out of host memory");
+        g_create_error = "out of host memory"; return PMM_ERR_INVALID;
+    }
+    catch (const std::exception& e) {
+        if (c) return c->fail(PMM_ERR_INVALID, e.what());
+        g_create_error = e.what(); return PMM_ERR_INVALID;
+    }
+}
+
 // =========================================================================================================
 extern "C" {
 
@@ -465,8 +495,17 @@ int pmm_create(int device, pmm_ctx** out)
         g_create_error = cudaGetErrorString(e); delete c; return PMM_ERR_CUDA;
     }
     c->stream = c->own_stream;
+    if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_create_error = cudaGetErrorString(e); cudaStreamDestroy(c->own_stream); delete c; return PMM_ERR_CUDA;
+    }
     for (auto& ev : c->ev) cudaEventCreate(&ev);
     cudaEventCreateWithFlags(&c->ev_block, cudaEventBlockingSync | cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_raw, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_h2d, cudaEventDisableTiming);
+    cudaEventCreate(&c->ev_ref);
+    cudaEventRecord(c->ev_ref, c->own_stream);
+    cudaEventSynchronize(c->ev_ref);
+    c->ref_host_s = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
     *out = c;
     return PMM_OK;
 }
@@ -476,11 +515,16 @@ void pmm_destroy(pmm_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     for (DevBuf* b : {&c->tables, &c->d_in, &c->d_params, &c->d_stream, &c->d_iyf, &c->d_iyd, &c->d_raw, &c->d_fb_tasks, &c->d_fb_idx,
                       &c->d_fb_hap, &c->d_fb_rows, &c->d_tiny_tasks, &c->d_dres, &c->d_ctrl, &c->d_scratch, &c->d_probe}) b->release();
     c->h_in.release(); c->h_out.release();
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     if (c->ev_block) cudaEventDestroy(c->ev_block);
+    if (c->ev_raw) cudaEventDestroy(c->ev_raw);
+    if (c->ev_h2d) cudaEventDestroy(c->ev_h2d);
+    if (c->ev_ref) cudaEventDestroy(c->ev_ref);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -538,7 +582,7 @@ int pmm_set_option(pmm_ctx* c, const char* key, const char* value)
     return c->fail(PMM_ERR_INVALID, "unknown option " + k);
 }
 
-int pmm_stage_flat(pmm_ctx* c, uint32_t num_read, const uint32_t* read_off,
+static int pmm_stage_flat_impl(pmm_ctx* c, uint32_t num_read, const uint32_t* read_off,
                    const uint8_t* bases, const uint8_t* q, const uint8_t* i, const uint8_t* d, const uint8_t* cc,
                    uint32_t num_hap, const uint32_t* hap_off, const uint8_t* hap_bases,
                    uint32_t num_region, const pmm_region_t* regions)
@@ -569,6 +613,8 @@ int pmm_launch(pmm_ctx* c)
     // sort of those tasks, [kCtrlCursors + 32 k] work-queue cursor of launch k
     uint32_t* ctrl = static_cast<uint32_t*>(c->d_ctrl.p);
     uint32_t launches = 0;
+    c->launched = false; c->have_raw = false; c->have_lists = false;
+    PMM_CUDA(c, cudaStreamWaitEvent(s, c->ev_raw, 0));          // the previous launch's copy of d_raw (no-op the first time)
     PMM_CUDA(c, cudaEventRecord(c->ev[0], s));
     PMM_CUDA(c, cudaMemsetAsync(ctrl, 0, sizeof(uint32_t) * kCtrlWords, s));
 
@@ -618,6 +664,14 @@ int pmm_launch(pmm_ctx* c)
         ++launches;
     }
     PMM_CUDA(c, cudaEventRecord(c->ev[1], s));
+    // The raw floats are final now: copy them back on the copy stream while the double pass runs, so that a fetch can
+    // take log10f of them (host libm) under it.
+    {
+        char* ho = static_cast<char*>(c->h_out.p);
+        PMM_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev[1], 0));
+        PMM_CUDA(c, cudaMemcpyAsync(ho + 256, c->d_raw.p, sizeof(float) * c->pairs, cudaMemcpyDeviceToHost, c->copy_stream));
+        PMM_CUDA(c, cudaEventRecord(c->ev_raw, c->copy_stream));
+    }
 
     // ---- double re-run (PairHMMWorker.cpp:176-184): the results below the threshold become tasks, the failing haplotypes
     //      of a read together; their number is only known on the device ------------------------------------------------
@@ -648,6 +702,18 @@ int pmm_launch(pmm_ctx* c)
     PMM_CUDA(c, launch_forward_f64(KD, c->f64_striped, a, f64_ctas, s));
     ++launches;
     PMM_CUDA(c, cudaEventRecord(c->ev[2], s));
+    // The length of the fallback list is only known on the device.  Copy the control words and a first slice of the list
+    // (an eighth of the pairs) back right behind the double pass, so that the common case needs no further round trip;
+    // the rest, if any, follows in the fetch.
+    {
+        char* ho = static_cast<char*>(c->h_out.p);
+        uint32_t* hidx = reinterpret_cast<uint32_t*>(ho + 256 + align_up(sizeof(float) * c->pairs));
+        double* hd = reinterpret_cast<double*>(reinterpret_cast<char*>(hidx) + align_up(sizeof(uint32_t) * c->pairs));
+        c->spec = (uint32_t)std::min<uint64_t>(c->pairs, std::max<uint64_t>(1024, c->pairs / 8));
+        PMM_CUDA(c, cudaMemcpyAsync(ho, c->d_ctrl.p, 12, cudaMemcpyDeviceToHost, s));
+        PMM_CUDA(c, cudaMemcpyAsync(hidx, c->d_fb_idx.p, sizeof(uint32_t) * c->spec, cudaMemcpyDeviceToHost, s));
+        PMM_CUDA(c, cudaMemcpyAsync(hd, c->d_dres.p, sizeof(double) * c->spec, cudaMemcpyDeviceToHost, s));
+    }
     c->stats.kernel_launches = launches;
     c->launched = true;
     return PMM_OK;
@@ -658,6 +724,7 @@ int pmm_sync(pmm_ctx* c)
     if (!c) return PMM_ERR_INVALID;
     cudaSetDevice(c->device);
     PMM_CUDA(c, cudaStreamSynchronize(c->stream));
+    PMM_CUDA(c, cudaStreamSynchronize(c->copy_stream));
     if (c->launched) {
         cudaEventElapsedTime(&c->stats.ms_f32, c->ev[0], c->ev[1]);
         cudaEventElapsedTime(&c->stats.ms_fallback, c->ev[1], c->ev[2]);
@@ -665,49 +732,91 @@ int pmm_sync(pmm_ctx* c)
     return PMM_OK;
 }
 
-// Wait for everything queued on the context's stream.  A caller with one context per core spins (lowest latency); the
-// pool, which runs several contexts per GPU from as many host threads, sleeps on a blocking event so that the waiting
-// threads do not take the cores the packing and log10 work of the other contexts needs.
-static cudaError_t wait_stream(pmm_ctx* c)
+// Wait for everything queued on one of the context's streams.  A caller with one context per core spins (lowest latency);
+// the pool, which runs several contexts per GPU from as many host threads, can sleep on a blocking event so that the
+// waiting threads do not take the cores the packing and log10 work of the other contexts needs.
+static cudaError_t wait_stream(pmm_ctx* c, cudaStream_t st)
 {
-    if (!c->block_sync) return cudaStreamSynchronize(c->stream);
-    cudaError_t e = cudaEventRecord(c->ev_block, c->stream);
+    if (!c->block_sync) return cudaStreamSynchronize(st);
+    cudaError_t e = cudaEventRecord(c->ev_block, st);
     return e != cudaSuccess ? e : cudaEventSynchronize(c->ev_block);
 }
 
-static int fetch_common(pmm_ctx* c, bool want_lists, uint32_t* nfb_out, uint32_t* ntiny_out)
+struct HostOut { uint32_t* ctrl; float* raw; uint32_t* idx; double* dres; };
+static HostOut host_out(const pmm_ctx* c)
+{
+    char* ho = static_cast<char*>(c->h_out.p);
+    HostOut o;
+    o.ctrl = reinterpret_cast<uint32_t*>(ho);                                       // 256 B header
+    o.raw = reinterpret_cast<float*>(ho + 256);
+    o.idx = reinterpret_cast<uint32_t*>(ho + 256 + align_up(sizeof(float) * c->pairs));
+    o.dres = reinterpret_cast<double*>(reinterpret_cast<char*>(o.idx) + align_up(sizeof(uint32_t) * c->pairs));
+    return o;
+}
+
+// The raw floats of the last launch are in h_out (copied by pmm_launch on the copy stream; the double pass may still run).
+static int ensure_raw(pmm_ctx* c)
 {
     if (!c->launched) return c->fail(PMM_ERR_STATE, "fetch before pmm_launch");
+    if (c->have_raw) return PMM_OK;
+    cudaSetDevice(c->device);
+    PMM_CUDA(c, wait_stream(c, c->copy_stream));
+    c->have_raw = true;
+    return PMM_OK;
+}
+
+// The control words and the whole fallback list of the last launch are in h_out.  Every fetch_* of one launch shares
+// these copies: nothing is transferred twice.
+static int ensure_lists(pmm_ctx* c)
+{
+    if (!c->launched) return c->fail(PMM_ERR_STATE, "fetch before pmm_launch");
+    if (c->have_lists) return PMM_OK;
     cudaSetDevice(c->device);
     cudaStream_t s = c->stream;
-    char* ho = static_cast<char*>(c->h_out.p);
-    uint32_t* hctrl = reinterpret_cast<uint32_t*>(ho);                          // 256 B header
-    float* hraw = reinterpret_cast<float*>(ho + 256);
-    uint32_t* hidx = reinterpret_cast<uint32_t*>(ho + 256 + align_up(sizeof(float) * c->pairs));
-    double* hd = reinterpret_cast<double*>(reinterpret_cast<char*>(hidx) + align_up(sizeof(uint32_t) * c->pairs));
-    // The length of the fallback list is only known on the device.  Copy a first slice of it (an eighth of the pairs)
-    // together with the results, so that the common case needs one round trip; the rest, if any, follows.
-    const uint32_t spec = want_lists ? (uint32_t)std::min<uint64_t>(c->pairs, std::max<uint64_t>(1024, c->pairs / 8)) : 0;
-    PMM_CUDA(c, cudaMemcpyAsync(hctrl, c->d_ctrl.p, 12, cudaMemcpyDeviceToHost, s));
-    PMM_CUDA(c, cudaMemcpyAsync(hraw, c->d_raw.p, sizeof(float) * c->pairs, cudaMemcpyDeviceToHost, s));
-    if (spec) {
-        PMM_CUDA(c, cudaMemcpyAsync(hidx, c->d_fb_idx.p, sizeof(uint32_t) * spec, cudaMemcpyDeviceToHost, s));
-        PMM_CUDA(c, cudaMemcpyAsync(hd, c->d_dres.p, sizeof(double) * spec, cudaMemcpyDeviceToHost, s));
-    }
-    PMM_CUDA(c, wait_stream(c));
-    const uint32_t nfb = hctrl[0], ntiny = hctrl[1];
+    const HostOut o = host_out(c);
+    PMM_CUDA(c, wait_stream(c, s));
+    const uint32_t nfb = o.ctrl[0], spec = c->spec;
     uint64_t d2h = 12 + sizeof(float) * c->pairs + (sizeof(uint32_t) + sizeof(double)) * spec;
-    if (want_lists && nfb > spec) {
-        PMM_CUDA(c, cudaMemcpyAsync(hidx + spec, static_cast<uint32_t*>(c->d_fb_idx.p) + spec, sizeof(uint32_t) * (nfb - spec), cudaMemcpyDeviceToHost, s));
-        PMM_CUDA(c, cudaMemcpyAsync(hd + spec, static_cast<double*>(c->d_dres.p) + spec, sizeof(double) * (nfb - spec), cudaMemcpyDeviceToHost, s));
-        PMM_CUDA(c, wait_stream(c));
+    if (nfb > spec) {
+        PMM_CUDA(c, cudaMemcpyAsync(o.idx + spec, static_cast<uint32_t*>(c->d_fb_idx.p) + spec, sizeof(uint32_t) * (nfb - spec), cudaMemcpyDeviceToHost, s));
+        PMM_CUDA(c, cudaMemcpyAsync(o.dres + spec, static_cast<double*>(c->d_dres.p) + spec, sizeof(double) * (nfb - spec), cudaMemcpyDeviceToHost, s));
+        PMM_CUDA(c, wait_stream(c, s));
         d2h += (sizeof(uint32_t) + sizeof(double)) * (nfb - spec);
     }
-    c->stats.fallback_pairs = nfb; c->stats.flush_pairs = ntiny; c->stats.recheck_pairs = hctrl[2]; c->stats.d2h_bytes = d2h;
+    c->stats.fallback_pairs = nfb; c->stats.flush_pairs = o.ctrl[1]; c->stats.recheck_pairs = o.ctrl[2]; c->stats.d2h_bytes = d2h;
     cudaEventElapsedTime(&c->stats.ms_f32, c->ev[0], c->ev[1]);
     cudaEventElapsedTime(&c->stats.ms_fallback, c->ev[1], c->ev[2]);
-    if (nfb_out) *nfb_out = nfb;
-    if (ntiny_out) *ntiny_out = ntiny;
+    c->have_lists = true;
+    return PMM_OK;
+}
+
+// (double)(log10f(v) - log10f(2^120)), float subtraction (PairHMMWorker.cpp:190); host libm on purpose
+static void log10_of_raw(const float* raw, uint64_t n, double* out)
+{
+    const float licf = host_tables().log10_ic_f;
+    parallel_for(n, 1 << 13, [&](uint64_t a, uint64_t b) { for (uint64_t k = a; k < b; ++k) out[k] = (double)(log10f(raw[k]) - licf); });
+}
+// log10(d) - log10(2^1020) for the pairs that fell back (PairHMMWorker.cpp:184)
+static int log10_of_fallback(const uint32_t* fb_index, const double* fb_value, uint64_t n_fb, uint64_t n, double* out)
+{
+    const double licd = host_tables().log10_ic_d;
+    for (uint64_t k = 0; k < n_fb; ++k) {
+        if (fb_index[k] >= n) return PMM_ERR_INVALID;
+        out[fb_index[k]] = log10(fb_value[k]) - licd;
+    }
+    return PMM_OK;
+}
+
+// The final doubles of the last launch: log10f of the raw floats is taken while the double pass is still running.
+static int fetch_log10_common(pmm_ctx* c, double* out, uint32_t* nfb_out)
+{
+    int rc = ensure_raw(c);
+    if (rc) return rc;
+    const HostOut o = host_out(c);
+    log10_of_raw(o.raw, c->pairs, out);
+    if ((rc = ensure_lists(c))) return rc;
+    if (log10_of_fallback(o.idx, o.dres, o.ctrl[0], c->pairs, out) != PMM_OK) return c->fail(PMM_ERR_CUDA, "fallback index out of range");
+    if (nfb_out) *nfb_out = o.ctrl[0];
     return PMM_OK;
 }
 
@@ -716,9 +825,9 @@ int pmm_fetch_raw(pmm_ctx* c, float* out_raw, uint64_t cap)
     if (!c || !out_raw) return PMM_ERR_INVALID;
     if (cap < c->pairs) return c->fail(PMM_ERR_INVALID, "output buffer too small");
     auto t0 = std::chrono::steady_clock::now();
-    int rc = fetch_common(c, false, nullptr, nullptr);
+    int rc = ensure_raw(c);
     if (rc) return rc;
-    memcpy(out_raw, static_cast<char*>(c->h_out.p) + 256, sizeof(float) * c->pairs);
+    memcpy(out_raw, host_out(c).raw, sizeof(float) * c->pairs);
     c->stats.ms_fetch = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return PMM_OK;
 }
@@ -727,29 +836,19 @@ int pmm_fetch_fallback_mask(pmm_ctx* c, uint8_t* mask, uint64_t cap)
 {
     if (!c || !mask) return PMM_ERR_INVALID;
     if (cap < c->pairs) return c->fail(PMM_ERR_INVALID, "mask buffer too small");
-    uint32_t nfb = 0;
-    int rc = fetch_common(c, true, &nfb, nullptr);
+    int rc = ensure_lists(c);
     if (rc) return rc;
     memset(mask, 0, c->pairs);
-    const char* ho = static_cast<const char*>(c->h_out.p);
-    const uint32_t* hidx = reinterpret_cast<const uint32_t*>(ho + 256 + align_up(sizeof(float) * c->pairs));
-    for (uint32_t k = 0; k < nfb; ++k) mask[hidx[k]] = 1;
+    const HostOut o = host_out(c);
+    for (uint32_t k = 0; k < o.ctrl[0]; ++k) mask[o.idx[k]] = 1;
     return PMM_OK;
 }
 
 int pmm_host_finish_log10(const float* raw, uint64_t n, const uint32_t* fb_index, const double* fb_value, uint64_t n_fb, double* out)
 {
     if (!out || (n && !raw) || (n_fb && (!fb_index || !fb_value))) return PMM_ERR_INVALID;
-    const HostTables& t = host_tables();
-    const float licf = t.log10_ic_f; const double licd = t.log10_ic_d;
-    // (double)(log10f(v) - log10f(2^120)), float subtraction (PairHMMWorker.cpp:190); host libm on purpose
-    parallel_for(n, 1 << 13, [&](uint64_t a, uint64_t b) { for (uint64_t k = a; k < b; ++k) out[k] = (double)(log10f(raw[k]) - licf); });
-    // log10(d) - log10(2^1020) for the pairs that fell back (PairHMMWorker.cpp:184)
-    for (uint64_t k = 0; k < n_fb; ++k) {
-        if (fb_index[k] >= n) return PMM_ERR_INVALID;
-        out[fb_index[k]] = log10(fb_value[k]) - licd;
-    }
-    return PMM_OK;
+    log10_of_raw(raw, n, out);
+    return log10_of_fallback(fb_index, fb_value, n_fb, n, out);
 }
 
 int pmm_fetch_log10(pmm_ctx* c, double* out, uint64_t cap, uint64_t* n_fallback)
@@ -758,13 +857,8 @@ int pmm_fetch_log10(pmm_ctx* c, double* out, uint64_t cap, uint64_t* n_fallback)
     if (cap < c->pairs) return c->fail(PMM_ERR_INVALID, "output buffer too small");
     auto t0 = std::chrono::steady_clock::now();
     uint32_t nfb = 0;
-    int rc = fetch_common(c, true, &nfb, nullptr);
+    int rc = fetch_log10_common(c, out, &nfb);
     if (rc) return rc;
-    const char* ho = static_cast<const char*>(c->h_out.p);
-    const float* hraw = reinterpret_cast<const float*>(ho + 256);
-    const uint32_t* hidx = reinterpret_cast<const uint32_t*>(ho + 256 + align_up(sizeof(float) * c->pairs));
-    const double* hd = reinterpret_cast<const double*>(reinterpret_cast<const char*>(hidx) + align_up(sizeof(uint32_t) * c->pairs));
-    pmm_host_finish_log10(hraw, c->pairs, hidx, hd, nfb, out);
     if (n_fallback) *n_fallback = nfb;
     c->stats.ms_fetch = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return PMM_OK;
@@ -776,17 +870,12 @@ int pmm_fetch_log10_indexed(pmm_ctx* c, double* out, uint64_t cap, uint32_t* fb_
     if (cap < c->pairs) return c->fail(PMM_ERR_INVALID, "output buffer too small");
     auto t0 = std::chrono::steady_clock::now();
     uint32_t nfb = 0;
-    int rc = fetch_common(c, true, &nfb, nullptr);
+    int rc = fetch_log10_common(c, out, &nfb);
     if (rc) return rc;
-    const char* ho = static_cast<const char*>(c->h_out.p);
-    const float* hraw = reinterpret_cast<const float*>(ho + 256);
-    const uint32_t* hidx = reinterpret_cast<const uint32_t*>(ho + 256 + align_up(sizeof(float) * c->pairs));
-    const double* hd = reinterpret_cast<const double*>(reinterpret_cast<const char*>(hidx) + align_up(sizeof(uint32_t) * c->pairs));
-    pmm_host_finish_log10(hraw, c->pairs, hidx, hd, nfb, out);
     *n_fallback = nfb;
     if (fb_index) {
         if (fb_cap < nfb) return c->fail(PMM_ERR_INVALID, "fallback index buffer too small");
-        memcpy(fb_index, hidx, sizeof(uint32_t) * nfb);
+        memcpy(fb_index, host_out(c).idx, sizeof(uint32_t) * nfb);
     }
     c->stats.ms_fetch = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return PMM_OK;
@@ -795,21 +884,19 @@ int pmm_fetch_log10_indexed(pmm_ctx* c, double* out, uint64_t cap, uint32_t* fb_
 int pmm_fetch_fallback(pmm_ctx* c, uint32_t* index, double* value, uint64_t cap, uint64_t* count)
 {
     if (!c || !count) return PMM_ERR_INVALID;
-    uint32_t nfb = 0;
-    int rc = fetch_common(c, true, &nfb, nullptr);
+    int rc = ensure_lists(c);
     if (rc) return rc;
+    const HostOut o = host_out(c);
+    const uint32_t nfb = o.ctrl[0];
     *count = nfb;
     if (!index && !value) return PMM_OK;
     if (!index || !value || cap < nfb) return c->fail(PMM_ERR_INVALID, "fallback buffers too small");
-    const char* ho = static_cast<const char*>(c->h_out.p);
-    const uint32_t* hidx = reinterpret_cast<const uint32_t*>(ho + 256 + align_up(sizeof(float) * c->pairs));
-    const double* hd = reinterpret_cast<const double*>(reinterpret_cast<const char*>(hidx) + align_up(sizeof(uint32_t) * c->pairs));
-    memcpy(index, hidx, sizeof(uint32_t) * nfb);
-    memcpy(value, hd, sizeof(double) * nfb);
+    memcpy(index, o.idx, sizeof(uint32_t) * nfb);
+    memcpy(value, o.dres, sizeof(double) * nfb);
     return PMM_OK;
 }
 
-int pmm_stage_serialized(pmm_ctx* c, const void* reads_ser, uint64_t reads_bytes, const void* haps_ser,
+static int pmm_stage_serialized_impl(pmm_ctx* c, const void* reads_ser, uint64_t reads_bytes, const void* haps_ser,
                          uint64_t haps_bytes, int* num_read, int* num_hap)
 {
     if (!c) return PMM_ERR_INVALID;
@@ -829,7 +916,7 @@ int pmm_get_stats(const pmm_ctx* c, pmm_stats_t* out)
     return PMM_OK;
 }
 
-int pmm_forward_raw_serialized(pmm_ctx* c, const void* reads_ser, uint64_t reads_bytes, const void* haps_ser,
+static int pmm_forward_raw_serialized_impl(pmm_ctx* c, const void* reads_ser, uint64_t reads_bytes, const void* haps_ser,
                                uint64_t haps_bytes, float* out_raw, uint64_t cap, int* num_read, int* num_hap)
 {
     if (!c || !out_raw) return PMM_ERR_INVALID;
@@ -844,7 +931,7 @@ int pmm_forward_raw_serialized(pmm_ctx* c, const void* reads_ser, uint64_t reads
     return pmm_fetch_raw(c, out_raw, cap);
 }
 
-int pmm_forward_log10_serialized(pmm_ctx* c, const void* reads_ser, uint64_t reads_bytes, const void* haps_ser,
+static int pmm_forward_log10_serialized_impl(pmm_ctx* c, const void* reads_ser, uint64_t reads_bytes, const void* haps_ser,
                                  uint64_t haps_bytes, double* out, uint64_t cap, int* num_read, int* num_hap,
                                  uint64_t* n_fallback)
 {
@@ -860,7 +947,7 @@ int pmm_forward_log10_serialized(pmm_ctx* c, const void* reads_ser, uint64_t rea
     return pmm_fetch_log10(c, out, cap, n_fallback);
 }
 
-int pmm_forward_log10(pmm_ctx* c, const pmm_read_t* reads, int num_read, const pmm_hap_t* haps, int num_hap,
+static int pmm_forward_log10_impl(pmm_ctx* c, const pmm_read_t* reads, int num_read, const pmm_hap_t* haps, int num_hap,
                       double* out, uint64_t* n_fallback)
 {
     if (!c || !reads || !haps || !out || num_read <= 0 || num_hap <= 0) return c ? c->fail(PMM_ERR_INVALID, "bad arguments") : PMM_ERR_INVALID;
@@ -898,7 +985,67 @@ int pmm_forward_log10(pmm_ctx* c, const pmm_read_t* reads, int num_read, const p
     return pmm_fetch_log10(c, out, (uint64_t)num_read * num_hap, n_fallback);
 }
 
-int pmm_plan_flat(uint32_t num_read, const uint32_t* read_off, uint32_t num_hap, const uint32_t* hap_off,
+// A GKL-shaped batch: one testcase per pair, pointers shared between the pairs of a read and of a haplotype.  Consecutive
+// testcases with the same read are a row; consecutive rows with the same haplotype sequence are a region.  The results
+// of the regions, read-major, are then exactly the testcases' order.
+static int pmm_forward_log10_testcases_impl(pmm_ctx* c, const pmm_testcase_t* tc, uint64_t n, double* out, uint64_t* n_fallback)
+{
+    if (!c) return PMM_ERR_INVALID;
+    if (!tc || !out || !n) return c->fail(PMM_ERR_INVALID, "bad arguments");
+    if (n >= (1ull << 31)) return c->fail(PMM_ERR_INVALID, "more than 2^31 pairs in one batch: split it");
+    cudaSetDevice(c->device);
+    auto same_read = [](const pmm_testcase_t& a, const pmm_testcase_t& b) {
+        return a.rs == b.rs && a.rslen == b.rslen && a.q == b.q && a.i == b.i && a.d == b.d && a.c == b.c; };
+    JobSource src;
+    std::vector<pmm_region_t> regions;
+    std::vector<uint32_t>& roff = c->tmp_roff; std::vector<uint32_t>& hoff = c->tmp_hoff;
+    roff.assign(1, 0); hoff.assign(1, 0);
+    c->tmp_rdesc.clear(); c->tmp_hdesc.clear();
+    uint64_t rbytes = 0, hbytes = 0;
+    uint64_t k = 0, prev_row = 0, prev_len = 0;        // previous row: testcases [prev_row, prev_row + prev_len)
+    bool have_prev = false;
+    while (k < n) {
+        uint64_t e = k + 1;
+        while (e < n && same_read(tc[k], tc[e])) ++e;
+        const pmm_testcase_t& t = tc[k];
+        if (t.rslen <= 0 || !t.rs || !t.q || !t.i || !t.d || !t.c) return c->fail(PMM_ERR_INVALID, "read of length 0 or null track");
+        bool same_haps = have_prev && e - k == prev_len;
+        for (uint64_t z = 0; same_haps && z < e - k; ++z)
+            same_haps = tc[k + z].hap == tc[prev_row + z].hap && tc[k + z].haplen == tc[prev_row + z].haplen;
+        if (!same_haps) {
+            // a new region: its haplotypes are this row's
+            pmm_region_t rg{(uint32_t)c->tmp_rdesc.size(), 0, (uint32_t)c->tmp_hdesc.size(), (uint32_t)(e - k)};
+            for (uint64_t z = k; z < e; ++z) {
+                if (tc[z].haplen <= 0 || !tc[z].hap) return c->fail(PMM_ERR_INVALID, "haplotype of length 0 or null");
+                const uint32_t len = (uint32_t)tc[z].haplen;
+                c->tmp_hdesc.push_back(HapDesc{(uint32_t)hbytes, len});
+                hoff.push_back(hoff.back() + len);
+                src.hap_parts.push_back(BlobPart{reinterpret_cast<const uint8_t*>(tc[z].hap), len});
+                hbytes += len;
+            }
+            regions.push_back(rg);
+        }
+        const uint32_t len = (uint32_t)t.rslen;
+        c->tmp_rdesc.push_back(ReadDesc{(uint32_t)rbytes, len, len});
+        roff.push_back(roff.back() + len);
+        const char* tr[5] = {t.rs, t.q, t.i, t.d, t.c};
+        for (int z = 0; z < 5; ++z) src.read_parts.push_back(BlobPart{reinterpret_cast<const uint8_t*>(tr[z]), len});
+        rbytes += 5ull * len;
+        if (rbytes + hbytes >= (1ull << 31)) return c->fail(PMM_ERR_INVALID, "batch larger than 2 GiB: split it");
+        regions.back().num_read++;
+        prev_row = k; prev_len = e - k; have_prev = true;
+        k = e;
+    }
+    src.rdesc = c->tmp_rdesc.data(); src.hdesc = c->tmp_hdesc.data();
+    int rc = stage_common(c, (uint32_t)c->tmp_rdesc.size(), roff.data(), (uint32_t)c->tmp_hdesc.size(), hoff.data(), src,
+                          (uint32_t)regions.size(), regions.data());
+    if (rc) return rc;
+    if (c->pairs != n) return c->fail(PMM_ERR_INVALID, "internal: testcase grouping lost pairs");
+    if ((rc = pmm_launch(c))) return rc;
+    return pmm_fetch_log10(c, out, n, n_fallback);
+}
+
+static int pmm_plan_flat_impl(uint32_t num_read, const uint32_t* read_off, uint32_t num_hap, const uint32_t* hap_off,
                   uint32_t num_region, const pmm_region_t* regions, int sm_count, int tasks_per_warp,
                   pmm_task_info_t* out, uint64_t capacity, uint64_t* num_tasks)
 {
@@ -917,6 +1064,50 @@ int pmm_plan_flat(uint32_t num_read, const uint32_t* read_off, uint32_t num_hap,
             o.rows_per_lane = (uint32_t)seg.v.K; o.lanes_per_read = (uint32_t)seg.v.W; o.striped = seg.v.striped ? 1u : 0u;
         }
     return PMM_OK;
+}
+
+int pmm_stage_flat(pmm_ctx* c, uint32_t num_read, const uint32_t* read_off,
+                   const uint8_t* bases, const uint8_t* q, const uint8_t* i, const uint8_t* d, const uint8_t* cc,
+                   uint32_t num_hap, const uint32_t* hap_off, const uint8_t* hap_bases,
+                   uint32_t num_region, const pmm_region_t* regions)
+{
+    return guarded(c, [&] { return pmm_stage_flat_impl(c, num_read, read_off, bases, q, i, d, cc, num_hap, hap_off, hap_bases, num_region, regions); });
+}
+
+int pmm_stage_serialized(pmm_ctx* c, const void* reads_ser, uint64_t reads_bytes, const void* haps_ser,
+                         uint64_t haps_bytes, int* num_read, int* num_hap)
+{
+    return guarded(c, [&] { return pmm_stage_serialized_impl(c, reads_ser, reads_bytes, haps_ser, haps_bytes, num_read, num_hap); });
+}
+
+int pmm_forward_raw_serialized(pmm_ctx* c, const void* reads_ser, uint64_t reads_bytes, const void* haps_ser,
+                               uint64_t haps_bytes, float* out_raw, uint64_t cap, int* num_read, int* num_hap)
+{
+    return guarded(c, [&] { return pmm_forward_raw_serialized_impl(c, reads_ser, reads_bytes, haps_ser, haps_bytes, out_raw, cap, num_read, num_hap); });
+}
+
+int pmm_forward_log10_serialized(pmm_ctx* c, const void* reads_ser, uint64_t reads_bytes, const void* haps_ser,
+                                 uint64_t haps_bytes, double* out, uint64_t cap, int* num_read, int* num_hap,
+                                 uint64_t* n_fallback)
+{
+    return guarded(c, [&] { return pmm_forward_log10_serialized_impl(c, reads_ser, reads_bytes, haps_ser, haps_bytes, out, cap, num_read, num_hap, n_fallback); });
+}
+
+int pmm_forward_log10(pmm_ctx* c, const pmm_read_t* reads, int num_read, const pmm_hap_t* haps, int num_hap,
+                      double* out, uint64_t* n_fallback)
+{
+    return guarded(c, [&] { return pmm_forward_log10_impl(c, reads, num_read, haps, num_hap, out, n_fallback); });
+}
+
+int pmm_plan_flat(uint32_t num_read, const uint32_t* read_off, uint32_t num_hap, const uint32_t* hap_off,
+                  uint32_t num_region, const pmm_region_t* regions, int sm_count, int tasks_per_warp,
+                  pmm_task_info_t* out, uint64_t capacity, uint64_t* num_tasks)
+{
+    return guarded(nullptr, [&] { return pmm_plan_flat_impl(num_read, read_off, num_hap, hap_off, num_region, regions, sm_count, tasks_per_warp, out, capacity, num_tasks); });
+}
+int pmm_forward_log10_testcases(pmm_ctx* c, const pmm_testcase_t* tc, uint64_t n, double* out, uint64_t* n_fallback)
+{
+    return guarded(c, [&] { return pmm_forward_log10_testcases_impl(c, tc, n, out, n_fallback); });
 }
 
 int pmm_host_table(int which, void* out, uint64_t capacity_bytes)
@@ -958,6 +1149,21 @@ int pmm_measure_fp32_peak(pmm_ctx* c, double* lane_instr_per_s, double* sm_mhz)
     }
     *lane_instr_per_s = best;
     if (sm_mhz) *sm_mhz = best / ((double)c->sm_count * 128.0) * 1e-6;   // lower bound: assumes 128 lanes/clk/SM fully used
+    return PMM_OK;
+}
+
+int pmm_get_timeline(pmm_ctx* c, pmm_timeline_t* out)
+{
+    if (!c || !out) return PMM_ERR_INVALID;
+    if (!c->launched) return c->fail(PMM_ERR_STATE, "pmm_get_timeline before pmm_launch");
+    cudaSetDevice(c->device);
+    PMM_CUDA(c, cudaEventSynchronize(c->ev[2]));
+    float a = 0, b = 0, d = 0;
+    PMM_CUDA(c, cudaEventElapsedTime(&a, c->ev_ref, c->ev[0]));
+    PMM_CUDA(c, cudaEventElapsedTime(&b, c->ev_ref, c->ev[1]));
+    PMM_CUDA(c, cudaEventElapsedTime(&d, c->ev_ref, c->ev[2]));
+    out->ref_host_s = c->ref_host_s;
+    out->kernels_start_s = a * 1e-3; out->f32_end_s = b * 1e-3; out->kernels_end_s = d * 1e-3;
     return PMM_OK;
 }
 

@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
@@ -63,9 +64,14 @@ struct pmm_pool {
     std::vector<int> devices;
     bool merge = true;                  // feeders merge small waiting jobs into one GPU job
     uint64_t merged_batches = 0;
+    bool tracing = false;               // pmm_pool_trace: one record per GPU job
+    std::vector<pmm_pool_trace_t> trace;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
 };
 
-static std::string g_pool_error;
+static thread_local std::string g_pool_error;      // errors of calls without a pool, and the text pmm_pool_last_error hands out
+
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 // Merging thresholds: a feeder that finds several jobs waiting takes more of them while the merged job stays below
 // kMergeCells cells, kMergeJobs jobs and the engine's per-job limits.  A job that is already large runs alone.
@@ -92,18 +98,22 @@ static uint64_t job_bytes(const Job* j)
     return 5ull * (j->read_off[j->num_read] - j->read_off[0]) + (j->hap_off[j->num_hap] - j->hap_off[0]);
 }
 
-static void run_single(pmm_pool* p, pmm_ctx* c, Job* j)
+struct Stamp { double staged = 0, launched = 0; bool ran = false; };   // host times of one GPU job, for the trace
+
+static void run_single(pmm_pool* p, pmm_ctx* c, Job* j, Stamp& st)
 {
     int rc = pmm_stage_flat(c, j->num_read, j->read_off, j->tr[0], j->tr[1], j->tr[2], j->tr[3], j->tr[4],
                             j->num_hap, j->hap_off, j->hap, j->num_region, j->regions);
+    st.staged = now_s();
     if (rc == PMM_OK) rc = pmm_launch(c);
+    st.launched = now_s(); st.ran = rc == PMM_OK;
     uint64_t nfb = 0;
     if (rc == PMM_OK) rc = pmm_fetch_log10(c, j->out, j->out_capacity, &nfb);
     j->rc = rc; j->n_fallback = nfb;
     if (rc != PMM_OK) j->err = pmm_last_error(c);
 }
 
-static void run_merged(pmm_pool* p, pmm_ctx* c, std::vector<Job*>& batch, MergeBuf& m)
+static void run_merged(pmm_pool* p, pmm_ctx* c, std::vector<Job*>& batch, MergeBuf& m, Stamp& st)
 {
     m.read_off.assign(1, 0); m.hap_off.assign(1, 0); m.regions.clear(); m.out_first.assign(1, 0);
     for (int t = 0; t < 5; ++t) m.tr[t].clear();
@@ -128,9 +138,18 @@ static void run_merged(pmm_pool* p, pmm_ctx* c, std::vector<Job*>& batch, MergeB
     int rc = pmm_stage_flat(c, (uint32_t)m.read_off.size() - 1, m.read_off.data(), m.tr[0].data(), m.tr[1].data(), m.tr[2].data(),
                             m.tr[3].data(), m.tr[4].data(), (uint32_t)m.hap_off.size() - 1, m.hap_off.data(), m.hap.data(),
                             (uint32_t)m.regions.size(), m.regions.data());
+    st.staged = now_s();
     if (rc == PMM_OK) rc = pmm_launch(c);
+    st.launched = now_s(); st.ran = rc == PMM_OK;
     uint64_t nfb = 0;
     if (rc == PMM_OK) rc = pmm_fetch_log10_indexed(c, m.out.data(), total, m.fb_index.data(), total, &nfb);
+    if (rc == PMM_ERR_INVALID) {
+        // One caller's bad job must not fail the others it happened to be merged with (submit-time validation should
+        // have caught it; this is the second line): run every job on its own, so that only the bad one fails.
+        Stamp each;
+        for (Job* j : batch) run_single(p, c, j, each);
+        return;
+    }
     const std::string err = rc == PMM_OK ? std::string() : std::string(pmm_last_error(c));
     for (size_t b = 0; b < batch.size(); ++b) {
         Job* j = batch[b];
@@ -167,10 +186,29 @@ static void feeder_main(pmm_pool* p, size_t slot)
                 cells += n->cells; bytes += job_bytes(n); pairs += job_pairs(n);
             }
         }
-        if (batch.size() == 1) run_single(p, c, batch[0]);
-        else run_merged(p, c, batch, merge);
+        const double t_take = now_s();
+        Stamp st;
+        if (batch.size() == 1) run_single(p, c, batch[0], st);
+        else run_merged(p, c, batch, merge, st);
+        const double t_fetched = now_s();
+        pmm_pool_trace_t rec{};
+        bool have_rec = false;
+        if (p->tracing && st.ran) {           // (read without the lock: a stale value only adds or drops one record)
+            pmm_timeline_t tl;
+            if (pmm_get_timeline(c, &tl) == PMM_OK) {
+                const double origin = std::chrono::duration<double>(p->t0.time_since_epoch()).count();
+                rec.device = p->ctx_device[slot]; rec.context = (int32_t)slot; rec.jobs = (uint32_t)batch.size();
+                for (Job* j : batch) { rec.regions += j->num_region; rec.cells += j->cells; rec.pairs += job_pairs(j); }
+                rec.t_take = t_take - origin; rec.t_staged = st.staged - origin; rec.t_launched = st.launched - origin;
+                rec.t_fetched = t_fetched - origin;
+                rec.d_start = tl.ref_host_s + tl.kernels_start_s - origin; rec.d_f32_end = tl.ref_host_s + tl.f32_end_s - origin;
+                rec.d_end = tl.ref_host_s + tl.kernels_end_s - origin;
+                have_rec = true;
+            }
+        }
         {
             std::lock_guard<std::mutex> lk(p->mu);
+            if (have_rec && p->tracing) p->trace.push_back(rec);
             for (Job* j : batch) {
                 j->device = p->ctx_device[slot]; j->done = true;
                 for (int d = 0; d < p->n_devices; ++d)
@@ -239,7 +277,14 @@ void pmm_pool_destroy(pmm_pool* p)
     delete p;
 }
 
-const char* pmm_pool_last_error(const pmm_pool* p) { return p ? p->err.c_str() : g_pool_error.c_str(); }
+const char* pmm_pool_last_error(const pmm_pool* p)
+{
+    if (p) {                                         // a copy taken under the lock: feeders and submitters write p->err
+        std::lock_guard<std::mutex> lk(const_cast<pmm_pool*>(p)->mu);
+        g_pool_error = p->err;
+    }
+    return g_pool_error.c_str();
+}
 
 int pmm_pool_num_devices(const pmm_pool* p) { return p ? p->n_devices : 0; }
 
@@ -253,6 +298,17 @@ int pmm_pool_submit_flat(pmm_pool* p, uint32_t num_read, const uint32_t* read_of
     if (!read_off || !hap_off || !bases || !q || !i || !d || !c || !hap_bases || !out_log10 || !num_read || !num_hap) {
         std::lock_guard<std::mutex> lk(p->mu);
         p->err = "null or empty input"; return PMM_ERR_INVALID;
+    }
+    // Validate here, so that a malformed job fails its own ticket and never reaches a merged GPU job (whose size
+    // arithmetic trusts ascending offsets): offsets ascend strictly (no read or haplotype of length 0), totals fit.
+    {
+        const char* bad = nullptr;
+        for (uint32_t k = 0; k < num_read && !bad; ++k) if (read_off[k + 1] <= read_off[k]) bad = "read offsets must ascend strictly (no read of length 0)";
+        for (uint32_t k = 0; k < num_hap && !bad; ++k) if (hap_off[k + 1] <= hap_off[k]) bad = "haplotype offsets must ascend strictly (no haplotype of length 0)";
+        if (!bad && 5ull * (read_off[num_read] - read_off[0]) + (hap_off[num_hap] - hap_off[0]) >= (1ull << 31)) bad = "job larger than 2 GiB: split it";
+        if (!bad && regions && num_region)
+            for (uint32_t g = 0; g < num_region && !bad; ++g) if (!regions[g].num_read || !regions[g].num_hap) bad = "empty region";
+        if (bad) { std::lock_guard<std::mutex> lk(p->mu); p->err = bad; return PMM_ERR_INVALID; }
     }
     Job* j = new Job();
     j->num_read = num_read; j->num_hap = num_hap;
@@ -313,6 +369,24 @@ int pmm_pool_set_merge(pmm_pool* p, int on, uint64_t* merged_batches)
     std::lock_guard<std::mutex> lk(p->mu);
     if (on >= 0) p->merge = on != 0;
     if (merged_batches) *merged_batches = p->merged_batches;
+    return PMM_OK;
+}
+
+int pmm_pool_trace(pmm_pool* p, int on)
+{
+    if (!p) return PMM_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(p->mu);
+    if (on) p->trace.clear();
+    p->tracing = on != 0;
+    return PMM_OK;
+}
+
+int pmm_pool_get_trace(pmm_pool* p, pmm_pool_trace_t* out, uint64_t capacity, uint64_t* count)
+{
+    if (!p || !count) return PMM_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(p->mu);
+    *count = p->trace.size();
+    if (out) memcpy(out, p->trace.data(), sizeof(pmm_pool_trace_t) * std::min<uint64_t>(capacity, p->trace.size()));
     return PMM_OK;
 }
 

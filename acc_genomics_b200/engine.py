@@ -20,11 +20,11 @@ PMM_OK, PMM_ERR_INVALID, PMM_ERR_CUDA, PMM_ERR_NO_DEVICE, PMM_ERR_STATE = 0, 1, 
 
 EXPORTS = [
     "pmm_create", "pmm_destroy", "pmm_last_error", "pmm_device_count", "pmm_set_option",
-    "pmm_forward_raw_serialized", "pmm_forward_log10", "pmm_forward_log10_serialized",
+    "pmm_forward_raw_serialized", "pmm_forward_log10", "pmm_forward_log10_serialized", "pmm_forward_log10_testcases",
     "pmm_stage_flat", "pmm_stage_serialized", "pmm_fetch_fallback", "pmm_fetch_log10_indexed", "pmm_launch", "pmm_sync", "pmm_fetch_raw", "pmm_fetch_log10", "pmm_fetch_fallback_mask",
     "pmm_get_stats", "pmm_measure_fp32_peak", "pmm_measure_fp64_peak", "pmm_plan_flat", "pmm_host_table", "pmm_host_finish_log10",
     "pmm_pool_create", "pmm_pool_destroy", "pmm_pool_last_error", "pmm_pool_num_devices", "pmm_pool_submit_flat",
-    "pmm_pool_wait", "pmm_pool_device_load", "pmm_pool_set_merge",
+    "pmm_pool_wait", "pmm_pool_device_load", "pmm_pool_set_merge", "pmm_pool_trace", "pmm_pool_get_trace", "pmm_get_timeline",
 ]
 
 
@@ -39,6 +39,17 @@ class PmmStats(C.Structure):
                 ("ms_fetch", C.c_float), ("recheck_pairs", C.c_uint64)]
 
 
+class PmmTimeline(C.Structure):
+    _fields_ = [("ref_host_s", C.c_double), ("kernels_start_s", C.c_double), ("f32_end_s", C.c_double), ("kernels_end_s", C.c_double)]
+
+
+class PmmPoolTrace(C.Structure):
+    _fields_ = [("device", C.c_int32), ("context", C.c_int32), ("jobs", C.c_uint32), ("regions", C.c_uint32),
+                ("cells", C.c_uint64), ("pairs", C.c_uint64), ("t_take", C.c_double), ("t_staged", C.c_double),
+                ("t_launched", C.c_double), ("t_fetched", C.c_double), ("d_start", C.c_double), ("d_f32_end", C.c_double),
+                ("d_end", C.c_double)]
+
+
 class PmmTaskInfo(C.Structure):
     _fields_ = [("read", C.c_uint32 * 4), ("out_base", C.c_uint32 * 4), ("hap_first", C.c_uint32), ("num_hap", C.c_uint32),
                 ("num_read", C.c_uint32), ("rows_per_lane", C.c_uint32), ("lanes_per_read", C.c_uint32), ("striped", C.c_uint32)]
@@ -51,6 +62,11 @@ class PmmRead(C.Structure):
 
 class PmmHap(C.Structure):
     _fields_ = [("len", C.c_int), ("_b", C.c_char_p)]
+
+
+class PmmTestcase(C.Structure):      # same field order as `testcase`, /root/reference/pairhmm/xlnx/host/host_type.h:69-73
+    _fields_ = [("rslen", C.c_int), ("haplen", C.c_int), ("q", C.c_char_p), ("i", C.c_char_p), ("d", C.c_char_p),
+                ("c", C.c_char_p), ("hap", C.c_char_p), ("rs", C.c_char_p)]
 
 
 class PmmError(RuntimeError):
@@ -79,6 +95,7 @@ def load_library() -> C.CDLL:
         L.pmm_forward_raw_serialized.argtypes = [vp, vp, u64, vp, u64, vp, u64, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.pmm_forward_log10_serialized.argtypes = [vp, vp, u64, vp, u64, vp, u64, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(u64)]
         L.pmm_forward_log10.argtypes = [vp, C.POINTER(PmmRead), C.c_int, C.POINTER(PmmHap), C.c_int, vp, C.POINTER(u64)]
+        L.pmm_forward_log10_testcases.argtypes = [vp, C.POINTER(PmmTestcase), u64, vp, C.POINTER(u64)]
         L.pmm_stage_flat.argtypes = [vp, u32, vp, vp, vp, vp, vp, vp, u32, vp, vp, u32, vp]
         L.pmm_stage_serialized.argtypes = [vp, vp, u64, vp, u64, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.pmm_fetch_fallback.argtypes = [vp, vp, vp, u64, C.POINTER(u64)]
@@ -101,6 +118,9 @@ def load_library() -> C.CDLL:
         L.pmm_pool_wait.argtypes = [vp, u64, C.POINTER(u64), C.POINTER(C.c_int)]
         L.pmm_pool_device_load.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(u64), C.POINTER(u64)]
         L.pmm_pool_set_merge.argtypes = [vp, C.c_int, C.POINTER(u64)]
+        L.pmm_pool_trace.argtypes = [vp, C.c_int]
+        L.pmm_pool_get_trace.argtypes = [vp, vp, u64, C.POINTER(u64)]
+        L.pmm_get_timeline.argtypes = [vp, C.POINTER(PmmTimeline)]
         for n in EXPORTS:
             if n not in ("pmm_destroy", "pmm_last_error", "pmm_pool_destroy", "pmm_pool_last_error"):
                 getattr(L, n).restype = C.c_int
@@ -286,6 +306,18 @@ class PairHMMEngine:
         return out.reshape(b.num_read, b.num_hap), int(nfb.value)
 
 
+    def forward_log10_testcases(self, pairs):
+        """Through pmm_forward_log10_testcases: `pairs` is a list of (read, hap) with read = the 5-tuple of bytes objects
+        (bases, q, i, d, c) and hap = a bytes object; pairs that name the same objects share pointers, like GKL's JNI."""
+        tc = (PmmTestcase * len(pairs))()
+        for k, (r, h) in enumerate(pairs):
+            tc[k] = PmmTestcase(len(r[0]), len(h), r[1], r[2], r[3], r[4], h, r[0])
+        out = np.empty(len(pairs), dtype=np.float64)
+        nfb = C.c_uint64()
+        self._ck(self.lib.pmm_forward_log10_testcases(self.h, tc, len(pairs), out.ctypes.data, C.byref(nfb)))
+        return out, int(nfb.value)
+
+
 class PairHMMPool:
     """The multi-GPU work queue (pmm_pool_*): regions in, log10 likelihoods out, whole regions per GPU, no collective."""
 
@@ -339,6 +371,17 @@ class PairHMMPool:
         n = C.c_uint64()
         self.lib.pmm_pool_set_merge(self.h, -1 if on is None else int(on), C.byref(n))
         return int(n.value)
+
+    def trace(self, on: bool) -> None:
+        """Start (and clear) or stop recording one timeline record per GPU job (pmm_pool_trace)."""
+        self.lib.pmm_pool_trace(self.h, int(on))
+
+    def get_trace(self) -> list:
+        n = C.c_uint64()
+        self.lib.pmm_pool_get_trace(self.h, None, 0, C.byref(n))
+        buf = (PmmPoolTrace * max(1, n.value))()
+        self.lib.pmm_pool_get_trace(self.h, C.cast(buf, C.c_void_p), n.value, C.byref(n))
+        return [{f: getattr(buf[k], f) for f, _ in PmmPoolTrace._fields_} for k in range(n.value)]
 
     def device_load(self):
         res = []

@@ -106,6 +106,16 @@ int  pmm_forward_log10_serialized(pmm_ctx* ctx, const void* reads_ser, uint64_t 
                                   double* out, uint64_t out_capacity, int* num_read, int* num_hap,
                                   uint64_t* n_fallback);
 
+/* The GKL-shaped batch entry (what Intel GKL's JNI computeLikelihoods builds and what the reference's worker converts
+ * its reads and haplotypes into, client/PairHMMWorker.cpp:113-127): one `testcase` per pair, same field order as
+ * xlnx/host/host_type.h:69-73, read-major, the pointers of a read shared by the pairs of its row and the pointers of a
+ * haplotype by the pairs of its column.  out[k] is the final log10 likelihood of tc[k] -- what the per-pair loop
+ * compute_fp_avxs / compute_fp_avxd + log10 of FalconPairHMM::computePairhmmAVX (xlnx/host/FalconPairHMM.cpp:69-95)
+ * returns.  Pairs that share a read (consecutive testcases with the same read pointers) are grouped into regions
+ * internally; any sequence of testcases is accepted, a full cross product is simply the one-region case. */
+typedef struct { int rslen, haplen; const char *q, *i, *d, *c; const char *hap, *rs; } pmm_testcase_t;
+int  pmm_forward_log10_testcases(pmm_ctx* ctx, const pmm_testcase_t* tc, uint64_t n, double* out, uint64_t* n_fallback);
+
 /* ---- staged calls: many regions per job, device-resident between steps -----------------------------------
  * The flat layout is five parallel byte arrays for the reads (bases, base / insertion / deletion /
  * gap-continuation qualities) indexed by read_off[0..num_read], one byte array for the haplotypes indexed by
@@ -139,6 +149,12 @@ int  pmm_fetch_fallback_mask(pmm_ctx* ctx, uint8_t* mask, uint64_t capacity);
 
 int  pmm_get_stats(const pmm_ctx* ctx, pmm_stats_t* out);
 
+/* Where the kernels of the last launched job sit on the device's clock, for idle-time analysis of the work queue:
+ * seconds since the context's reference event (recorded when the context was created), and the host's steady clock
+ * (std::chrono::steady_clock, seconds) at that reference.  Waits for the job's kernels. */
+typedef struct { double ref_host_s, kernels_start_s, f32_end_s, kernels_end_s; } pmm_timeline_t;
+int  pmm_get_timeline(pmm_ctx* ctx, pmm_timeline_t* out);
+
 /* ---- multi-GPU work queue --------------------------------------------------------------------------------
  * Independent read x haplotype regions are partitioned across the GPUs of one box by a host-side queue; nothing is
  * reduced, so there is no collective.  The pool owns contexts_per_device contexts on each of
@@ -167,6 +183,20 @@ int  pmm_pool_wait(pmm_pool* pool, uint64_t ticket, uint64_t* n_fallback, int* d
 int  pmm_pool_set_merge(pmm_pool* pool, int on, uint64_t* merged_batches);
 /* Jobs and cells completed so far by the slot-th device of the pool (0 <= slot < pmm_pool_num_devices). */
 int  pmm_pool_device_load(const pmm_pool* pool, int slot, int* device, uint64_t* jobs, uint64_t* cells);
+/* Timeline of the pool's GPU jobs (one record per job a feeder ran; merged jobs count once), for finding idle time:
+ * host times of the feeder's stages and the device times of the job's kernels, all in seconds since the pool was
+ * created.  pmm_pool_trace(pool, 1) starts recording (and clears), 0 stops; pmm_pool_get_trace copies up to capacity
+ * records and returns how many exist. */
+typedef struct {
+    int32_t  device, context;           /* CUDA device and the pool's context index that ran the job          */
+    uint32_t jobs, regions;             /* submitted jobs merged into this GPU job, regions in it               */
+    uint64_t cells, pairs;
+    double   t_take, t_staged, t_launched, t_fetched;   /* host: job taken from the queue, pmm_stage_flat returned,
+                                                            pmm_launch returned, results delivered                */
+    double   d_start, d_f32_end, d_end; /* device: first kernel starts, float pass ends, double re-run ends      */
+} pmm_pool_trace_t;
+int  pmm_pool_trace(pmm_pool* pool, int on);
+int  pmm_pool_get_trace(pmm_pool* pool, pmm_pool_trace_t* out, uint64_t capacity, uint64_t* count);
 
 /* ---- host-only entry points (no GPU needed) -------------------------------------------------------------
  * pmm_plan_flat: how pmm_stage_flat would cut a job into warp-tasks on a GPU with sm_count SMs.  This is the

@@ -2,16 +2,36 @@
 // (client/PairHMMClient.h:9-21, client/PairHMMClient.cpp:12-17,57-65,75-76, client/PairHMMWorker.cpp:241,251):
 // numbered input and output blocks, start() to run the accelerator, a virtual compute() that Blaze calls when the
 // accelerator is unreachable or its task fails.
+//
+// Beyond the reference's surface: startAsync() / wait().  The reference's worker overlaps its CPU share with the
+// accelerator on a side thread (client/PairHMMWorker.cpp:213-214); here there is no CPU share, and what is worth
+// overlapping is the accelerator's own tiles: startAsync() hands the current input blocks to a helper thread that runs
+// the task, the caller fills the next set of input blocks meanwhile, and wait() delivers the outputs of the oldest
+// task in flight.  At most kMaxInFlight tasks are in flight; each needs a free slot of the accelerator (two per GPU by
+// default), so two tiles of one batch really run side by side: the packing and copies of one under the kernels of the
+// other.
 #pragma once
+#include <deque>
+#include <thread>
+
 #include "PlatformManager.h"
 
 namespace blaze {
 
 class Client {
  public:
+    static constexpr int kMaxInFlight = 2;
+
     Client(const std::string& acc_id, int num_inputs, int num_outputs, int port = 1027)
         : acc_id_(acc_id), port_(port), inputs_(num_inputs), capacity_(num_inputs, 0), outputs_(num_outputs) {}
-    virtual ~Client() {}
+    virtual ~Client()
+    {
+        for (auto& l : lanes_) {
+            { std::lock_guard<std::mutex> lk(l->mu); l->stop = true; }
+            l->cv.notify_all();
+            if (l->th.joinable()) l->th.join();
+        }
+    }
 
     // Allocate (or re-declare the size of) input block idx: num_items x item_length elements of data_width bytes.
     // A block only ever grows; declaring a smaller size keeps the allocation and its contents.
@@ -83,6 +103,44 @@ class Client {
         for (size_t k = 0; k < outputs_.size(); ++k) outputs_[k] = k < out.size() ? out[k] : DataBlock_ptr();
     }
 
+    // Start the accelerator on the current input blocks and return at once.  The blocks travel with the task; the next
+    // createInput()/setInput() fills a fresh (recycled) set.  Throws if kMaxInFlight tasks are already in flight.
+    void startAsync()
+    {
+        if ((int)flights_.size() >= kMaxInFlight) throw invalidParam("Client::startAsync: too many tasks in flight, call wait()");
+        Lane* lane = nullptr;
+        for (auto& l : lanes_) if (!l->busy) { lane = l.get(); break; }
+        if (!lane) {
+            lanes_.emplace_back(new Lane());
+            lane = lanes_.back().get();
+            lane->th = std::thread([lane] { lane->loop(); });
+        }
+        lane->inputs.swap(inputs_);              // the task owns this set now
+        lane->in_capacity.swap(capacity_);
+        lane->outputs.clear(); lane->error.clear(); lane->failed = false;
+        lane->acc_id = acc_id_; lane->port = port_;
+        // the next batch is packed into the set the oldest finished task left behind (grow-only blocks, recycled)
+        inputs_.assign(lane->inputs.size(), DataBlock_ptr()); capacity_.assign(lane->inputs.size(), 0);
+        if (!spare_inputs_.empty()) { inputs_.swap(spare_inputs_.back().first); capacity_.swap(spare_inputs_.back().second); spare_inputs_.pop_back(); }
+        { std::lock_guard<std::mutex> lk(lane->mu); lane->busy = true; lane->go = true; lane->done = false; }
+        lane->cv.notify_all();
+        flights_.push_back(lane);
+    }
+    // Wait for the oldest task in flight; afterwards getOutputPtr() etc. refer to its output blocks.  If that task
+    // failed, the client's own compute() runs (Blaze's contract), like in start().
+    void wait()
+    {
+        if (flights_.empty()) throw invalidParam("Client::wait: nothing in flight");
+        Lane* lane = flights_.front(); flights_.pop_front();
+        { std::unique_lock<std::mutex> lk(lane->mu); lane->cv.wait(lk, [&] { return lane->done; }); lane->busy = false; }
+        spare_inputs_.emplace_back(std::move(lane->inputs), std::move(lane->in_capacity));
+        lane->inputs.clear(); lane->in_capacity.clear();
+        last_error_.clear();
+        if (lane->failed) { last_error_ = lane->error; compute(); return; }
+        for (size_t k = 0; k < outputs_.size(); ++k) outputs_[k] = k < lane->outputs.size() ? lane->outputs[k] : DataBlock_ptr();
+    }
+    int inFlight() const { return (int)flights_.size(); }
+
     virtual void compute() = 0;
 
     const std::string& lastError() const { return last_error_; }
@@ -91,12 +149,41 @@ class Client {
     void check_in(int idx) const { if (idx < 0 || idx >= (int)inputs_.size()) throw invalidParam("input index out of range"); }
     void check_out(int idx) const { if (idx < 0 || idx >= (int)outputs_.size()) throw invalidParam("output index out of range"); }
 
+    // one helper thread and the task it is running
+    struct Lane {
+        std::thread th;
+        std::mutex mu;
+        std::condition_variable cv;
+        bool go = false, done = false, stop = false, busy = false, failed = false;
+        std::string acc_id, error;
+        int port = 0;
+        std::vector<DataBlock_ptr> inputs, outputs;
+        std::vector<size_t> in_capacity;
+        void loop()
+        {
+            for (;;) {
+                { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return go || stop; }); if (stop) return; go = false; }
+                try {
+                    PlatformManager* pm = AppCommManager::lookup(port);
+                    Accelerator* acc = pm ? pm->find(acc_id) : nullptr;
+                    if (!acc) { failed = true; error = "no accelerator manager serves \"" + acc_id + "\""; }
+                    else acc->run(inputs, outputs);
+                } catch (const std::exception& e) { failed = true; error = e.what(); }
+                { std::lock_guard<std::mutex> lk(mu); done = true; }
+                cv.notify_all();
+            }
+        }
+    };
+
     std::string acc_id_;
     int port_;
     std::vector<DataBlock_ptr> inputs_;
     std::vector<size_t> capacity_;
     std::vector<DataBlock_ptr> outputs_;
     std::string last_error_;
+    std::vector<std::unique_ptr<Lane> > lanes_;
+    std::deque<Lane*> flights_;
+    std::vector<std::pair<std::vector<DataBlock_ptr>, std::vector<size_t> > > spare_inputs_;
 };
 
 }  // namespace blaze

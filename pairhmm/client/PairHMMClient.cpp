@@ -2,7 +2,7 @@
 #include "PairHMMClient.h"
 
 PairHMMClient::PairHMMClient()
-    : blaze::Client("PairHMM", 3, 2), num_read_(0), num_hap_(0), num_cell_(0), reads_(nullptr), haps_(nullptr) {}
+    : blaze::Client("PairHMM", 3, 3), num_read_(0), num_hap_(0), num_cell_(0), reads_(nullptr), haps_(nullptr) {}
 
 void PairHMMClient::setup(read_t* reads, int num_read, hap_t* haps, int num_hap) {
   if (!reads || !haps || num_read <= 0 || num_hap <= 0) throw blaze::invalidParam("PairHMMClient::setup: empty batch");

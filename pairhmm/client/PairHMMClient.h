@@ -7,7 +7,7 @@
 // Differences from the reference, all on purpose:
 //   * no batch-size or length caps (the reference sizes its blocks for 2048 x 192-base reads and 128 x 1024-base
 //     haplotypes, client/PairHMMClient.cpp:15-16);
-//   * two output blocks: block 1 is the task's fallback list (see task/cuda/PairHMMTask.h);
+//   * three output blocks: block 1 is the task's fallback list, block 2 its final log10 doubles (task/cuda/PairHMMTask.h);
 //   * compute() -- the CPU path Blaze falls back to -- does not exist in this build.  It throws, carrying the
 //     accelerator's error message: the B200 engine has no CPU fallback by design.
 #ifndef PairHMMCLIENT_H

@@ -2,7 +2,9 @@
 #include "PairHMMWorker.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <stdexcept>
 
 #include "pairhmm_cuda.h"
@@ -27,44 +29,86 @@ void PairHMMWorker::compute() {
   throw std::runtime_error("PairHMMWorker::compute(): this build has no CPU compute path");
 }
 
+// How many tiles (slices of reads) a batch is cut into.  Two tasks are kept in flight (blaze::Client::startAsync), so
+// with three or more tiles the serialization, packing and host-to-device copy of tile k+1 and the copy-back and log10
+// of tile k-1 run under the kernels of tile k; only the first tile's way in and the last tile's way out stay exposed.
+// More tiles shrink that exposed part but cost GPU efficiency (fewer warp-tasks per launch, more launches), and a
+// small batch gains nothing.  PAIRHMM_WORKER_TILES overrides (tuning).
+static int pick_tiles(uint64_t cells, int num_read) {
+  if (const char* e = getenv("PAIRHMM_WORKER_TILES")) { const int v = atoi(e); if (v >= 1) return std::min(v, std::max(1, num_read)); }
+  if (cells < 1200000000ull) return 1;
+  const int t = (int)std::min<uint64_t>(6, std::max<uint64_t>(3, cells / 1200000000ull));
+  return std::min(t, std::max(1, num_read));
+}
+
+void PairHMMWorker::consume(int row, int n) {
+  const float* results = static_cast<const float*>(client_->getOutputPtr(0));
+  memcpy(&output_[(size_t)row * num_hap_], results, sizeof(float) * (size_t)n * num_hap_);
+
+  if (client_->getNumOutputs() > 1 && client_->getOutputSize(1) >= sizeof(uint64_t)) {
+    const char* p = static_cast<const char*>(client_->getOutputPtr(1));
+    uint64_t nfb; memcpy(&nfb, p, sizeof nfb);
+    const uint32_t* idx = reinterpret_cast<const uint32_t*>(p + sizeof(uint64_t));
+    const double* val = reinterpret_cast<const double*>(p + sizeof(uint64_t) + (nfb * sizeof(uint32_t) + 7) / 8 * 8);
+    for (uint64_t k = 0; k < nfb; ++k) {
+      fallback_index_.push_back((uint32_t)((uint64_t)row * num_hap_ + idx[k]));
+      fallback_value_.push_back(val[k]);
+    }
+  }
+  // the task's final doubles (output block 2): nothing is left to do in getOutput()
+  if (client_->getNumOutputs() > 2 && client_->getOutputSize(2) >= sizeof(double) * (size_t)n * num_hap_) {
+    if (final_.empty()) final_.resize((size_t)num_read_ * num_hap_);
+    memcpy(&final_[(size_t)row * num_hap_], client_->getOutputPtr(2), sizeof(double) * (size_t)n * num_hap_);
+    final_rows_ += n;
+  }
+}
+
 void PairHMMWorker::run() {
-  fallback_index_.clear(); fallback_value_.clear();
+  fallback_index_.clear(); fallback_value_.clear(); final_.clear(); final_rows_ = 0;
   ran_ = true;
   if (num_read_ == 0 || num_hap_ == 0) return;
 
-  // Rows (reads) per accelerator call: everything, unless that would cross the engine's job limits.
-  uint64_t hap_bytes = 0, max_read = 1;
-  for (int j = 0; j < num_hap_; ++j) hap_bytes += (uint64_t)host_haps_[j].len + 4;
-  for (int i = 0; i < num_read_; ++i) max_read = std::max<uint64_t>(max_read, (uint64_t)host_reads_[i].len);
+  // Rows (reads) per accelerator call.  Upper bound: the engine's job limits.
+  uint64_t hap_bytes = 0, hap_bases = 0, read_bases = 0, max_read = 1;
+  for (int j = 0; j < num_hap_; ++j) { hap_bytes += (uint64_t)host_haps_[j].len + 4; hap_bases += (uint64_t)host_haps_[j].len; }
+  for (int i = 0; i < num_read_; ++i) { max_read = std::max<uint64_t>(max_read, (uint64_t)host_reads_[i].len); read_bases += (uint64_t)host_reads_[i].len; }
   const uint64_t byte_budget = (1ull << 30);                        // half of the 2 GiB limit, for headroom
   if (hap_bytes >= byte_budget) throw std::runtime_error("PairHMMWorker: haplotypes of one batch exceed 1 GiB");
   uint64_t rows = std::min<uint64_t>((byte_budget - hap_bytes) / (5 * max_read + 4), (1ull << 30) / (uint64_t)num_hap_);
   rows = std::max<uint64_t>(1, std::min<uint64_t>(rows, (uint64_t)num_read_));
+  const int tiles = pick_tiles(read_bases * hap_bases, num_read_);
+  rows = std::min<uint64_t>(rows, ((uint64_t)num_read_ + tiles - 1) / tiles);
 
-  for (int row = 0; row < num_read_; row += (int)rows) {
-    const int n = std::min<int>((int)rows, num_read_ - row);
-    client_->setup(&host_reads_[row], n, host_haps_, num_hap_);
-    client_->start();
-
-    const float* results = static_cast<const float*>(client_->getOutputPtr(0));
-    memcpy(&output_[(size_t)row * num_hap_], results, sizeof(float) * (size_t)n * num_hap_);
-
-    if (client_->getNumOutputs() > 1 && client_->getOutputSize(1) >= sizeof(uint64_t)) {
-      const char* p = static_cast<const char*>(client_->getOutputPtr(1));
-      uint64_t nfb; memcpy(&nfb, p, sizeof nfb);
-      const uint32_t* idx = reinterpret_cast<const uint32_t*>(p + sizeof(uint64_t));
-      const double* val = reinterpret_cast<const double*>(p + sizeof(uint64_t) + (nfb * sizeof(uint32_t) + 7) / 8 * 8);
-      for (uint64_t k = 0; k < nfb; ++k) {
-        fallback_index_.push_back((uint32_t)((uint64_t)row * num_hap_ + idx[k]));
-        fallback_value_.push_back(val[k]);
+  // two tasks in flight: submit tile k+1 (and k+2) before waiting for tile k
+  std::deque<std::pair<int, int> > flying;                          // (first row, rows) of the tasks in flight, oldest first
+  int next = 0;
+  try {
+    while (next < num_read_ || !flying.empty()) {
+      while (next < num_read_ && client_->inFlight() < blaze::Client::kMaxInFlight) {
+        const int n = std::min<int>((int)rows, num_read_ - next);
+        client_->setup(&host_reads_[next], n, host_haps_, num_hap_);
+        client_->startAsync();
+        flying.emplace_back(next, n);
+        next += n;
       }
+      client_->wait();
+      consume(flying.front().first, flying.front().second);
+      flying.pop_front();
     }
+  } catch (...) {
+    // leave nothing in flight behind an exception: the tasks borrow the caller's reads through their input blocks
+    while (client_->inFlight() > 0) { try { client_->wait(); } catch (...) {} }
+    throw;
   }
 }
 
 void PairHMMWorker::getOutput(double* output) {
   if (!ran_) throw std::runtime_error("PairHMMWorker::getOutput() before run()");
   const size_t total = (size_t)num_read_ * (size_t)num_hap_;
+  if (final_rows_ == num_read_ && final_.size() == total) {        // every tile came back with the task's final doubles
+    memcpy(output, final_.data(), sizeof(double) * total);
+    return;
+  }
   // every result below the threshold must have come back with a double re-run (there is no CPU re-run in this build)
   size_t under = 0;
   for (size_t p = 0; p < total; ++p) under += output_[p] < kMinAccepted;

@@ -65,6 +65,14 @@ void PairHMM::compute() {
   const uint64_t pairs = (uint64_t)num_read * (uint64_t)num_hap;
 
   check(pmm_launch(engine_->ctx), "launch");
+  // Output block 2 (extension, see PairHMMTask.h): the final log10 doubles.  Taken first: the engine takes log10f of the
+  // raw floats on the host while the double re-run is still on the GPU, so the task's wait ends with the kernels.
+  // The three fetches below share one set of device-to-host copies.
+  if (conf_flag("emit_log10", true)) {
+    blaze::DataBlock_ptr lg = env->create_block(1, (int)std::min<uint64_t>(pairs, 0x7fffffff), pairs * sizeof(double), 64, blaze::DataBlock::OWNED);
+    check(pmm_fetch_log10(engine_->ctx, reinterpret_cast<double*>(lg->getData()), pairs, nullptr), "fetch log10");
+    setOutput(2, lg);
+  }
   check(pmm_fetch_raw(engine_->ctx, reinterpret_cast<float*>(output_->getData()), output_->getSize() / sizeof(float)), "fetch");
 
   if (conf_flag("emit_fallback", true)) {
@@ -81,7 +89,6 @@ void PairHMM::compute() {
     }
     setOutput(1, fb);
   }
-  (void)pairs;
 }
 
 extern "C" blaze::Task* create() { return new PairHMM(); }

@@ -11,7 +11,10 @@
 // Extension: output block 1 (fallback list).  The GPU also re-runs every pair whose float result is below 1e-28f in
 // double precision (what the reference's client does on the CPU afterwards, client/PairHMMWorker.cpp:176-184); block 1
 // carries `uint64 n`, then n x `uint32 index` (position in block 0), padding to 8 bytes, then n x `double` likelihoods
-// scaled by 2^1020.  A client that only reads block 0 behaves exactly like the reference's.
+// scaled by 2^1020.  Output block 2 (conf "emit_log10", default on): `double[num_read * num_hap]`, the final log10
+// likelihoods of PairHMMWorker::getOutput (client/PairHMMWorker.cpp:157-197) -- log10f of the floats is taken by the
+// host libm while the double re-run is still on the GPU.  A client that only reads block 0 behaves exactly like the
+// reference's.
 #ifndef PAIRHMM_TASK_H
 #define PAIRHMM_TASK_H
 

@@ -188,3 +188,49 @@ def test_double_rerun_task_shapes(engine, checker, golden, tasks_per_warp, max_r
     finally:
         engine.set_option("f64_tasks_per_warp", 6)
         engine.set_option("f64_max_run", 6)
+
+
+def test_gkl_testcase_batch(engine, checker):
+    """pmm_forward_log10_testcases: GKL's per-pair `testcase` array (host_type.h:69-73).  A full cross product, two
+    regions back to back, a ragged tail and a lone pair in one call: out[k] belongs to tc[k]."""
+    a = synth.config(3, seed=51, scale=0.012)[0]            # 12 reads x 64 haplotypes, about half of them fall back
+    b = synth.config(5, seed=52, scale=0.0004)[0].slice_reads(0, 9)
+    want, pairs, nfb_want = [], [], 0
+    for reg in (a, b):
+        reads = [tuple(bytes(x) for x in reg.read(k)) for k in range(reg.num_read)]
+        haps = [bytes(reg.haplotype(k)) for k in range(reg.num_hap)]
+        _, out_r, fb_r = checker.batch(reg, threads=8)
+        for i, r in enumerate(reads):
+            for j, h in enumerate(haps):
+                pairs.append((r, h)); want.append(out_r[i, j]); nfb_want += int(fb_r[i, j])
+    # ragged tail: one read of region a against three of its haplotypes only, then a lone pair of region b
+    reads_a = [tuple(bytes(x) for x in a.read(k)) for k in range(2)]
+    haps_a = [bytes(a.haplotype(k)) for k in (5, 1, 40)]
+    _, out_a, fb_a = checker.batch(a, threads=8)
+    for j, hj in zip((5, 1, 40), haps_a):
+        pairs.append((reads_a[1], hj)); want.append(out_a[1, j]); nfb_want += int(fb_a[1, j])
+    rb = tuple(bytes(x) for x in b.read(3)); hb = bytes(b.haplotype(7))
+    _, out_b, fb_b = checker.batch(b, threads=8)
+    pairs.append((rb, hb)); want.append(out_b[3, 7]); nfb_want += int(fb_b[3, 7])
+    out, nfb = engine.forward_log10_testcases(pairs)
+    assert_bits_equal(out, np.array(want), "testcase batch")
+    assert nfb == nfb_want
+    st = engine.stats()
+    assert st["pairs"] == len(pairs)
+    from acc_genomics_b200.engine import PmmError
+    with pytest.raises(PmmError):
+        engine.forward_log10_testcases([((b"", b"", b"", b"", b""), b"ACGT")])      # read of length 0
+
+
+def test_stage_launch_stage_without_fetch(engine, checker):
+    """The pinned input arena is reused by the next stage: it must wait for the previous job's copy."""
+    b1 = synth.config(2, seed=61, scale=0.05)[0]
+    b2 = synth.config(1, seed=62, scale=0.5)[0]
+    engine.stage([b1]); engine.launch()
+    engine.stage([b2]); engine.launch()
+    out, _ = engine.fetch_log10()
+    assert_bits_equal(out.reshape(b2.num_read, b2.num_hap), checker.batch(b2, threads=8)[1], "second job")
+    # fetches of one launch share their copies: any order, any repetition
+    raw1 = engine.fetch_raw(); m = engine.fetch_fallback_mask(); out2, _ = engine.fetch_log10(); raw2 = engine.fetch_raw()
+    assert_bits_equal(raw1, raw2, "raw twice"); assert_bits_equal(out, out2, "log10 twice")
+    assert np.array_equal(m, raw1 < np.float32(1e-28))

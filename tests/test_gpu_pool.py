@@ -67,3 +67,29 @@ def test_small_jobs_are_merged_and_split_again(built, checker):
         assert_bits_equal(pool.wait(t)[0], out_r.ravel(), "unmerged job")
     assert pool.set_merge() == before
     pool.close()
+
+
+def test_bad_job_fails_alone_and_trace_records_the_rest(built, checker):
+    """A malformed job (a read of length 0) is refused at submit time and never reaches a merged GPU job; the good jobs
+    queued around it run, and the pool's timeline has one record per GPU job with sane times."""
+    from acc_genomics_b200.engine import PairHMMPool, PmmError, concat_regions
+    pool = PairHMMPool(devices=[0], contexts_per_device=2)
+    pool.trace(True)
+    regions = synth.config(5, scale=0.004, seed=21)
+    tickets = [pool.submit(b) for b in regions[:5]]
+    bad = concat_regions([regions[5]])
+    bad["read_off"] = bad["read_off"].copy(); bad["read_off"][3] = bad["read_off"][2]          # read 2 has length 0
+    with pytest.raises(PmmError):
+        pool.submit(None, job=bad)
+    tickets += [pool.submit(b) for b in regions[5:]]
+    for b, t in zip(regions, tickets):
+        out, nfb, _ = pool.wait(t)
+        assert_bits_equal(out, checker.batch(b, threads=8)[1].ravel(), "job next to a refused one")
+    pool.trace(False)
+    tr = pool.get_trace()
+    assert tr and sum(r["jobs"] for r in tr) == len(regions) and sum(r["cells"] for r in tr) == sum(b.num_cells for b in regions)
+    for r in tr:
+        assert r["t_take"] <= r["t_staged"] <= r["t_launched"] <= r["t_fetched"]
+        assert r["d_start"] <= r["d_f32_end"] <= r["d_end"]
+        assert r["t_take"] - 0.05 <= r["d_start"] and r["d_end"] <= r["t_fetched"] + 0.05      # device and host clocks line up
+    pool.close()

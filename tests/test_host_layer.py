@@ -134,6 +134,38 @@ def test_client_threads_share_the_manager(host, golden_folder):
     assert len(used) >= 2
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("tiles", ["1", "3", "7"])
+def test_worker_pipeline_through_the_c_entry(host, checker, tiles, monkeypatch):
+    """PairHMMClient + PairHMMWorker over libPairHMMTask.so behind pairhmm_worker_forward: one tile, three tiles with two
+    tasks in flight, seven ragged tiles -- always the oracle's doubles, bit for bit."""
+    from acc_genomics_b200 import hostlayer
+    monkeypatch.setenv("PAIRHMM_WORKER_TILES", tiles)
+    for b in (synth.config(3, seed=71, scale=0.1)[0], synth.config(5, seed=72, scale=0.0004)[0]):
+        out, nrecal = hostlayer.worker_forward(b)
+        _, want, fb = checker.batch(b, threads=8)
+        assert np.array_equal(out.view(np.int64), np.asarray(want).ravel().view(np.int64))
+        assert nrecal == int(fb.sum())
+
+
+@pytest.mark.gpu
+def test_worker_c_entry_from_several_threads(host, checker):
+    """One PairHMMClient per calling thread, one manager: GATK's threading model."""
+    import threading
+    from acc_genomics_b200 import hostlayer
+    batches = [synth.config(2, seed=80 + k, scale=0.06)[0] for k in range(4)]
+    want = [np.asarray(checker.batch(b, threads=8)[1]).ravel() for b in batches]
+    got = [None] * 4
+
+    def work(k):
+        for _ in range(3):
+            got[k] = hostlayer.worker_forward(hostlayer.WorkerJob(batches[k]))[0].copy()
+    th = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    [t.start() for t in th]; [t.join() for t in th]
+    for k in range(4):
+        assert np.array_equal(got[k].view(np.int64), want[k].view(np.int64)), k
+
+
 # ---- the standalone entry: class FalconPairHMM (reference: pairhmm/xlnx/host/FalconPairHMM.h) ------------------
 def test_falcon_entry_builds_and_refuses_to_run_without_a_gpu(host):
     syms = subprocess.run(["nm", "-DC", "--defined-only", os.path.join(LIB, "libfalcon_pairhmm.so")], capture_output=True, text=True).stdout
