@@ -72,7 +72,8 @@ struct pmm_ctx {
     int sm_count = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t copy_stream = nullptr; // D2H of the raw floats as soon as the float pass is over, under the double pass
-    cudaEvent_t ev_raw = nullptr;       // ... recorded after that copy; the next launch's float pass waits for it
+    cudaStream_t list_stream = nullptr; // D2H of the control words and the fallback list behind the double pass
+    cudaEvent_t ev_raw = nullptr, ev_lists = nullptr;   // recorded after those copies; the next launch waits for them
     cudaEvent_t ev_h2d = nullptr;       // recorded after the input arena's H2D copy; the next stage waits before repacking
     bool h2d_pending = false;
     cudaEvent_t ev_ref = nullptr;       // recorded and waited for in pmm_create: origin of the context's device timeline ...
@@ -495,12 +496,16 @@ int pmm_create(int device, pmm_ctx** out)
         g_create_error = cudaGetErrorString(e); delete c; return PMM_ERR_CUDA;
     }
     c->stream = c->own_stream;
-    if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) {
-        g_create_error = cudaGetErrorString(e); cudaStreamDestroy(c->own_stream); delete c; return PMM_ERR_CUDA;
+    if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&c->list_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_create_error = cudaGetErrorString(e);
+        if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+        cudaStreamDestroy(c->own_stream); delete c; return PMM_ERR_CUDA;
     }
     for (auto& ev : c->ev) cudaEventCreate(&ev);
     cudaEventCreateWithFlags(&c->ev_block, cudaEventBlockingSync | cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_raw, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_lists, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_h2d, cudaEventDisableTiming);
     cudaEventCreate(&c->ev_ref);
     cudaEventRecord(c->ev_ref, c->own_stream);
@@ -516,12 +521,15 @@ void pmm_destroy(pmm_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    if (c->list_stream) cudaStreamSynchronize(c->list_stream);
     for (DevBuf* b : {&c->tables, &c->d_in, &c->d_params, &c->d_stream, &c->d_iyf, &c->d_iyd, &c->d_raw, &c->d_fb_tasks, &c->d_fb_idx,
                       &c->d_fb_hap, &c->d_fb_rows, &c->d_tiny_tasks, &c->d_dres, &c->d_ctrl, &c->d_scratch, &c->d_probe}) b->release();
     c->h_in.release(); c->h_out.release();
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     if (c->ev_block) cudaEventDestroy(c->ev_block);
     if (c->ev_raw) cudaEventDestroy(c->ev_raw);
+    if (c->ev_lists) cudaEventDestroy(c->ev_lists);
+    if (c->list_stream) cudaStreamDestroy(c->list_stream);
     if (c->ev_h2d) cudaEventDestroy(c->ev_h2d);
     if (c->ev_ref) cudaEventDestroy(c->ev_ref);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -614,7 +622,8 @@ int pmm_launch(pmm_ctx* c)
     uint32_t* ctrl = static_cast<uint32_t*>(c->d_ctrl.p);
     uint32_t launches = 0;
     c->launched = false; c->have_raw = false; c->have_lists = false;
-    PMM_CUDA(c, cudaStreamWaitEvent(s, c->ev_raw, 0));          // the previous launch's copy of d_raw (no-op the first time)
+    PMM_CUDA(c, cudaStreamWaitEvent(s, c->ev_raw, 0));          // the previous launch's copies out of d_raw, d_ctrl and the
+    PMM_CUDA(c, cudaStreamWaitEvent(s, c->ev_lists, 0));        // fallback list (no-ops the first time)
     PMM_CUDA(c, cudaEventRecord(c->ev[0], s));
     PMM_CUDA(c, cudaMemsetAsync(ctrl, 0, sizeof(uint32_t) * kCtrlWords, s));
 
@@ -710,9 +719,12 @@ int pmm_launch(pmm_ctx* c)
         uint32_t* hidx = reinterpret_cast<uint32_t*>(ho + 256 + align_up(sizeof(float) * c->pairs));
         double* hd = reinterpret_cast<double*>(reinterpret_cast<char*>(hidx) + align_up(sizeof(uint32_t) * c->pairs));
         c->spec = (uint32_t)std::min<uint64_t>(c->pairs, std::max<uint64_t>(1024, c->pairs / 8));
-        PMM_CUDA(c, cudaMemcpyAsync(ho, c->d_ctrl.p, 12, cudaMemcpyDeviceToHost, s));
-        PMM_CUDA(c, cudaMemcpyAsync(hidx, c->d_fb_idx.p, sizeof(uint32_t) * c->spec, cudaMemcpyDeviceToHost, s));
-        PMM_CUDA(c, cudaMemcpyAsync(hd, c->d_dres.p, sizeof(double) * c->spec, cudaMemcpyDeviceToHost, s));
+        cudaStream_t ls = c->list_stream;                       // not the kernels' stream: the next job need not wait for these
+        PMM_CUDA(c, cudaStreamWaitEvent(ls, c->ev[2], 0));
+        PMM_CUDA(c, cudaMemcpyAsync(ho, c->d_ctrl.p, 12, cudaMemcpyDeviceToHost, ls));
+        PMM_CUDA(c, cudaMemcpyAsync(hidx, c->d_fb_idx.p, sizeof(uint32_t) * c->spec, cudaMemcpyDeviceToHost, ls));
+        PMM_CUDA(c, cudaMemcpyAsync(hd, c->d_dres.p, sizeof(double) * c->spec, cudaMemcpyDeviceToHost, ls));
+        PMM_CUDA(c, cudaEventRecord(c->ev_lists, ls));
     }
     c->stats.kernel_launches = launches;
     c->launched = true;
@@ -725,6 +737,7 @@ int pmm_sync(pmm_ctx* c)
     cudaSetDevice(c->device);
     PMM_CUDA(c, cudaStreamSynchronize(c->stream));
     PMM_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+    PMM_CUDA(c, cudaStreamSynchronize(c->list_stream));
     if (c->launched) {
         cudaEventElapsedTime(&c->stats.ms_f32, c->ev[0], c->ev[1]);
         cudaEventElapsedTime(&c->stats.ms_fallback, c->ev[1], c->ev[2]);
@@ -772,7 +785,7 @@ static int ensure_lists(pmm_ctx* c)
     if (!c->launched) return c->fail(PMM_ERR_STATE, "fetch before pmm_launch");
     if (c->have_lists) return PMM_OK;
     cudaSetDevice(c->device);
-    cudaStream_t s = c->stream;
+    cudaStream_t s = c->list_stream;
     const HostOut o = host_out(c);
     PMM_CUDA(c, wait_stream(c, s));
     const uint32_t nfb = o.ctrl[0], spec = c->spec;
@@ -780,6 +793,7 @@ static int ensure_lists(pmm_ctx* c)
     if (nfb > spec) {
         PMM_CUDA(c, cudaMemcpyAsync(o.idx + spec, static_cast<uint32_t*>(c->d_fb_idx.p) + spec, sizeof(uint32_t) * (nfb - spec), cudaMemcpyDeviceToHost, s));
         PMM_CUDA(c, cudaMemcpyAsync(o.dres + spec, static_cast<double*>(c->d_dres.p) + spec, sizeof(double) * (nfb - spec), cudaMemcpyDeviceToHost, s));
+        PMM_CUDA(c, cudaEventRecord(c->ev_lists, s));
         PMM_CUDA(c, wait_stream(c, s));
         d2h += (sizeof(uint32_t) + sizeof(double)) * (nfb - spec);
     }

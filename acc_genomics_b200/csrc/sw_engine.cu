@@ -170,9 +170,11 @@ int sw_align_batch(sw_ctx* c, uint32_t n_pairs,
         while (k < n_pairs) {
             const uint32_t p = order[k];
             const uint32_t stride = (seq2_len[p] + 31 + 7) / 8;      // words per row: codes are indexed by step (l2 + 31 of them)
-            const uint64_t w = (uint64_t)seq1_len[p] * stride;
+            // blocks of 32 x K rows, every block [word][lane][row of the lane]: rows are padded to whole blocks
+            const uint32_t K = pick_rows_per_lane(seq1_len[p]);
+            const uint64_t w = (uint64_t)((seq1_len[p] + 32 * K - 1) / (32 * K)) * 32 * K * stride;
             if (k > first && words + w > c->bt_budget_words) break;
-            hp[k] = PairDesc{seq1_start[p], seq1_len[p], seq2_start[p], seq2_len[p], words, stride, p, pick_rows_per_lane(seq1_len[p]), 0u};
+            hp[k] = PairDesc{seq1_start[p], seq1_len[p], seq2_start[p], seq2_len[p], words, stride, p, K, 0u};
             words += w; ++k;
         }
         chunks.emplace_back(first, k);

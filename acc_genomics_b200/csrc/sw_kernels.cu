@@ -12,8 +12,10 @@
 //   * The last row of a block is carried to the next block through a per-warp row in shared memory (written by lane 31,
 //     read 31 steps earlier by lane 0 -- one buffer is enough).  The alternate sequence, the last row / last column of H
 //     (for the end-cell search) and the traceback tile live in shared memory too.
-//   * Backtrack codes are packed 8 cells per 32-bit word per row (row-major), so a lane stores one word every 8 steps
-//     and the traceback can fetch a 32-row x 64-column tile with one 32-byte segment per lane.
+//   * Backtrack codes are packed 8 cells per 32-bit word per row; a lane completes one word per row every 8 steps.  The
+//     words of a block of rows are laid out [word][lane][row of the lane], so the K words a lane stores at such a step
+//     are contiguous and the warp's stores cover whole sectors; the traceback fetches a 32-row x 64-column tile as nine
+//     words per row, the rows of one lane next to each other.
 //   * The traceback is a pointer chase, but most of it is runs of diagonal moves: all lanes fetch a tile of codes, lane r
 //     looks r cells down the diagonal and a ballot finds how far the run goes (one iteration per run or gap cell).
 #include "sw_kernels.cuh"
@@ -112,8 +114,10 @@ __device__ __forceinline__ void fill_matrix(const FillCtx& c)
                 E[k] = kLowInit;
                 acc[k] = 0;
             }
-            uint32_t* const brow0 = c.B + (size_t)(ifirst - 1) * c.stride;   // backtrack row of the lane's first row
-            const int nvalid = min(K, nrow - ifirst + 1);               // rows of this lane that exist (<= 0: none)
+            // backtrack words of this block: [word][lane][row of the lane] -- the K words a lane completes at one step are
+            // contiguous and the warp's 32 K words are one contiguous run, so every store fills whole 32-byte sectors
+            // (row-major rows of words put each 4-byte store into a sector of its own: 2.5 x the bytes in DRAM writes)
+            uint32_t* const bblk = c.B + ((size_t)blk * c.stride * 32 + lane) * K;
             int prev_up = (ifirst - 1 == 0) ? 0 : (indel ? open + (ifirst - 2) * extend : 0);   // H[ifirst-1][0]
             int lastF = kLowInit;
             // the lane and row that hold the matrix's last row (for the end-cell search); -1 if not in this block
@@ -174,9 +178,10 @@ __device__ __forceinline__ void fill_matrix(const FillCtx& c)
                 if (lane == 31) { sm.carryH[j] = Hrow[K - 1]; sm.carryF[j] = lastF; }
             };
             auto store_words = [&](const int word, const int shift) {
+                static_assert(K % 2 == 0, "rows per lane are stored as 8-byte pairs");
+                uint2* dst = reinterpret_cast<uint2*>(bblk + (size_t)word * 32 * K);     // rows past nrow: padding, allocated
                 #pragma unroll
-                for (int k = 0; k < K; ++k)
-                    if (k < nvalid) brow0[(size_t)k * c.stride + word] = acc[k] << shift;
+                for (int k = 0; k < K; k += 2) dst[k >> 1] = make_uint2(acc[k] << shift, acc[k + 1] << shift);
             };
 
             // Backtrack words are indexed by step, not by column: the code of row i, column j sits in word t >> 3 of the
@@ -258,6 +263,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 3) sw_align_kernel(const Ar
         const int K = (int)pd.rows_per_lane;
         const uint32_t kdiv = ((1u << 20) + K - 1) / K;                 // (x * kdiv) >> 20 == x / K for x < 4096
         auto lane_of_row = [&](int row) { return (int)((((uint32_t)(row - 1) * kdiv) >> 20) & 31u); };
+        // word w of a row in the [block][word][lane][row of the lane] layout of the backtrack matrix
+        auto row_base = [&](int row) {
+            const uint32_t q = ((uint32_t)(row - 1) * kdiv) >> 20;          // (row - 1) / K
+            return B + ((size_t)(q >> 5) * stride * 32 + (q & 31u)) * K + ((uint32_t)(row - 1) - q * K);
+        };
 
         __syncwarp();
         for (int x = lane; x < ncol; x += 32) sm.alt[x] = s2[x];
@@ -342,11 +352,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 3) sw_align_kernel(const Ar
                 // (lane of the row) % 8 codes, give the eight column-indexed words cw0 .. cw0 + 7
                 const int row = ai - lane;
                 const int lr = row >= 1 ? lane_of_row(row) : 0;
-                const uint32_t* src = B + (size_t)max(row - 1, 0) * stride;
+                const uint32_t* src = row_base(max(row, 1));
                 const int w0 = cw0 + (lr >> 3), sh = 4 * (lr & 7);
                 uint32_t raw[9];
                 #pragma unroll
-                for (int w = 0; w < 9; ++w) raw[w] = (row >= 1 && (uint32_t)(w0 + w) < stride) ? __ldcg(src + w0 + w) : 0u;
+                for (int w = 0; w < 9; ++w) raw[w] = (row >= 1 && (uint32_t)(w0 + w) < stride) ? __ldcg(src + (size_t)(w0 + w) * 32 * K) : 0u;
                 #pragma unroll
                 for (int w = 0; w < 8; ++w) sm.tile[w * 32 + lane] = __funnelshift_l(raw[w + 1], raw[w], sh);
             }

@@ -2,7 +2,9 @@
 //
 // Layout in HBM for one chunk of pairs:
 //   seq1 / seq2 blobs   bytes; pair p is seq1[s1 .. s1+l1) (reference, matrix rows) against seq2[s2 .. s2+l2) (alternate, columns)
-//   backtrack           per pair l1 rows of `bt_stride` 32-bit words, 8 cells per word, 4 bits per cell: bit 3 "the insertion
+//   backtrack           per pair ceil(l1 / (32 K)) blocks of 32 K rows (K = rows_per_lane), every row `bt_stride` 32-bit words,
+//                       laid out [block][word][lane][row of the lane] so that the fill's stores cover whole sectors;
+//                       8 cells per word, 4 bits per cell: bit 3 "the insertion
 //                       into this cell opens a gap" (else it extends one), bit 2 the same for the deletion, bit 1 "the
 //                       insertion beats the diagonal", bit 0 "the deletion beats both" -- the information of the reference's
 //                       codes (/root/reference/htc-sw/intel_avx/smithwaterman_common.h:18-22) as raw comparison results.

@@ -261,8 +261,10 @@ class AppCommManager {
     }
 
  private:
-    static std::map<int, PlatformManager*>& registry() { static std::map<int, PlatformManager*> r; return r; }
-    static std::mutex& registry_mu() { static std::mutex m; return m; }
+    // Never destroyed: endpoints may be withdrawn from static destructors of the host program, after function-local statics
+    // of this header would already be gone.
+    static std::map<int, PlatformManager*>& registry() { static std::map<int, PlatformManager*>* r = new std::map<int, PlatformManager*>(); return *r; }
+    static std::mutex& registry_mu() { static std::mutex* m = new std::mutex(); return *m; }
     int port_;
 };
 

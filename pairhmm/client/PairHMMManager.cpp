@@ -9,13 +9,22 @@
 #include "pairhmm_cuda.h"
 
 namespace {
-std::unique_ptr<blaze::PlatformManager> g_pm;
-std::unique_ptr<blaze::AppCommManager> g_comm;
+// Plain pointers on purpose: the default manager lives until pairhmm_shutdown_manager() or the end of the process.  It is
+// not torn down from a static destructor -- by then the CUDA runtime and the statics of other libraries may be gone.
+struct Holder { blaze::PlatformManager* get() const { return p; } blaze::PlatformManager* p = nullptr; explicit operator bool() const { return p != nullptr; } };
+Holder g_pm;
+blaze::AppCommManager* g_comm = nullptr;
 std::mutex g_mu;
 
+void drop() {
+  delete g_comm; g_comm = nullptr;
+  delete g_pm.p; g_pm.p = nullptr;
+}
+
 void publish(blaze::PlatformManager* pm) {
-  g_pm.reset(pm);
-  g_comm.reset(new blaze::AppCommManager(pm, "127.0.0.1", 1027));
+  drop();
+  g_pm.p = pm;
+  g_comm = new blaze::AppCommManager(pm, "127.0.0.1", 1027);
 }
 }  // namespace
 
@@ -38,7 +47,11 @@ blaze::PlatformManager* pairhmm_default_manager(const char* plugin_path, int slo
   const int n = pmm_device_count();
   if (n <= 0) throw std::runtime_error("no CUDA device visible: the PairHMM accelerator has no CPU fallback");
   std::map<std::string, std::string> param;
-  param["devices"] = "all";
+  // $PAIRHMM_DEVICES ("0,1", default every visible GPU) and $PAIRHMM_SLOTS (tasks in flight per GPU) let a host program
+  // that runs one process per GPU (bench.py under torchrun) keep each process on its own device
+  const char* devs = getenv("PAIRHMM_DEVICES");
+  param["devices"] = devs && *devs ? devs : "all";
+  if (const char* e = getenv("PAIRHMM_SLOTS")) { const int v = atoi(e); if (v >= 1 && v <= 8) slots_per_device = v; }
   param["slots_per_device"] = std::to_string(slots_per_device);
   std::unique_ptr<blaze::PlatformManager> pm(new blaze::PlatformManager());
   pm->registerAcc("PairHMM", plugin_path && *plugin_path ? plugin_path : pairhmm_default_plugin_path(), param, n);
@@ -63,6 +76,5 @@ blaze::PlatformManager* pairhmm_manager_from_conf(const std::string& conf_path) 
 
 void pairhmm_shutdown_manager() {
   std::lock_guard<std::mutex> lk(g_mu);
-  g_comm.reset();
-  g_pm.reset();
+  drop();
 }
