@@ -550,6 +550,26 @@ int pmm_set_option(pmm_ctx* c, const char* key, const char* value)
         else c->stream = reinterpret_cast<cudaStream_t>(strtoull(value, nullptr, 0));
         return PMM_OK;
     }
+    if (k == "priority") {
+        // rank of this context's kernels among the contexts sharing the GPU: 0 = first in line (highest CUDA stream
+        // priority), larger = later.  The kernels are persistent (one launch fills the GPU), so the order only decides
+        // whose blocks take the slots another kernel's tail frees -- e.g. the double re-run of tile k before the float
+        // pass of tile k+2 when a batch is cut into tiles that run on several contexts (pairhmm/client/PairHMMWorker).
+        const int rank = atoi(value);
+        if (rank < 0 || rank > 64) return c->fail(PMM_ERR_INVALID, "priority rank out of range");
+        cudaSetDevice(c->device);
+        int least = 0, greatest = 0;
+        PMM_CUDA(c, cudaDeviceGetStreamPriorityRange(&least, &greatest));        // numerically: greatest <= least
+        const int prio = std::min(least, greatest + rank);
+        cudaStream_t ns = nullptr;
+        PMM_CUDA(c, cudaStreamCreateWithPriority(&ns, cudaStreamNonBlocking, prio));
+        PMM_CUDA(c, cudaStreamSynchronize(c->own_stream));
+        const bool was_own = c->stream == c->own_stream;
+        cudaStreamDestroy(c->own_stream);
+        c->own_stream = ns;
+        if (was_own) c->stream = ns;
+        return PMM_OK;
+    }
     if (k == "tasks_per_warp") {
         const int v = atoi(value);
         if (v < 1 || v > 64) return c->fail(PMM_ERR_INVALID, "tasks_per_warp out of range");

@@ -370,7 +370,7 @@ def measure_plugin(batch, steps: int, local: int, threads: int):
     with its own client and its own copy of the batch."""
     from acc_genomics_b200 import hostlayer
     os.environ.setdefault("PAIRHMM_DEVICES", str(local))
-    os.environ.setdefault("PAIRHMM_SLOTS", "3")
+    os.environ.setdefault("PAIRHMM_SLOTS", "4")
     jobs = [hostlayer.WorkerJob(batch) for _ in range(threads)]
     for j in jobs:
         hostlayer.worker_forward(j)
@@ -685,7 +685,7 @@ def _main(args, real_stdout):
         if plugin:
             line["e2e"].update({
                 "plugin_value": job_cells / p1_s * 1e-9, "plugin_ms_per_step": p1_s * 1e3,
-                "plugin_path": "pairhmm_worker_forward -> PairHMMClient::setup (serialize) + PairHMMWorker::run (tiles, two tasks in flight on "
+                "plugin_path": "pairhmm_worker_forward -> PairHMMClient::setup (serialize) + PairHMMWorker::run (tiles, all in flight on their own slots of "
                                "libPairHMMTask.so: prepare = stage, compute = launch + fetch) + getOutput; one caller thread, one batch at a time",
                 "plugin_threads_value": job_cells / p3_s * 1e-9, "plugin_threads": 3, "plugin_bit_equal": plugin["same"]})
         if fast:

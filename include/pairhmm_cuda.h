@@ -70,6 +70,9 @@ int  pmm_device_count(void);
 /* Options (strings, like the task's get_conf(key, value), task/xlnx/PairHMMTask.h:73-77):
  *   "stream"          = value of a cudaStream_t (decimal or 0x..) to run on, "default" for the legacy default
  *                       stream, "own" for the context's own non-blocking stream (the initial setting)
+ *   "priority"        = rank of this context among the contexts that share its GPU, 0 = first in line (the highest CUDA
+ *                       stream priority), larger = later; replaces the context's own stream.  Decides whose thread blocks take
+ *                       the SM slots another context's kernel frees at its tail
  *   "tasks_per_warp"  = target queue depth per resident warp used when cutting regions into warp-tasks
  *   "mode"            = "exact" (default): every multiply and add of the float pass is rounded on its own, results are
  *                       bit-identical to the reference's AVX code.  "fast": the float cell update is contracted to

@@ -7,10 +7,11 @@
 // accelerator on a side thread (client/PairHMMWorker.cpp:213-214); here there is no CPU share, and what is worth
 // overlapping is the accelerator's own tiles: startAsync() hands the current input blocks to a helper thread that runs
 // the task, the caller fills the next set of input blocks meanwhile, and wait() delivers the outputs of the oldest
-// task in flight.  At most kMaxInFlight tasks are in flight; each needs a free slot of the accelerator (two per GPU by
-// default), so two tiles of one batch really run side by side: the packing and copies of one under the kernels of the
-// other.
+// task in flight.  At most kMaxInFlight tasks are in flight; each needs a free slot of the accelerator (four per GPU by
+// default), so the tiles of one batch really run side by side: the packing and copies of one under the kernels of the
+// others.
 #pragma once
+#include <atomic>
 #include <deque>
 #include <thread>
 
@@ -20,7 +21,7 @@ namespace blaze {
 
 class Client {
  public:
-    static constexpr int kMaxInFlight = 2;
+    static constexpr int kMaxInFlight = 4;
 
     Client(const std::string& acc_id, int num_inputs, int num_outputs, int port = 1027)
         : acc_id_(acc_id), port_(port), inputs_(num_inputs), capacity_(num_inputs, 0), outputs_(num_outputs) {}
@@ -122,7 +123,9 @@ class Client {
         // the next batch is packed into the set the oldest finished task left behind (grow-only blocks, recycled)
         inputs_.assign(lane->inputs.size(), DataBlock_ptr()); capacity_.assign(lane->inputs.size(), 0);
         if (!spare_inputs_.empty()) { inputs_.swap(spare_inputs_.back().first); capacity_.swap(spare_inputs_.back().second); spare_inputs_.pop_back(); }
+        lane->done_flag.store(false, std::memory_order_relaxed);
         { std::lock_guard<std::mutex> lk(lane->mu); lane->busy = true; lane->go = true; lane->done = false; }
+        lane->flag.store(true, std::memory_order_release);
         lane->cv.notify_all();
         flights_.push_back(lane);
     }
@@ -132,6 +135,7 @@ class Client {
     {
         if (flights_.empty()) throw invalidParam("Client::wait: nothing in flight");
         Lane* lane = flights_.front(); flights_.pop_front();
+        for (int spin = 0; spin < 200000 && !lane->done_flag.load(std::memory_order_acquire); ++spin) Lane::cpu_relax();
         { std::unique_lock<std::mutex> lk(lane->mu); lane->cv.wait(lk, [&] { return lane->done; }); lane->busy = false; }
         spare_inputs_.emplace_back(std::move(lane->inputs), std::move(lane->in_capacity));
         lane->inputs.clear(); lane->in_capacity.clear();
@@ -155,6 +159,13 @@ class Client {
         std::mutex mu;
         std::condition_variable cv;
         bool go = false, done = false, stop = false, busy = false, failed = false;
+        std::atomic<bool> flag{false}, done_flag{false};   // lock-free mirrors of go / done for the short polls
+        static void cpu_relax()
+        {
+#if defined(__x86_64__) || defined(__i386__)
+            __builtin_ia32_pause();
+#endif
+        }
         std::string acc_id, error;
         int port = 0;
         std::vector<DataBlock_ptr> inputs, outputs;
@@ -162,7 +173,10 @@ class Client {
         void loop()
         {
             for (;;) {
-                { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return go || stop; }); if (stop) return; go = false; }
+                // A tile follows the previous one within microseconds while a batch is in flight: poll briefly before
+                // sleeping, a condition-variable wake-up costs more than a tile's host work
+                for (int spin = 0; spin < 20000 && !flag.load(std::memory_order_acquire); ++spin) cpu_relax();
+                { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return go || stop; }); if (stop) return; go = false; flag.store(false, std::memory_order_relaxed); }
                 try {
                     PlatformManager* pm = AppCommManager::lookup(port);
                     Accelerator* acc = pm ? pm->find(acc_id) : nullptr;
@@ -170,6 +184,7 @@ class Client {
                     else acc->run(inputs, outputs);
                 } catch (const std::exception& e) { failed = true; error = e.what(); }
                 { std::lock_guard<std::mutex> lk(mu); done = true; }
+                done_flag.store(true, std::memory_order_release);
                 cv.notify_all();
             }
         }

@@ -127,13 +127,14 @@ class Accelerator {
         for (auto& kv : param) conf_->write_conf(kv.first, kv.second);
         if (devices.empty()) throw invalidParam("accelerator " + id + " has no device");
         for (int s = 0; s < std::max(1, slots_per_device); ++s)
-            for (int d : devices) { envs_.emplace_back(new CudaEnv(d)); busy_.push_back(false); }
+            for (int d : devices) { envs_.emplace_back(new CudaEnv(d, s)); busy_.push_back(false); }
         load_.assign(envs_.size(), 0);
     }
     ~Accelerator()
     {
         envs_.clear();                         // scratch objects reference code of the plugin: drop them first
-        if (handle_) dlclose(handle_);
+        // The plugin stays loaded: output blocks it created (their deleters are its code) may outlive the manager in the
+        // hands of clients.
     }
     const std::string& id() const { return id_; }
     int numEnvs() const { return (int)envs_.size(); }

@@ -39,10 +39,12 @@ class TaskEnv {
 
 class CudaEnv : public TaskEnv {
  public:
-    explicit CudaEnv(int device) : device_(device) {}
+    explicit CudaEnv(int device, int slot = 0) : device_(device), slot_(slot) {}
     int getDevice() const { return device_; }
+    // which of the device's task slots this environment is (0 = the one a free accelerator hands out first)
+    int getSlot() const { return slot_; }
  private:
-    int device_;
+    int device_, slot_;
 };
 
 }  // namespace blaze

@@ -9,7 +9,7 @@
 
 #include "blaze/PlatformManager.h"
 
-blaze::PlatformManager* pairhmm_default_manager(const char* plugin_path = nullptr, int slots_per_device = 2);
+blaze::PlatformManager* pairhmm_default_manager(const char* plugin_path = nullptr, int slots_per_device = 4);
 blaze::PlatformManager* pairhmm_manager_from_conf(const std::string& conf_path);
 void pairhmm_shutdown_manager();
 std::string pairhmm_default_plugin_path();

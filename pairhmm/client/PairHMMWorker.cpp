@@ -2,6 +2,8 @@
 #include "PairHMMWorker.h"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <deque>
@@ -29,15 +31,17 @@ void PairHMMWorker::compute() {
   throw std::runtime_error("PairHMMWorker::compute(): this build has no CPU compute path");
 }
 
-// How many tiles (slices of reads) a batch is cut into.  Two tasks are kept in flight (blaze::Client::startAsync), so
-// with three or more tiles the serialization, packing and host-to-device copy of tile k+1 and the copy-back and log10
-// of tile k-1 run under the kernels of tile k; only the first tile's way in and the last tile's way out stay exposed.
-// More tiles shrink that exposed part but cost GPU efficiency (fewer warp-tasks per launch, more launches), and a
-// small batch gains nothing.  PAIRHMM_WORKER_TILES overrides (tuning).
+// How many tiles (slices of reads) a batch is cut into.  Up to blaze::Client::kMaxInFlight tasks are in flight, each on
+// its own accelerator slot (engine context, stream, staging buffers), so all tiles of a typical batch are submitted at
+// once: their serialization, packing and host-to-device copies run under the kernels of the first tile, and the
+// copy-back and log10 of a finished tile under the kernels of the next.  Only the first tile's way in and the last
+// tile's way out stay exposed, which is why the first tile is half the size of the others.  More tiles shrink the
+// exposed part but cost GPU efficiency (fewer warp-tasks per launch, more launches), and a small batch gains nothing.
+// PAIRHMM_WORKER_TILES overrides (tuning).
 static int pick_tiles(uint64_t cells, int num_read) {
   if (const char* e = getenv("PAIRHMM_WORKER_TILES")) { const int v = atoi(e); if (v >= 1) return std::min(v, std::max(1, num_read)); }
   if (cells < 1200000000ull) return 1;
-  const int t = (int)std::min<uint64_t>(6, std::max<uint64_t>(3, cells / 1200000000ull));
+  const int t = (int)std::min<uint64_t>(6, std::max<uint64_t>(3, cells / 1100000000ull));
   return std::min(t, std::max(1, num_read));
 }
 
@@ -77,22 +81,34 @@ void PairHMMWorker::run() {
   uint64_t rows = std::min<uint64_t>((byte_budget - hap_bytes) / (5 * max_read + 4), (1ull << 30) / (uint64_t)num_hap_);
   rows = std::max<uint64_t>(1, std::min<uint64_t>(rows, (uint64_t)num_read_));
   const int tiles = pick_tiles(read_bases * hap_bases, num_read_);
-  rows = std::min<uint64_t>(rows, ((uint64_t)num_read_ + tiles - 1) / tiles);
+  // tile sizes: the first one half a share (2 tiles - 1 half-shares in all), never above the engine's limit
+  const uint64_t half_share = std::max<uint64_t>(1, ((uint64_t)num_read_ + 2 * tiles - 2) / (2 * tiles - 1));
+  const uint64_t limit = rows;
 
   // two tasks in flight: submit tile k+1 (and k+2) before waiting for tile k
   std::deque<std::pair<int, int> > flying;                          // (first row, rows) of the tasks in flight, oldest first
   int next = 0;
+  static const bool trace = getenv("PAIRHMM_TRACE") != nullptr;     // one line per step on stderr, microseconds since run()
+  const auto t0 = std::chrono::steady_clock::now();
+  auto us = [&] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(); };
   try {
     while (next < num_read_ || !flying.empty()) {
       while (next < num_read_ && client_->inFlight() < blaze::Client::kMaxInFlight) {
-        const int n = std::min<int>((int)rows, num_read_ - next);
+        const uint64_t want = tiles == 1 ? (uint64_t)num_read_ : (next == 0 ? half_share : 2 * half_share);
+        const int n = (int)std::min<uint64_t>(std::min<uint64_t>(want, limit), (uint64_t)(num_read_ - next));
+        const double a = us();
         client_->setup(&host_reads_[next], n, host_haps_, num_hap_);
+        const double b = us();
         client_->startAsync();
+        if (trace) fprintf(stderr, "[worker] tile rows %d+%d: setup %.0f..%.0f us, started %.0f\n", next, n, a, b, us());
         flying.emplace_back(next, n);
         next += n;
       }
+      const double a = us();
       client_->wait();
+      const double b = us();
       consume(flying.front().first, flying.front().second);
+      if (trace) fprintf(stderr, "[worker] tile rows %d: waited %.0f..%.0f us, consumed %.0f\n", flying.front().first, a, b, us());
       flying.pop_front();
     }
   } catch (...) {

@@ -8,6 +8,11 @@
 #include "PairHMMManager.h"
 #include "PairHMMWorker.h"
 
+static std::unique_ptr<PairHMMClient>& thread_client() {
+  static thread_local std::unique_ptr<PairHMMClient> client;
+  return client;
+}
+
 extern "C" int pairhmm_worker_forward(int num_read, const int32_t* read_off, const char* bases, const char* q, const char* i,
                                       const char* d, const char* c, int num_hap, const int32_t* hap_off, const char* hap,
                                       double* out, int* num_recalc, char* err, int err_capacity) {
@@ -15,7 +20,7 @@ extern "C" int pairhmm_worker_forward(int num_read, const int32_t* read_off, con
     if (num_read <= 0 || num_hap <= 0 || !read_off || !hap_off || !bases || !q || !i || !d || !c || !hap || !out)
       throw std::invalid_argument("pairhmm_worker_forward: null or empty input");
     if (!blaze::AppCommManager::lookup(1027)) pairhmm_default_manager();
-    static thread_local std::unique_ptr<PairHMMClient> client;
+    std::unique_ptr<PairHMMClient>& client = thread_client();
     if (!client) client.reset(new PairHMMClient());
     // read_t / hap_t views of the caller's arrays: nothing is copied until PairHMMClient::setup serializes a tile
     static thread_local std::vector<read_t> reads;
@@ -39,4 +44,7 @@ extern "C" int pairhmm_worker_forward(int num_read, const int32_t* read_off, con
   }
 }
 
-extern "C" void pairhmm_worker_shutdown(void) { pairhmm_shutdown_manager(); }
+extern "C" void pairhmm_worker_shutdown(void) {
+  thread_client().reset();            // the calling thread's client (other threads' clients end with their threads)
+  pairhmm_shutdown_manager();
+}

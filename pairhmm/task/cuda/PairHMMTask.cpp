@@ -1,6 +1,8 @@
 // PairHMMTask.cpp -- see PairHMMTask.h.
 #include "PairHMMTask.h"
 
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -41,7 +43,14 @@ void PairHMM::prepare() {
 
   num_cell = *static_cast<uint64_t*>(getInput(0));
 
-  if (!env->getScratch("engine", engine_)) engine_.reset(new PairHMMEngine(env->getDevice()));
+  if (!env->getScratch("engine", engine_)) {
+    engine_.reset(new PairHMMEngine(env->getDevice()));
+    // Slots of one GPU are handed out in order, so the tiles of a batch (client/PairHMMWorker.cpp) land on slots 0, 1, 2, ...:
+    // the earlier tile's kernels go first wherever two tiles compete for thread-block slots, and the tiles finish in order
+    // instead of all at once -- the worker consumes tile k while tile k+1 is still on the GPU.
+    if (conf_flag("slot_priority", true))
+      check(pmm_set_option(engine_->ctx, "priority", std::to_string(env->getSlot()).c_str()), "priority");
+  }
 
   std::string v;
   if (get_conf("tasks_per_warp", v)) check(pmm_set_option(engine_->ctx, "tasks_per_warp", v.c_str()), "tasks_per_warp");
@@ -63,6 +72,8 @@ void PairHMM::prepare() {
 void PairHMM::compute() {
   if (!engine_) throw std::runtime_error("PairHMM::compute() before prepare()");
   const uint64_t pairs = (uint64_t)num_read * (uint64_t)num_hap;
+  static const bool trace = getenv("PAIRHMM_TRACE") != nullptr;
+  const uint64_t t0 = blaze::getUs();
 
   check(pmm_launch(engine_->ctx), "launch");
   // Output block 2 (extension, see PairHMMTask.h): the final log10 doubles.  Taken first: the engine takes log10f of the
@@ -88,6 +99,11 @@ void PairHMM::compute() {
                                reinterpret_cast<double*>(p + sizeof(uint64_t) + idx_bytes), n, &n), "fallback list");
     }
     setOutput(1, fb);
+  }
+  if (trace) {
+    pmm_stats_t st; pmm_get_stats(engine_->ctx, &st);
+    fprintf(stderr, "[task] %d x %d: compute() %llu us (stage %.0f us before it; kernels f32 %.0f + f64 %.0f us)\n", num_read, num_hap,
+            (unsigned long long)(blaze::getUs() - t0), st.ms_stage * 1e3, st.ms_f32 * 1e3, st.ms_fallback * 1e3);
   }
 }
 
