@@ -81,6 +81,7 @@ struct pmm_ctx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_block = nullptr;     // "sync" = "block": waits sleep on this event instead of spinning on the stream
     bool block_sync = false;
+    int spin_us = 0;                    // "sync" = "hybrid": poll this long, then sleep on the blocking event
     std::string err;
     int tasks_per_warp = 16;
     bool fast = false;                  // "mode" option: fast = contracted float kernels + exact re-check near the threshold
@@ -596,8 +597,9 @@ int pmm_set_option(pmm_ctx* c, const char* key, const char* value)
     }
     if (k == "sync") {
         const std::string v = value;
-        if (v != "spin" && v != "block") return c->fail(PMM_ERR_INVALID, "sync is \"spin\" or \"block\"");
-        c->block_sync = v == "block";
+        if (v != "spin" && v != "block" && v != "hybrid") return c->fail(PMM_ERR_INVALID, "sync is \"spin\", \"block\" or \"hybrid\"");
+        c->block_sync = v != "spin";
+        c->spin_us = v == "hybrid" ? 60 : 0;
         return PMM_OK;
     }
     if (k == "force_variant") {
@@ -772,7 +774,16 @@ static cudaError_t wait_stream(pmm_ctx* c, cudaStream_t st)
 {
     if (!c->block_sync) return cudaStreamSynchronize(st);
     cudaError_t e = cudaEventRecord(c->ev_block, st);
-    return e != cudaSuccess ? e : cudaEventSynchronize(c->ev_block);
+    if (e != cudaSuccess) return e;
+    if (c->spin_us > 0) {
+        // hybrid: what is about to finish is caught without a wake-up, what takes long does not hold a core
+        const auto until = std::chrono::steady_clock::now() + std::chrono::microseconds(c->spin_us);
+        do {
+            e = cudaEventQuery(c->ev_block);
+            if (e != cudaErrorNotReady) return e;
+        } while (std::chrono::steady_clock::now() < until);
+    }
+    return cudaEventSynchronize(c->ev_block);
 }
 
 struct HostOut { uint32_t* ctrl; float* raw; uint32_t* idx; double* dres; };

@@ -2,11 +2,11 @@
 //
 // Read x haplotype pairs are independent and nothing is reduced, so multi-GPU is a partition of whole regions with
 // no collective: the pool owns `contexts_per_device` engine contexts (pmm_ctx, each with its own stream and pinned
-// staging buffers) on every device it was given and one feeder thread per context.  Jobs go into one queue ordered
-// by cell count, largest first (the skewed length distribution of configs 4/5 leaves the small jobs to fill the
-// tail); a feeder takes the next job, stages it, launches and fetches it through the same C ABI a single-GPU caller
-// uses.  Two or three contexts per GPU keep the copy engines and the host-side packing of job i+1 busy while the
-// kernels of job i run.  This is the piece that stands where the reference has Blaze's per-accelerator task queue
+// staging buffers) on every device it was given and one feeder thread per pair of contexts.  Jobs go into one queue
+// served by generation (a run of consecutive tickets) and, inside a generation, largest first (the skewed length
+// distribution of configs 4/5 leaves the small jobs to fill the tail); a feeder takes the next job, stages it,
+// launches and fetches it through the same C ABI a single-GPU caller uses, always with a second job already queued on
+// the GPU behind the one it is waiting for.  This is the piece that stands where the reference has Blaze's per-accelerator task queue
 // and the FPGA processing-unit balancer (/root/reference/pairhmm/interface/PairHMMFpgaInterface.cpp:67-170).
 #include "../../include/pairhmm_cuda.h"
 
@@ -26,7 +26,7 @@
 namespace {
 
 struct Job {
-    uint64_t ticket = 0, cells = 0;
+    uint64_t ticket = 0, cells = 0, generation = 0;
     // flat layout, borrowed from the caller until pmm_pool_wait returns
     uint32_t num_read = 0, num_hap = 0, num_region = 0;
     const uint32_t* read_off = nullptr; const uint8_t* tr[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -38,10 +38,15 @@ struct Job {
     int rc = PMM_OK; std::string err; uint64_t n_fallback = 0; int device = -1; bool done = false;
 };
 
+// Order of service: by generation (a run of consecutive tickets), inside a generation the largest job first.  Largest
+// first is what balances a bounded set of jobs (the small ones fill the tail), but as the only key it starves the small
+// jobs of a continuous stream behind ever newer large ones -- with eight GPUs draining the queue that stalled a caller
+// waiting for its oldest ticket every ~50 ms on all devices at once (profiles/r02_pool_timeline_n8_before.jsonl).
 struct JobOrder {
-    bool operator()(const Job* a, const Job* b) const
+    bool operator()(const Job* a, const Job* b) const            // priority_queue: "less" = served later
     {
-        if (a->cells != b->cells) return a->cells < b->cells;      // priority_queue: largest on top
+        if (a->generation != b->generation) return a->generation > b->generation;
+        if (a->cells != b->cells) return a->cells < b->cells;
         return a->ticket > b->ticket;
     }
 };
@@ -98,27 +103,44 @@ static uint64_t job_bytes(const Job* j)
     return 5ull * (j->read_off[j->num_read] - j->read_off[0]) + (j->hap_off[j->num_hap] - j->hap_off[0]);
 }
 
-struct Stamp { double staged = 0, launched = 0; bool ran = false; };   // host times of one GPU job, for the trace
+// One GPU job of a feeder: the submitted jobs it serves, where it is in its life, and the host times of the trace.
+struct Flight {
+    std::vector<Job*> batch;
+    MergeBuf m;                         // merged inputs / outputs (batch.size() > 1)
+    bool active = false;                // staged and launched, results not yet fetched
+    bool merged = false;
+    int rc = PMM_OK;
+    double t_take = 0, t_staged = 0, t_launched = 0;
+};
 
-static void run_single(pmm_pool* p, pmm_ctx* c, Job* j, Stamp& st)
+// Stage and launch; the kernels run while the caller does something else.
+static void start_single(pmm_ctx* c, Flight& f)
 {
-    int rc = pmm_stage_flat(c, j->num_read, j->read_off, j->tr[0], j->tr[1], j->tr[2], j->tr[3], j->tr[4],
-                            j->num_hap, j->hap_off, j->hap, j->num_region, j->regions);
-    st.staged = now_s();
-    if (rc == PMM_OK) rc = pmm_launch(c);
-    st.launched = now_s(); st.ran = rc == PMM_OK;
+    Job* j = f.batch[0];
+    f.merged = false;
+    f.rc = pmm_stage_flat(c, j->num_read, j->read_off, j->tr[0], j->tr[1], j->tr[2], j->tr[3], j->tr[4],
+                          j->num_hap, j->hap_off, j->hap, j->num_region, j->regions);
+    f.t_staged = now_s();
+    if (f.rc == PMM_OK) f.rc = pmm_launch(c);
+    f.t_launched = now_s();
+}
+
+static void finish_single(pmm_ctx* c, Job* j, int rc)
+{
     uint64_t nfb = 0;
     if (rc == PMM_OK) rc = pmm_fetch_log10(c, j->out, j->out_capacity, &nfb);
     j->rc = rc; j->n_fallback = nfb;
     if (rc != PMM_OK) j->err = pmm_last_error(c);
 }
 
-static void run_merged(pmm_pool* p, pmm_ctx* c, std::vector<Job*>& batch, MergeBuf& m, Stamp& st)
+static void start_merged(pmm_ctx* c, Flight& f)
 {
+    MergeBuf& m = f.m;
+    f.merged = true;
     m.read_off.assign(1, 0); m.hap_off.assign(1, 0); m.regions.clear(); m.out_first.assign(1, 0);
     for (int t = 0; t < 5; ++t) m.tr[t].clear();
     m.hap.clear();
-    for (Job* j : batch) {
+    for (Job* j : f.batch) {
         const uint32_t rbase = (uint32_t)m.read_off.size() - 1, hbase = (uint32_t)m.hap_off.size() - 1;
         const uint32_t r0 = j->read_off[0], h0 = j->hap_off[0];
         const uint32_t rshift = m.read_off.back(), hshift = m.hap_off.back();
@@ -135,21 +157,34 @@ static void run_merged(pmm_pool* p, pmm_ctx* c, std::vector<Job*>& batch, MergeB
     }
     const uint64_t total = m.out_first.back();
     m.out.resize(total); m.fb_index.resize(total);
-    int rc = pmm_stage_flat(c, (uint32_t)m.read_off.size() - 1, m.read_off.data(), m.tr[0].data(), m.tr[1].data(), m.tr[2].data(),
-                            m.tr[3].data(), m.tr[4].data(), (uint32_t)m.hap_off.size() - 1, m.hap_off.data(), m.hap.data(),
-                            (uint32_t)m.regions.size(), m.regions.data());
-    st.staged = now_s();
-    if (rc == PMM_OK) rc = pmm_launch(c);
-    st.launched = now_s(); st.ran = rc == PMM_OK;
+    f.rc = pmm_stage_flat(c, (uint32_t)m.read_off.size() - 1, m.read_off.data(), m.tr[0].data(), m.tr[1].data(), m.tr[2].data(),
+                          m.tr[3].data(), m.tr[4].data(), (uint32_t)m.hap_off.size() - 1, m.hap_off.data(), m.hap.data(),
+                          (uint32_t)m.regions.size(), m.regions.data());
+    f.t_staged = now_s();
+    if (f.rc == PMM_OK) f.rc = pmm_launch(c);
+    f.t_launched = now_s();
+}
+
+static void finish_merged(pmm_ctx* c, Flight& f)
+{
+    MergeBuf& m = f.m;
+    std::vector<Job*>& batch = f.batch;
+    const uint64_t total = m.out_first.back();
+    int rc = f.rc;
     uint64_t nfb = 0;
     if (rc == PMM_OK) rc = pmm_fetch_log10_indexed(c, m.out.data(), total, m.fb_index.data(), total, &nfb);
     if (rc == PMM_ERR_INVALID) {
         // One caller's bad job must not fail the others it happened to be merged with (submit-time validation should
         // have caught it; this is the second line): run every job on its own, so that only the bad one fails.
-        Stamp each;
-        for (Job* j : batch) run_single(p, c, j, each);
+        for (Job* j : batch) {
+            Flight one; one.batch.assign(1, j);
+            start_single(c, one);
+            finish_single(c, j, one.rc);
+        }
+        f.rc = PMM_ERR_INVALID;
         return;
     }
+    f.rc = rc;
     const std::string err = rc == PMM_OK ? std::string() : std::string(pmm_last_error(c));
     for (size_t b = 0; b < batch.size(); ++b) {
         Job* j = batch[b];
@@ -163,60 +198,95 @@ static void run_merged(pmm_pool* p, pmm_ctx* c, std::vector<Job*>& batch, MergeB
         }
 }
 
-static void feeder_main(pmm_pool* p, size_t slot)
+// Takes the next job (and, when merging, the small jobs waiting behind it) off the queue.  wait = false: returns false at
+// once if nothing is queued.  Returns false with an empty batch also when the pool is stopping and drained.
+static bool take_batch(pmm_pool* p, std::vector<Job*>& batch, bool wait)
 {
-    pmm_ctx* c = p->ctxs[slot];
-    MergeBuf merge;
-    std::vector<Job*> batch;
+    batch.clear();
+    std::unique_lock<std::mutex> lk(p->mu);
+    if (wait) p->cv_work.wait(lk, [&] { return p->stopping || !p->queue.empty(); });
+    if (p->queue.empty()) return false;
+    Job* j = p->queue.top(); p->queue.pop();
+    batch.push_back(j);
+    // the queue is ordered largest first: everything behind a small job is small too
+    uint64_t cells = j->cells, bytes = job_bytes(j), pairs = job_pairs(j);
+    while (p->merge && !p->queue.empty() && batch.size() < kMergeJobs) {
+        Job* n = p->queue.top();
+        if (cells + n->cells > kMergeCells || bytes + job_bytes(n) > kMergeBytes || pairs + job_pairs(n) > kMergePairs) break;
+        p->queue.pop();
+        batch.push_back(n);
+        cells += n->cells; bytes += job_bytes(n); pairs += job_pairs(n);
+    }
+    return true;
+}
+
+// A feeder thread drives two contexts of one GPU in turn: it stages and launches a job on one while the job on the other
+// is still running, and only then waits for that other one.  So a job is always queued on the GPU behind the one whose
+// results the thread is fetching: the host work between two jobs of a context (copy-back, log10, merging, packing the next
+// one, about a millisecond) never leaves the GPU idle, and neither does the wake-up of a sleeping wait.  (One thread per
+// context -- round 1 -- let all contexts of a GPU fall into step: kernels launched together share the GPU, finish
+// together, and the GPU then waits for all their feeders at once; profiles/r02_pool_timeline_n8.jsonl.)
+static void feeder_main(pmm_pool* p, size_t slot_a, size_t slot_b)
+{
+    const size_t slots[2] = {slot_a, slot_b};
+    const int n_ctx = slot_b == (size_t)-1 ? 1 : 2;
+    Flight fl[2];
+    uint64_t seq = 0, started[2] = {0, 0};
+    bool stopping = false;
     for (;;) {
-        batch.clear();
+        // ---- start a job on every free context: sleep for work only when nothing is in flight; with a job in flight,
+        //      take what is waiting or go and deliver that job ---------------------------------------------------------
+        for (int k = 0; k < n_ctx && !stopping; ++k) {
+            Flight& f = fl[k];
+            if (f.active) continue;
+            const bool any_active = fl[0].active || fl[1].active;
+            if (take_batch(p, f.batch, !any_active)) {
+                f.t_take = now_s();
+                if (f.batch.size() == 1) start_single(p->ctxs[slots[k]], f); else start_merged(p->ctxs[slots[k]], f);
+                f.active = true; started[k] = ++seq;
+            } else if (!any_active) {
+                stopping = true;                          // woken with an empty queue: the pool is shutting down
+            } else break;
+        }
+        if (!fl[0].active && !fl[1].active) {
+            if (stopping) return;
+            continue;
+        }
+        // ---- finish the older of the jobs in flight ------------------------------------------------------------------------
+        const int fin = (fl[0].active && (!fl[1].active || started[0] < started[1])) ? 0 : 1;
+        Flight& g = fl[fin];
         {
-            std::unique_lock<std::mutex> lk(p->mu);
-            p->cv_work.wait(lk, [&] { return p->stopping || !p->queue.empty(); });
-            if (p->queue.empty()) return;          // stopping and drained
-            Job* j = p->queue.top(); p->queue.pop();
-            batch.push_back(j);
-            // the queue is ordered largest first: everything behind a small job is small too
-            uint64_t cells = j->cells, bytes = job_bytes(j), pairs = job_pairs(j);
-            while (p->merge && !p->queue.empty() && batch.size() < kMergeJobs) {
-                Job* n = p->queue.top();
-                if (cells + n->cells > kMergeCells || bytes + job_bytes(n) > kMergeBytes || pairs + job_pairs(n) > kMergePairs) break;
-                p->queue.pop();
-                batch.push_back(n);
-                cells += n->cells; bytes += job_bytes(n); pairs += job_pairs(n);
+            pmm_ctx* c = p->ctxs[slots[fin]];
+            if (g.merged) finish_merged(c, g); else { finish_single(c, g.batch[0], g.rc); g.rc = g.batch[0]->rc; }
+            const double t_fetched = now_s();
+            pmm_pool_trace_t rec{};
+            bool have_rec = false;
+            if (p->tracing && g.rc == PMM_OK) {          // (read without the lock: a stale value only adds or drops one record)
+                pmm_timeline_t tl;
+                if (pmm_get_timeline(c, &tl) == PMM_OK) {
+                    const double origin = std::chrono::duration<double>(p->t0.time_since_epoch()).count();
+                    rec.device = p->ctx_device[slots[fin]]; rec.context = (int32_t)slots[fin]; rec.jobs = (uint32_t)g.batch.size();
+                    for (Job* j : g.batch) { rec.regions += j->num_region; rec.cells += j->cells; rec.pairs += job_pairs(j); }
+                    rec.t_take = g.t_take - origin; rec.t_staged = g.t_staged - origin; rec.t_launched = g.t_launched - origin;
+                    rec.t_fetched = t_fetched - origin;
+                    rec.d_start = tl.ref_host_s + tl.kernels_start_s - origin; rec.d_f32_end = tl.ref_host_s + tl.f32_end_s - origin;
+                    rec.d_end = tl.ref_host_s + tl.kernels_end_s - origin;
+                    have_rec = true;
+                }
             }
-        }
-        const double t_take = now_s();
-        Stamp st;
-        if (batch.size() == 1) run_single(p, c, batch[0], st);
-        else run_merged(p, c, batch, merge, st);
-        const double t_fetched = now_s();
-        pmm_pool_trace_t rec{};
-        bool have_rec = false;
-        if (p->tracing && st.ran) {           // (read without the lock: a stale value only adds or drops one record)
-            pmm_timeline_t tl;
-            if (pmm_get_timeline(c, &tl) == PMM_OK) {
-                const double origin = std::chrono::duration<double>(p->t0.time_since_epoch()).count();
-                rec.device = p->ctx_device[slot]; rec.context = (int32_t)slot; rec.jobs = (uint32_t)batch.size();
-                for (Job* j : batch) { rec.regions += j->num_region; rec.cells += j->cells; rec.pairs += job_pairs(j); }
-                rec.t_take = t_take - origin; rec.t_staged = st.staged - origin; rec.t_launched = st.launched - origin;
-                rec.t_fetched = t_fetched - origin;
-                rec.d_start = tl.ref_host_s + tl.kernels_start_s - origin; rec.d_f32_end = tl.ref_host_s + tl.f32_end_s - origin;
-                rec.d_end = tl.ref_host_s + tl.kernels_end_s - origin;
-                have_rec = true;
+            {
+                std::lock_guard<std::mutex> lk(p->mu);
+                if (have_rec && p->tracing) p->trace.push_back(rec);
+                for (Job* j : g.batch) {
+                    j->device = p->ctx_device[slots[fin]]; j->done = true;
+                    for (int d = 0; d < p->n_devices; ++d)
+                        if (p->devices[d] == j->device) { p->cells_per_device[d] += j->cells; p->jobs_per_device[d]++; }
+                }
+                p->merged_batches += g.batch.size() > 1;
             }
+            p->cv_done.notify_all();
+            g.active = false;
         }
-        {
-            std::lock_guard<std::mutex> lk(p->mu);
-            if (have_rec && p->tracing) p->trace.push_back(rec);
-            for (Job* j : batch) {
-                j->device = p->ctx_device[slot]; j->done = true;
-                for (int d = 0; d < p->n_devices; ++d)
-                    if (p->devices[d] == j->device) { p->cells_per_device[d] += j->cells; p->jobs_per_device[d]++; }
-            }
-            p->merged_batches += batch.size() > 1;
-        }
-        p->cv_done.notify_all();
     }
 }
 
@@ -252,13 +322,21 @@ int pmm_pool_create(const int* devices, int n_devices, int contexts_per_device, 
                 return rc;
             }
             p->ctxs.push_back(c); p->ctx_device.push_back(d);
+            // PMM_POOL_PRIORITY=1: the contexts of a device get distinct stream priorities (tuning)
+            if (const char* e = getenv("PMM_POOL_PRIORITY")) if (atoi(e) > 0) pmm_set_option(c, "priority", std::to_string(rep).c_str());
         }
     // Waits spin by default.  Measured on an 8-GPU box with 32 host cores (24 feeder threads): spinning 14 100 GCUPS,
     // sleeping on a blocking event 13 400 -- the wake-up latency costs more than the cores it frees.  PMM_POOL_SYNC=block
     // selects the sleeping wait for hosts with fewer cores than feeder threads.
     if (const char* e = getenv("PMM_POOL_SYNC"))
-        if (!strcmp(e, "block")) for (pmm_ctx* c : p->ctxs) pmm_set_option(c, "sync", "block");
-    for (size_t s = 0; s < p->ctxs.size(); ++s) p->feeders.emplace_back(feeder_main, p, s);
+        if (!strcmp(e, "block") || !strcmp(e, "hybrid") || !strcmp(e, "spin")) for (pmm_ctx* c : p->ctxs) pmm_set_option(c, "sync", e);
+    // feeder threads: the contexts of a device in pairs (ctxs is laid out [rep][device])
+    const size_t nd = devs.size();
+    for (size_t d = 0; d < nd; ++d)
+        for (int rep = 0; rep < contexts_per_device; rep += 2) {
+            const size_t a = (size_t)rep * nd + d, b = rep + 1 < contexts_per_device ? (size_t)(rep + 1) * nd + d : (size_t)-1;
+            p->feeders.emplace_back(feeder_main, p, a, b);
+        }
     *out = p;
     return PMM_OK;
 }
@@ -338,6 +416,7 @@ int pmm_pool_submit_flat(pmm_pool* p, uint32_t num_read, const uint32_t* read_of
         std::lock_guard<std::mutex> lk(p->mu);
         if (p->stopping) { delete j; p->err = "pool is shutting down"; return PMM_ERR_STATE; }
         j->ticket = p->next_ticket++;
+        j->generation = j->ticket / (2 * p->ctxs.size() + 1);      // about two jobs per context
         p->jobs[j->ticket] = j;
         p->queue.push(j);
         *ticket = j->ticket;

@@ -14,7 +14,7 @@ The JSON line
   value         whole-job GCUPS (cells = sum(read_len) * sum(hap_len), /root/reference/pairhmm/host/main.cpp:305-313) with
                 inputs resident in HBM, CUDA events, L2 flushed between steps
   e2e           the same metric with HOST buffers: pack + H2D + kernels + D2H + host log10 inside the timed region.
-                `value` = through the work queue (pmm_pool_*, 3 contexts, neighbouring steps overlap); `serial_value` = one
+                `value` = through the work queue (pmm_pool_*, 4 contexts, neighbouring steps overlap); `serial_value` = one
                 context, nothing overlapped; `plugin_value` = through the reference-named classes PairHMMClient +
                 PairHMMWorker over the task plugin libPairHMMTask.so (pairhmm_worker_forward), one caller thread;
                 `plugin_threads_value` = the same from three caller threads (GATK's threading model)
@@ -300,7 +300,7 @@ class Gpu:
         raw = self.eng.fetch_raw(); out, nfb = self.eng.fetch_log10(); mask = self.eng.fetch_fallback_mask()
         return raw, out, mask, nfb
 
-    def pool_e2e(self, job, pairs: int, steps: int, depth: int = 3):
+    def pool_e2e(self, job, pairs: int, steps: int, depth: int = 4):
         """Seconds for `steps` jobs through a one-GPU pool with `depth` contexts (host buffers in, float64 log10 out)."""
         from collections import deque
         from acc_genomics_b200.engine import PairHMMPool
@@ -397,7 +397,7 @@ def measure_plugin(batch, steps: int, local: int, threads: int):
     return (time.perf_counter() - t0) / (per * threads), jobs[0].out.copy()
 
 
-def measure_queue(n_gpus: int, jobs_per_gpu: int, timeline_path: str):
+def measure_queue(n_gpus: int, jobs_per_gpu: int, timeline_path: str, contexts: int = 4):
     """The cfg5 stream (jobs of 25 regions, host buffers in, float64 log10 out) through ONE pool over n_gpus devices, and the
     same stream through a one-GPU pool in the same run.  -> dict for the JSON line (+ the jobs for the parity leg)."""
     from collections import deque
@@ -407,8 +407,8 @@ def measure_queue(n_gpus: int, jobs_per_gpu: int, timeline_path: str):
     job_cells = [cells_of(regs[k:k + 25]) for k in range(0, len(regs), 25)]
 
     def stream(devices, n_jobs, trace):
-        pool = PairHMMPool(devices=devices, contexts_per_device=3)
-        window = 6 * len(devices) + 6
+        pool = PairHMMPool(devices=devices, contexts_per_device=contexts)
+        window = 2 * contexts * len(devices) + 6
         outs = [np.empty(jobs[0]["pairs"], dtype=np.float64) for _ in range(window + 1)]
 
         def run(n, keep=None):
@@ -462,7 +462,7 @@ def measure_queue(n_gpus: int, jobs_per_gpu: int, timeline_path: str):
             for r in tr:
                 f.write(json.dumps(r) + "\n")
     return {"workload": "cfg5 stream: jobs of 25 regions (100 reads x 40 haps each) from 150 distinct regions, host buffers in, float64 log10 out",
-            "path": "pmm_pool_submit_flat / pmm_pool_wait, ONE pool in ONE process over all GPUs, 3 contexts per GPU, no collective",
+            "path": f"pmm_pool_submit_flat / pmm_pool_wait, ONE pool in ONE process over all GPUs, {contexts} contexts per GPU, no collective",
             "n_gpus": n_gpus, "jobs": jobs_per_gpu * n_gpus, "gcups": all_gcups, "seconds": all_s, "gcups_1gpu": one_gcups, "seconds_1gpu": one_s,
             "efficiency": all_gcups / (one_gcups * n_gpus), "per_device": load, "gpu_idle_frac": idle, "mean_per_job": host,
             "gpu_jobs_traced": len(tr)}, regs, kept
@@ -654,7 +654,7 @@ def _main(args, real_stdout):
             "fallback_pairs": int(nfb), "flush_pairs": int(st["flush_pairs"]),
             "e2e": {"value": job_cells * args.steps / e2e_s * 1e-9, "unit": UNIT, "h2d_bytes_per_step": int(st2["h2d_bytes"]),
                     "d2h_bytes_per_step": int(st2["d2h_bytes"]), "ms_per_step": e2e_s / args.steps * 1e3,
-                    "path": "pmm_pool_submit_flat / pmm_pool_wait, 3 contexts on the GPU: per step pack + H2D + kernels + D2H + host "
+                    "path": "pmm_pool_submit_flat / pmm_pool_wait, 4 contexts (2 feeder threads) on the GPU: per step pack + H2D + kernels + D2H + host "
                             "log10, host numpy buffers in, float64 log10 out, steps overlapped by the queue",
                     "serial_value": job_cells * args.steps / e2e_serial_s * 1e-9, "serial_ms_per_step": e2e_serial_s / args.steps * 1e3,
                     "serial_path": "pmm_stage_flat + pmm_launch + pmm_fetch_log10 on one context, one step at a time"},

@@ -135,7 +135,7 @@ class Client {
     {
         if (flights_.empty()) throw invalidParam("Client::wait: nothing in flight");
         Lane* lane = flights_.front(); flights_.pop_front();
-        for (int spin = 0; spin < 200000 && !lane->done_flag.load(std::memory_order_acquire); ++spin) Lane::cpu_relax();
+        for (int spin = 0; spin < 4000 && !lane->done_flag.load(std::memory_order_acquire); ++spin) Lane::cpu_relax();
         { std::unique_lock<std::mutex> lk(lane->mu); lane->cv.wait(lk, [&] { return lane->done; }); lane->busy = false; }
         spare_inputs_.emplace_back(std::move(lane->inputs), std::move(lane->in_capacity));
         lane->inputs.clear(); lane->in_capacity.clear();
@@ -175,7 +175,7 @@ class Client {
             for (;;) {
                 // A tile follows the previous one within microseconds while a batch is in flight: poll briefly before
                 // sleeping, a condition-variable wake-up costs more than a tile's host work
-                for (int spin = 0; spin < 20000 && !flag.load(std::memory_order_acquire); ++spin) cpu_relax();
+                for (int spin = 0; spin < 2000 && !flag.load(std::memory_order_acquire); ++spin) cpu_relax();
                 { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return go || stop; }); if (stop) return; go = false; flag.store(false, std::memory_order_relaxed); }
                 try {
                     PlatformManager* pm = AppCommManager::lookup(port);
