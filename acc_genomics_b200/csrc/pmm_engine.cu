@@ -82,6 +82,7 @@ struct pmm_ctx {
     cudaEvent_t ev_block = nullptr;     // "sync" = "block": waits sleep on this event instead of spinning on the stream
     bool block_sync = false;
     int spin_us = 0;                    // "sync" = "hybrid": poll this long, then sleep on the blocking event
+    bool auto_sync = false;             // "sync" = "auto": spin while few threads of the process do, else sleep
     std::string err;
     int tasks_per_warp = 16;
     bool fast = false;                  // "mode" option: fast = contracted float kernels + exact re-check near the threshold
@@ -597,9 +598,10 @@ int pmm_set_option(pmm_ctx* c, const char* key, const char* value)
     }
     if (k == "sync") {
         const std::string v = value;
-        if (v != "spin" && v != "block" && v != "hybrid") return c->fail(PMM_ERR_INVALID, "sync is \"spin\", \"block\" or \"hybrid\"");
-        c->block_sync = v != "spin";
+        if (v != "spin" && v != "block" && v != "hybrid" && v != "auto") return c->fail(PMM_ERR_INVALID, "sync is \"spin\", \"block\", \"hybrid\" or \"auto\"");
+        c->block_sync = v == "block" || v == "hybrid";
         c->spin_us = v == "hybrid" ? 60 : 0;
+        c->auto_sync = v == "auto";
         return PMM_OK;
     }
     if (k == "force_variant") {
@@ -770,8 +772,28 @@ int pmm_sync(pmm_ctx* c)
 // Wait for everything queued on one of the context's streams.  A caller with one context per core spins (lowest latency);
 // the pool, which runs several contexts per GPU from as many host threads, can sleep on a blocking event so that the
 // waiting threads do not take the cores the packing and log10 work of the other contexts needs.
+// "auto": a spinning wait is the fastest (no wake-up), but every spinner holds a core.  The first few waiting threads
+// of the process spin, the rest sleep -- a host with one or two caller threads gets the latency, a host with dozens (or a
+// box with a process per GPU) keeps its cores for the packing and log10 work.
+static std::atomic<int> g_spinners{0};
+static int spinner_budget()
+{
+    static const int b = [] { const unsigned hw = std::thread::hardware_concurrency(); return (int)std::max(1u, hw / 16); }();
+    return b;
+}
+
 static cudaError_t wait_stream(pmm_ctx* c, cudaStream_t st)
 {
+    if (c->auto_sync) {
+        if (g_spinners.fetch_add(1, std::memory_order_relaxed) < spinner_budget()) {
+            const cudaError_t e = cudaStreamSynchronize(st);
+            g_spinners.fetch_sub(1, std::memory_order_relaxed);
+            return e;
+        }
+        g_spinners.fetch_sub(1, std::memory_order_relaxed);
+        cudaError_t e = cudaEventRecord(c->ev_block, st);
+        return e != cudaSuccess ? e : cudaEventSynchronize(c->ev_block);
+    }
     if (!c->block_sync) return cudaStreamSynchronize(st);
     cudaError_t e = cudaEventRecord(c->ev_block, st);
     if (e != cudaSuccess) return e;

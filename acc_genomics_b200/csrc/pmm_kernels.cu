@@ -129,8 +129,9 @@ __device__ __forceinline__ void push_recheck(const FallbackQueue& fq, uint32_t r
 // One warp-task: the reads of one group against a run of haplotypes.
 // ---------------------------------------------------------------------------------------------------------
 // F: bit flags.  kFlush: emulate x86 flush-to-zero after every double product.  kPush: append results below the
-// fallback threshold to the fallback list (float).  kFast: contract the float cell update to 4 FMUL + 4 FFMA (results
-// within a few ulp of the exact order; the engine re-checks everything near the threshold with an exact kernel).
+// fallback threshold to the fallback list (float).  kFast: the float cell update contracted to 8 instructions (FADD +
+// 4 FMUL + 3 FFMA; results within a few ulp of the exact order; the engine re-checks everything near the threshold with
+// an exact kernel).
 // kInline: compute the float row parameters in the kernel instead of reading read_params_kernel's planes (single-pair
 // re-check tasks have no parameter block).
 constexpr int kFlush = 1, kPush = 2, kFast = 4, kInline = 8;
@@ -288,9 +289,13 @@ __device__ __forceinline__ void run_task(const ForwardArgs& a, const Task* tk, T
             for (int j = K - 1; j >= 0; --j) {
                 const T md = j ? M[j - 1] : dM, xd = j ? X[j - 1] : dX, yd = j ? Y[j - 1] : dY;
                 if constexpr (FAST) {
-                    // same formulas, each multiply-add pair contracted: FMUL + 2 FFMA + FMUL, and FMUL + FFMA
-                    const float t5 = __fmaf_rn(yd, pG[j], __fmaf_rn(xd, pG[j], __fmul_rn(md, pMM[j])));
-                    Mn[j] = __fmul_rn(t5, w[j]);
+                    // 8 instructions per cell instead of 12: M = fma(Xd + Yd, pG, Md pMM) w, and FMUL + FFMA for each of X
+                    // and Y.  What counts beside the instructions is their register operands -- the register file feeds
+                    // two per issue slot, a three-register FFMA costs ~1.5 slots (tools/microbench/ffma_regs.cu) -- 19
+                    // here against 24 in the exact order.  (Tried: folding w into pre-multiplied pMM w / pG w tables,
+                    // 7 instructions and 17 operands, needs a second LDS.128 per four rows and saturates the
+                    // shared-memory pipe: 2.74 against 2.92 TCUPS on config 2.)
+                    Mn[j] = __fmul_rn(__fmaf_rn(__fadd_rn(xd, yd), pG[j], __fmul_rn(md, pMM[j])), w[j]);
                     Yn[j] = __fmaf_rn(Y[j], pC[j], __fmul_rn(M[j], pMY[j]));
                 } else {
                     // M = ((Md*pMM + Xd*pGAPM) + Yd*pGAPM) * w        (avx-pairhmm-template.h:188)

@@ -329,7 +329,7 @@ int pmm_pool_create(const int* devices, int n_devices, int contexts_per_device, 
     // sleeping on a blocking event 13 400 -- the wake-up latency costs more than the cores it frees.  PMM_POOL_SYNC=block
     // selects the sleeping wait for hosts with fewer cores than feeder threads.
     if (const char* e = getenv("PMM_POOL_SYNC"))
-        if (!strcmp(e, "block") || !strcmp(e, "hybrid") || !strcmp(e, "spin")) for (pmm_ctx* c : p->ctxs) pmm_set_option(c, "sync", e);
+        if (!strcmp(e, "block") || !strcmp(e, "hybrid") || !strcmp(e, "spin") || !strcmp(e, "auto")) for (pmm_ctx* c : p->ctxs) pmm_set_option(c, "sync", e);
     // feeder threads: the contexts of a device in pairs (ctxs is laid out [rep][device])
     const size_t nd = devs.size();
     for (size_t d = 0; d < nd; ++d)

@@ -478,12 +478,11 @@ def measure_sw(local: int, sm_mhz):
     pairs = sw.haplotype_pairs(1, 2080, ref_len=(250, 500), per_ref=260)
     cells = sum(len(r) * len(a) for r, a in pairs)
     al.align(pairs[:64], 0)
-    best = None
+    best = [float("inf"), float("inf")]                        # kernel ms, whole-call ms: best of five each
     for _ in range(5):
         out = al.align(pairs, 0)
         st = al.stats()
-        if best is None or st["ms_kernel"] < best[0]:
-            best = (st["ms_kernel"], st["ms_total"])
+        best = [min(best[0], st["ms_kernel"]), min(best[1], st["ms_total"])]
     sms = torch.cuda.get_device_properties(local).multi_processor_count
     # ~11.5 ALU-pipe instructions per cell (adds, min/max, funnel shifts), half rate: 23 issue cycles per cell and lane
     bound = sms * 128 / 23.0 * (sm_mhz or 1965.0) * 1e6 * 1e-9

@@ -88,7 +88,7 @@ int  pmm_device_count(void);
  *                       f64_tasks_per_warp tasks per resident warp (default 6), at most f64_max_run haplotypes each (6)
  *   "sync"            = "spin" (default): waits poll the stream, lowest latency for one context per core; "block":
  *                       waits sleep on a blocking event (for hosts with fewer cores than waiting threads); "hybrid": poll
- *                       for 60 us, then sleep.  The pool takes it from the environment variable PMM_POOL_SYNC, the task
+ *                       for 60 us, then sleep; "auto": spin while fewer than cores/16 threads of the process do, else sleep.  The pool takes it from the environment variable PMM_POOL_SYNC, the task
  *                       plugin from its conf key "sync" or PAIRHMM_SYNC                                              */
 int  pmm_set_option(pmm_ctx* ctx, const char* key, const char* value);
 

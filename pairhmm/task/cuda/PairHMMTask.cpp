@@ -49,8 +49,9 @@ void PairHMM::prepare() {
     // the earlier tile's kernels go first wherever two tiles compete for thread-block slots, and the tiles finish in order
     // instead of all at once -- the worker consumes tile k while tile k+1 is still on the GPU.
     // How the task waits for the GPU: several tiles per client and one client per caller thread mean many waiting threads;
-    // they sleep unless told otherwise (conf "sync" or $PAIRHMM_SYNC: spin | block | hybrid).
-    std::string sync = "hybrid";
+    // the first few of the process spin, the rest sleep, unless told otherwise (conf "sync" or $PAIRHMM_SYNC: spin | block |
+    // hybrid | auto).
+    std::string sync = "auto";
     if (const char* e = getenv("PAIRHMM_SYNC")) sync = e;
     get_conf("sync", sync);
     check(pmm_set_option(engine_->ctx, "sync", sync.c_str()), "sync");
