@@ -97,7 +97,10 @@ template <typename T, int K> __host__ __device__ constexpr int min_ctas()
 #ifndef PMM_F32_3CTA_MAXK
 #define PMM_F32_3CTA_MAXK 14
 #endif
-    return sizeof(T) == 8 ? (K <= 6 ? 3 : 2) : K <= PMM_F32_4CTA_MAXK ? 4 : K <= PMM_F32_3CTA_MAXK ? 3 : 2;
+#ifndef PMM_F64_4CTA_MAXK
+#define PMM_F64_4CTA_MAXK 0
+#endif
+    return sizeof(T) == 8 ? (K <= PMM_F64_4CTA_MAXK ? 4 : K <= 6 ? 3 : 2) : K <= PMM_F32_4CTA_MAXK ? 4 : K <= PMM_F32_3CTA_MAXK ? 3 : 2;
 }
 
 // ---- fallback count: the float pass counts the pairs whose result is below 1e-28f the moment the result exists ----

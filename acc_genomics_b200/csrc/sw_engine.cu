@@ -37,16 +37,19 @@ struct Buf {
 };
 }  // namespace
 
+constexpr uint64_t kCigarScratchBytes = 256ull << 20;   // per-chunk scratch rows of the traceback (cigar_cap elements per pair)
+
 struct sw_ctx {
     int device = 0, sm_count = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     std::string err;
     Buf d_seq1, d_seq2, d_pairs, d_bt, d_cigars, d_compact, d_first, d_nelem, d_off, d_score, d_counter;
-    Buf h_stage, h_out;
+    Buf h_stage, h_out, h_cig;
+    uint64_t compact_hint = 16;                   // CIGAR elements per pair the compact array is sized for (grows on overflow)
     uint64_t bt_budget_words = (1ull << 30);      // 4 GiB of backtrack codes per chunk
     sw_stats_t stats{};
-    sw_ctx() { h_stage.pinned = true; h_out.pinned = true; }
+    sw_ctx() { h_stage.pinned = true; h_out.pinned = true; h_cig.pinned = true; }
     int fail(int code, const std::string& m) { err = m; return code; }
     int fail_cuda(cudaError_t e, const char* what) { err = std::string(what) + ": " + cudaGetErrorString(e); return SW_ERR_CUDA; }
 };
@@ -86,7 +89,7 @@ void sw_destroy(sw_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (Buf* b : {&c->d_seq1, &c->d_seq2, &c->d_pairs, &c->d_bt, &c->d_cigars, &c->d_compact, &c->d_first, &c->d_nelem, &c->d_off, &c->d_score, &c->d_counter, &c->h_stage, &c->h_out}) b->release();
+    for (Buf* b : {&c->d_seq1, &c->d_seq2, &c->d_pairs, &c->d_bt, &c->d_cigars, &c->d_compact, &c->d_first, &c->d_nelem, &c->d_off, &c->d_score, &c->d_counter, &c->h_stage, &c->h_out, &c->h_cig}) b->release();
     cudaEventDestroy(c->ev[0]); cudaEventDestroy(c->ev[1]);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -146,8 +149,11 @@ int sw_align_batch(sw_ctx* c, uint32_t n_pairs,
     SW_CUDA(c, c->d_seq1.reserve(ext1)); SW_CUDA(c, c->d_seq2.reserve(ext2));
     SW_CUDA(c, c->h_stage.reserve(ext1 + ext2 + sizeof(PairDesc) * (size_t)n_pairs + 64));
     SW_CUDA(c, c->d_pairs.reserve(sizeof(PairDesc) * (size_t)n_pairs));
-    SW_CUDA(c, c->d_cigars.reserve(sizeof(int2) * (size_t)n_pairs * cigar_cap));
-    SW_CUDA(c, c->d_compact.reserve(sizeof(int2) * (size_t)n_pairs * cigar_cap));
+    // CIGARs are a few elements per pair, not cigar_cap of them (callers pass the longest sequence, ~12 KB per pair): the
+    // compact array is sized from an estimate and the batch repeated with more room if it ever runs over; the per-pair
+    // scratch rows exist per chunk, not per batch (see the chunk loop)
+    const uint64_t compact_cap = std::min<uint64_t>((uint64_t)n_pairs * cigar_cap, std::max<uint64_t>((uint64_t)n_pairs * c->compact_hint, 1u << 16));
+    SW_CUDA(c, c->d_compact.reserve(sizeof(int2) * compact_cap));
     SW_CUDA(c, c->d_first.reserve(sizeof(uint32_t) * (size_t)n_pairs));
     SW_CUDA(c, c->d_nelem.reserve(sizeof(int32_t) * (size_t)n_pairs));
     SW_CUDA(c, c->d_off.reserve(sizeof(int32_t) * (size_t)n_pairs));
@@ -173,7 +179,7 @@ int sw_align_batch(sw_ctx* c, uint32_t n_pairs,
             // blocks of 32 x K rows, every block [word][lane][row of the lane]: rows are padded to whole blocks
             const uint32_t K = pick_rows_per_lane(seq1_len[p]);
             const uint64_t w = (uint64_t)((seq1_len[p] + 32 * K - 1) / (32 * K)) * 32 * K * stride;
-            if (k > first && words + w > c->bt_budget_words) break;
+            if (k > first && (words + w > c->bt_budget_words || (uint64_t)(k - first + 1) * cigar_cap * sizeof(int2) > kCigarScratchBytes)) break;
             hp[k] = PairDesc{seq1_start[p], seq1_len[p], seq2_start[p], seq2_len[p], words, stride, p, K, 0u};
             words += w; ++k;
         }
@@ -181,6 +187,11 @@ int sw_align_batch(sw_ctx* c, uint32_t n_pairs,
         max_words = std::max(max_words, words);
     }
     SW_CUDA(c, c->d_bt.reserve(max_words * sizeof(uint32_t)));
+    {
+        uint64_t most = 1;
+        for (const auto& ch : chunks) most = std::max<uint64_t>(most, ch.second - ch.first);
+        SW_CUDA(c, c->d_cigars.reserve(sizeof(int2) * most * cigar_cap));
+    }
     SW_CUDA(c, cudaMemcpyAsync(c->d_pairs.p, hp, sizeof(PairDesc) * (size_t)n_pairs, cudaMemcpyHostToDevice, s));
 
     mark("staged");
@@ -196,7 +207,7 @@ int sw_align_batch(sw_ctx* c, uint32_t n_pairs,
         a.bt = static_cast<uint32_t*>(c->d_bt.p);
         a.match = w_match; a.mismatch = w_mismatch; a.open = w_open; a.extend = w_extend; a.strategy = overhang_strategy;
         a.cigar_cap = cigar_cap; a.cigars = static_cast<int2*>(c->d_cigars.p);
-        a.compact = static_cast<int2*>(c->d_compact.p); a.compact_count = d_count; a.compact_first = static_cast<uint32_t*>(c->d_first.p);
+        a.compact = static_cast<int2*>(c->d_compact.p); a.compact_cap = (uint32_t)std::min<uint64_t>(compact_cap, 0xffffffffu); a.compact_count = d_count; a.compact_first = static_cast<uint32_t*>(c->d_first.p);
         a.n_elem = static_cast<int32_t*>(c->d_nelem.p); a.offset = static_cast<int32_t*>(c->d_off.p);
         a.score = static_cast<int32_t*>(c->d_score.p);
         a.max_l1 = 0; a.max_l2 = 0;
@@ -212,7 +223,7 @@ int sw_align_batch(sw_ctx* c, uint32_t n_pairs,
     // Results: the per-pair integers and the number of CIGAR elements first, then the compact CIGAR array (a few
     // elements per pair, contiguous) which is scattered into the caller's rows of cigar_cap elements here.
     const size_t sz_i = sizeof(int32_t) * (size_t)n_pairs;
-    SW_CUDA(c, c->h_out.reserve(4 * sz_i + 64 + sizeof(int2) * (size_t)n_pairs * cigar_cap));   // grow-only: worst case once
+    SW_CUDA(c, c->h_out.reserve(4 * sz_i + 64));
     char* ho = static_cast<char*>(c->h_out.p);
     SW_CUDA(c, cudaMemcpyAsync(ho, c->d_nelem.p, sz_i, cudaMemcpyDeviceToHost, s));
     SW_CUDA(c, cudaMemcpyAsync(ho + sz_i, c->d_off.p, sz_i, cudaMemcpyDeviceToHost, s));
@@ -227,8 +238,15 @@ int sw_align_batch(sw_ctx* c, uint32_t n_pairs,
     static_assert(sizeof(sw_cigar_elem_t) == sizeof(int2), "cigar element layout");
     uint32_t total = 0;
     memcpy(&total, ho + 4 * sz_i, sizeof total);
+    if (total > compact_cap) {
+        // more CIGAR elements than the estimate allowed for: remember, and run the batch again with room for all of them
+        c->compact_hint = std::max<uint64_t>(c->compact_hint * 2, ((uint64_t)total + n_pairs - 1) / n_pairs + 1);
+        return sw_align_batch(c, n_pairs, seq1_bytes, seq1_start, seq1_len, seq2_bytes, seq2_start, seq2_len, w_match, w_mismatch,
+                              w_open, w_extend, overhang_strategy, cigar_cap, cigars, n_elem, alignment_offset, score);
+    }
     if (total) {
-        const int2* hc = reinterpret_cast<const int2*>(ho + 4 * sz_i + 64);
+        SW_CUDA(c, c->h_cig.reserve(sizeof(int2) * (size_t)total));
+        const int2* hc = static_cast<const int2*>(c->h_cig.p);
         SW_CUDA(c, cudaMemcpyAsync(const_cast<int2*>(hc), c->d_compact.p, sizeof(int2) * (size_t)total, cudaMemcpyDeviceToHost, s));
         SW_CUDA(c, cudaStreamSynchronize(s));
         const uint32_t* first = reinterpret_cast<const uint32_t*>(ho + 3 * sz_i);

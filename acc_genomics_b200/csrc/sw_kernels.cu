@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 3) sw_align_kernel(const Ar
         // lanes fetch a 32-row x 64-column tile of codes, realigned from step-indexed words to column-indexed ones; then
         // lane r looks at the r-th cell down the diagonal from the current one and a ballot finds how far the diagonal run
         // goes -- one iteration per run or per gap cell instead of one per move (a 400-move walk: ~25 iterations).
-        int2* out = a.cigars + (size_t)pd.index * a.cigar_cap;
+        int2* out = a.cigars + (size_t)p * a.cigar_cap;              // scratch row of this pair within its chunk
         int n = 0;                         // elements written (run-length encoded, still in backward order)
         int cur_state = -1, cur_len = 0;   // the open run
         int raw_ops = 0;                   // getCIGAR's cigarId: number of un-merged operations so far
@@ -409,7 +409,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 3) sw_align_kernel(const Ar
                 // pair instead of cigar_cap); `out` was the scratch row of the backward pass
                 const int stored = min(n, (int)a.cigar_cap);
                 const uint32_t first = atomicAdd(a.compact_count, (uint32_t)stored);
-                for (int x = 0; x < stored; ++x) a.compact[first + x] = out[stored - 1 - x];
+                // (the compact array is sized from an estimate; when it runs over, the host sees the count and repeats the
+                // batch with room for everything)
+                if (first + (uint32_t)stored <= a.compact_cap)
+                    for (int x = 0; x < stored; ++x) a.compact[first + x] = out[stored - 1 - x];
                 a.compact_first[pd.index] = first;
                 a.n_elem[pd.index] = n;
                 a.offset[pd.index] = off;

@@ -38,8 +38,9 @@ struct Args {
     uint32_t*       bt;
     int             match, mismatch, open, extend, strategy;
     uint32_t        cigar_cap;
-    int2*           cigars;              // (length, state): per pair a scratch row of cigar_cap elements (backward order)
+    int2*           cigars;              // (length, state): per pair of the chunk a scratch row of cigar_cap elements (backward order)
     int2*           compact;             // forward-order CIGARs of all pairs back to back, in completion order
+    uint32_t        compact_cap;         // room in `compact`; appends beyond it are counted but not written
     uint32_t*       compact_count;       // elements in `compact` so far (zero at the first launch of a batch)
     uint32_t*       compact_first;       // per pair: where its CIGAR starts in `compact`
     int32_t*        n_elem;

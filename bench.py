@@ -219,6 +219,18 @@ def log(msg: str):
     print(f"[bench +{time.perf_counter() - _T0:7.2f}s] {msg}", file=sys.stderr, flush=True)
 
 
+def max_over_ranks(vals, world: int, device) -> list:
+    """Every timing of the JSON line is the slowest rank's: one all-reduce (MAX) of a float64 vector.  The collective is
+    control plane only (NCCL on the GPU box, gloo in the CPU test); the data path has none."""
+    if world <= 1:
+        return [float(v) for v in vals]
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(v) for v in vals], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t.tolist()]
+
+
 def checker():
     import oracle
     lib = oracle.reference()
@@ -610,10 +622,7 @@ def _main(args, real_stdout):
     vals = [dev_s, e2e_s, e2e_serial_s, plugin["s_per_step"] if plugin else 0.0, plugin["s_per_step_threads3"] if plugin else 0.0]
     for r in per:
         vals += [r["dev_s"], r["e2e_s"]]
-    times = torch.tensor(vals, dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    vals = [float(x) for x in times.tolist()]
+    vals = max_over_ranks(vals, world, "cuda")
     dev_s, e2e_s, e2e_serial_s, p1_s, p3_s = vals[:5]
     for k, r in enumerate(per):
         r["dev_s"], r["e2e_s"] = vals[5 + 2 * k], vals[6 + 2 * k]

@@ -131,3 +131,17 @@ def test_cpp_host_layer(built, sw_checker, tmp_path):
     p = subprocess.run([exe, "cuda:0", str(tmp_path / "pairs.txt")], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stderr
     assert p.stdout.split("\n")[:len(want)] == want
+
+
+def test_fragmented_alignments_overflow_the_cigar_estimate(built, sw_checker):
+    """The compact CIGAR array is sized for 16 elements per pair; noisy long alternates need several times that.  The engine
+    notices, repeats the batch with room for everything, and remembers (no worst-case n_pairs x cigar_cap buffers)."""
+    a = sw.SmithWaterman(0)
+    pairs = sw.haplotype_pairs(77, 48, ref_len=(900, 1400), per_ref=6, sub=0.05, indel=0.04)
+    got = a.align(pairs, 0, cigar_cap=512)
+    assert np.mean([len(c) for _, c, _ in got]) > 20, "not fragmented enough to overflow the estimate"
+    for (r, alt), (off, cig, _) in zip(pairs, got):
+        assert (off, cig) == sw_checker.align(r, alt, 0)
+    # a second, ordinary batch on the same context
+    check(a, sw_checker, sw.haplotype_pairs(78, 64, ref_len=(200, 400), per_ref=8), 0)
+    a.close()

@@ -1,11 +1,12 @@
-"""GPU box: randomized parity fuzz -- random region shapes, multi-region jobs, every entry point, exact and fast mode,
+"""GPU box: randomized parity fuzz -- random region shapes, multi-region jobs, every entry point (staged, serialized,
+read_t/hap_t, GKL testcases, client/worker/task plugin, pool), exact and fast mode,
 PairHMM and Smith-Waterman, each result compared with the oracle (bit-exact where the contract says so).
     python tools/fuzz_gpu.py [seconds] [seed]"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import oracle
-from acc_genomics_b200 import synth, sw
+from acc_genomics_b200 import hostlayer, synth, sw
 from acc_genomics_b200 import batch as B
 from acc_genomics_b200.engine import PairHMMEngine, PairHMMPool
 
@@ -54,6 +55,18 @@ while time.time() - t0 < budget:
     assert same(o2.ravel(), want[0][1].ravel()), ("serialized", it)
     o3, _ = eng.forward_log10_structs(b0)
     assert same(o3.ravel(), want[0][1].ravel()), ("structs", it)
+    # GKL-shaped testcase batch over all regions of the job (pointer-sharing pairs, regions found again by the engine)
+    tc = []
+    for b in regs:
+        reads = [tuple(bytes(x) for x in b.read(k)) for k in range(b.num_read)]
+        haps = [bytes(b.haplotype(k)) for k in range(b.num_hap)]
+        tc += [(r, h) for r in reads for h in haps]
+    o4, nfb4 = eng.forward_log10_testcases(tc)
+    assert same(o4, np.concatenate([w[1].ravel() for w in want])) and nfb4 == nfb, ("testcases", it)
+    # the client path: PairHMMClient + PairHMMWorker over the task plugin, a random number of tiles
+    os.environ["PAIRHMM_WORKER_TILES"] = str(int(rng.integers(1, 6)))
+    o5, nre = hostlayer.worker_forward(b0)
+    assert same(o5, want[0][1].ravel()) and nre == int(want[0][2].sum()), ("worker", it)
     # pool (merging of small jobs included)
     tk = [pool.submit(b) for b in regs]
     for t, w in zip(tk, want):
