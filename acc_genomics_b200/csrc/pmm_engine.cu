@@ -80,6 +80,7 @@ struct pmm_ctx {
     double ref_host_s = 0;              // ... and the host's steady clock at that moment (pmm_get_timeline)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_block = nullptr;     // "sync" = "block": waits sleep on this event instead of spinning on the stream
+    cudaEvent_t ev_poll = nullptr;      // "sync" = "auto": spun on or polled
     bool block_sync = false;
     int spin_us = 0;                    // "sync" = "hybrid": poll this long, then sleep on the blocking event
     bool auto_sync = false;             // "sync" = "auto": spin while few threads of the process do, else sleep
@@ -506,6 +507,7 @@ int pmm_create(int device, pmm_ctx** out)
     }
     for (auto& ev : c->ev) cudaEventCreate(&ev);
     cudaEventCreateWithFlags(&c->ev_block, cudaEventBlockingSync | cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_poll, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_raw, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_lists, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_h2d, cudaEventDisableTiming);
@@ -529,6 +531,7 @@ void pmm_destroy(pmm_ctx* c)
     c->h_in.release(); c->h_out.release();
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     if (c->ev_block) cudaEventDestroy(c->ev_block);
+    if (c->ev_poll) cudaEventDestroy(c->ev_poll);
     if (c->ev_raw) cudaEventDestroy(c->ev_raw);
     if (c->ev_lists) cudaEventDestroy(c->ev_lists);
     if (c->list_stream) cudaStreamDestroy(c->list_stream);
@@ -785,14 +788,22 @@ static int spinner_budget()
 static cudaError_t wait_stream(pmm_ctx* c, cudaStream_t st)
 {
     if (c->auto_sync) {
-        if (g_spinners.fetch_add(1, std::memory_order_relaxed) < spinner_budget()) {
-            const cudaError_t e = cudaStreamSynchronize(st);
+        // Whoever finds a spinner's place free takes it (the earliest waiter, i.e. the job that finishes first); the others
+        // nap and look again -- for the event and for a free place -- so a waiter is promoted as soon as the one ahead of it
+        // is done, and a sleeping thread never costs more than a wake-up of a few tens of microseconds.
+        cudaError_t e = cudaEventRecord(c->ev_poll, st);
+        if (e != cudaSuccess) return e;
+        for (;;) {
+            if (g_spinners.fetch_add(1, std::memory_order_relaxed) < spinner_budget()) {
+                e = cudaEventSynchronize(c->ev_poll);
+                g_spinners.fetch_sub(1, std::memory_order_relaxed);
+                return e;
+            }
             g_spinners.fetch_sub(1, std::memory_order_relaxed);
-            return e;
+            e = cudaEventQuery(c->ev_poll);
+            if (e != cudaErrorNotReady) return e;
+            std::this_thread::sleep_for(std::chrono::microseconds(25));
         }
-        g_spinners.fetch_sub(1, std::memory_order_relaxed);
-        cudaError_t e = cudaEventRecord(c->ev_block, st);
-        return e != cudaSuccess ? e : cudaEventSynchronize(c->ev_block);
     }
     if (!c->block_sync) return cudaStreamSynchronize(st);
     cudaError_t e = cudaEventRecord(c->ev_block, st);

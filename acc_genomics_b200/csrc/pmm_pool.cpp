@@ -67,7 +67,10 @@ struct pmm_pool {
     std::vector<uint64_t> cells_per_device, jobs_per_device;
     int n_devices = 0;
     std::vector<int> devices;
-    bool merge = true;                  // feeders merge small waiting jobs into one GPU job
+    // Feeders can merge small waiting jobs into one GPU job (pmm_pool_set_merge).  Off by default: with two contexts per
+    // feeder and several feeders per GPU, single-region jobs of 4 000 pairs stream at 1 910-1 940 GCUPS unmerged against
+    // 1 090-1 630 merged (the host copies of merging cost more than the launches they save; tools/small_pool.py).
+    bool merge = false;
     uint64_t merged_batches = 0;
     bool tracing = false;               // pmm_pool_trace: one record per GPU job
     std::vector<pmm_pool_trace_t> trace;

@@ -22,7 +22,7 @@ The JSON line
   roofline      float forward kernel vs the measured FP32 issue rate (12 FP32 instr per cell)
   roofline_f64  double re-run vs the measured FP64 issue rate (12 DP instr per cell of the re-run pairs)
   per_config    the other BASELINE.json shapes (cfg1, 3, 4, a 5-slice): value, e2e, kernel fractions, fallback share,
-                parity, fast mode -- 5 steps each
+                parity, fast mode -- 5 steps each (more for the small config 1: about 20 ms of timed work)
   queue         rank 0 only: the cfg5 stream through ONE pmm_pool over all N GPUs (north_star's host work queue), the same
                 stream on one GPU in the same run, efficiency, per-GPU idle fraction from the pool's timeline
   cpu_baseline  the reference's AVX implementation (oracle/_ref) on this box's host cores -- reported, not the target
@@ -362,6 +362,9 @@ def measure_config(gpu: Gpu, cfg: int, scale: float, steps: int, fast: bool):
     job = eng.stage(batches)
     for _ in range(3):
         eng.launch()
+    # a small configuration (config 1 is 0.13 ms per step) gets more steps: about 20 ms of timed work, at least `steps`
+    probe = gpu.timed_launches(2) / 2
+    steps = int(max(steps, min(200, 0.02 / max(probe, 1e-6))))
     dev_s = gpu.timed_launches(steps)
     f32_ms, fb_ms = gpu.kernel_ms(min(5, steps))
     raw, out, mask, nfb = gpu.results()

@@ -167,8 +167,9 @@ int  pmm_get_timeline(pmm_ctx* ctx, pmm_timeline_t* out);
  * tiles to client_->start() one after another) and the per-PU balancer (interface/PairHMMFpgaInterface.cpp:67-170).
  *   pmm_pool_submit_flat : same layout as pmm_stage_flat (regions == NULL: one region of everything); the input
  *                          arrays and out_log10 are borrowed until pmm_pool_wait(ticket) returns.  Thread-safe.
- * Small jobs that are waiting together are merged by the feeder into one multi-region GPU job (up to about 3e9 cells or
- * 64 jobs) and their results split again -- a stream of small active regions then runs at the rate of large ones.
+ * On request (pmm_pool_set_merge) small jobs that are waiting together are merged by the feeder into one multi-region GPU
+ * job (up to about 3e9 cells or 64 jobs) and their results split again; off by default, the contexts' concurrency already
+ * streams single-region jobs at the rate of large ones.
  *   pmm_pool_wait        : blocks until that job is done; returns the job's status, the number of pairs that took
  *                          the double re-run and the device that ran it.  Each ticket is waited for exactly once. */
 typedef struct pmm_pool pmm_pool;
@@ -182,7 +183,7 @@ int  pmm_pool_submit_flat(pmm_pool* pool, uint32_t num_read, const uint32_t* rea
                           uint32_t num_region, const pmm_region_t* regions,
                           double* out_log10, uint64_t out_capacity, uint64_t* ticket);
 int  pmm_pool_wait(pmm_pool* pool, uint64_t ticket, uint64_t* n_fallback, int* device);
-/* on = 1 / 0 switches the merging of small waiting jobs (default on), on < 0 leaves it; merged_batches (may be NULL)
+/* on = 1 / 0 switches the merging of small waiting jobs (default off), on < 0 leaves it; merged_batches (may be NULL)
  * receives how many merged GPU jobs have run so far. */
 int  pmm_pool_set_merge(pmm_pool* pool, int on, uint64_t* merged_batches);
 /* Jobs and cells completed so far by the slot-th device of the pool (0 <= slot < pmm_pool_num_devices). */

@@ -49,6 +49,7 @@ def test_small_jobs_are_merged_and_split_again(built, checker):
     own results and its own fallback count."""
     from acc_genomics_b200.engine import PairHMMPool
     pool = PairHMMPool(devices=[0], contexts_per_device=1)
+    pool.set_merge(True)                                                 # off by default
     regions = synth.config(5, scale=0.016, seed=12)                      # 40 regions
     regions += [synth.config(3, scale=0.02, seed=13)[0]]                 # one fallback-heavy region
     want = [checker.batch(b, threads=8) for b in regions]

@@ -16,7 +16,7 @@ rng = np.random.Generator(np.random.PCG64(seed))
 chk = oracle.reference() or oracle.port()
 swchk = oracle.sw_reference() or oracle.sw_port()
 eng = PairHMMEngine(0); fast = PairHMMEngine(0); fast.set_option("mode", "fast")
-pool = PairHMMPool(devices=[0], contexts_per_device=2)
+pool = PairHMMPool(devices=[0], contexts_per_device=2); pool.set_merge(True)
 al = sw.SmithWaterman(0)
 t0 = time.time(); it = 0; pairs = 0; swpairs = 0
 
