@@ -206,6 +206,8 @@ int stage_common(pmm_ctx* c, uint32_t num_read, const uint32_t* read_off, uint32
         if (arena_err != cudaSuccess) return c->fail_cuda(arena_err, "input arena");
         if (rc) return c->fail(rc, perr);
     }
+    static const bool trace = getenv("PMM_TRACE_STAGE") != nullptr;       // phase times of staging on stderr
+    const auto t_plan = std::chrono::steady_clock::now();
     const uint32_t max_hap = plan.max_hap_len;
     const uint64_t pairs = plan.pairs, cells = plan.cells;
     const std::vector<RegionDesc>& rdesc = plan.regions;
@@ -232,6 +234,7 @@ int stage_common(pmm_ctx* c, uint32_t num_read, const uint32_t* read_off, uint32
     memcpy(hb + c->off_groups, plan.groups.data(), sz_groups);
     c->num_groups = (uint32_t)plan.groups.size();
 
+    const auto t_pack = std::chrono::steady_clock::now();
     // ---- device buffers -------------------------------------------------------------------------------------
     const size_t stream_bytes = kStreamFrontPad + (size_t)pos + 1 + kStreamTailPad;
     PMM_CUDA(c, c->d_stream.reserve(stream_bytes));
@@ -277,6 +280,11 @@ int stage_common(pmm_ctx* c, uint32_t num_read, const uint32_t* read_off, uint32
     c->stats = pmm_stats_t{};
     c->stats.pairs = pairs; c->stats.cells = cells; c->stats.h2d_bytes = arena; c->stats.f32_tasks = c->num_tasks;
     c->stats.ms_stage = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (trace) {
+        auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+        fprintf(stderr, "[stage] %u reads x %u haps, %zu tasks: plan %.0f us, pack %.0f us, reserve + enqueue %.0f us\n", num_read, num_hap,
+                (size_t)plan.num_tasks, us(t0, t_plan), us(t_plan, t_pack), us(t_pack, std::chrono::steady_clock::now()));
+    }
     c->staged = true;
     return PMM_OK;
 }

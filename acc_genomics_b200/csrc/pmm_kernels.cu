@@ -20,7 +20,8 @@
 //   * The match/mismatch emission weight is not selected per cell (that would cost a LOP3 + FSEL issue slot each;
 //     the measured issue rate is 1 instr/clk/SMSP for FP32 and ALU alike, tools/microbench/issue_mix2.cu): each
 //     warp stages a [5 classes][K rows] weight table for its reads in shared memory, laid out so that one
-//     conflict-free LDS.128 per 4 rows fetches the weights for whatever haplotype base the lane is looking at.
+//     LDS.128 per 4 rows fetches the weights for whatever haplotype base the lane is looking at (16 bytes per lane,
+//     consecutive lanes consecutive: the 512 bytes of a warp take the minimum of four wavefronts).
 //   * Steady-state steps are branch-free; only the W steps around a separator run the checked variant.
 //   * The AVX code's stripe initialisation feeds M[r-1][1] into Y[r][1] for the first row of every 8-row stripe
 //     (avx-pairhmm-template.h:171-176); that value is exactly 0 for r >= 3, so there is nothing to reproduce.

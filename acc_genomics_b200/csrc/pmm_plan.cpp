@@ -14,7 +14,21 @@ namespace pmm {
 
 // Maximise useful FP work per issue slot, 12*R / (W * step_cost(K)), subject to R + 1 <= K * W (one boundary row),
 // with a mild penalty for variants whose register count lowers occupancy.
+static Variant pick_variant_uncached(int R);
+
 Variant pick_variant(int R)
+{
+    // one answer per read length: looked up, not searched, for every read group of every job
+    constexpr int kMemo = 1024;
+    static const std::vector<Variant> memo = [] {
+        std::vector<Variant> m(kMemo);
+        for (int r = 0; r < kMemo; ++r) m[r] = pick_variant_uncached(r);
+        return m;
+    }();
+    return R >= 0 && R < kMemo ? memo[R] : pick_variant_uncached(R);
+}
+
+static Variant pick_variant_uncached(int R)
 {
     Variant best{kStripedK, 32, true};
     double best_eff = -1.0;
@@ -157,18 +171,38 @@ int plan_job(uint32_t num_read, const uint32_t* read_off, uint32_t num_hap, cons
     auto vkey = [](const Variant& v) { return (v.striped ? 1 << 20 : 0) + v.K * v.W * 64 + v.W; };
     std::stable_sort(gorder.begin(), gorder.end(), [&](uint32_t x, uint32_t y) { return vkey(groups[x].v) > vkey(groups[y].v); });
 
-    // ---- pass A: group descriptors, launch segments, and the cost of every task (in generation order) -------------
-    // Cost = steps of the wavefront = haplotype bases + separators of the run.
-    plan.groups.reserve(groups.size());
-    std::vector<uint32_t> cost;
-    cost.reserve(std::min<uint64_t>(group_haps, 1u << 24));
-    auto runs_of = [&](const Group& gr, const RegionDesc& r) {
-        const uint32_t hpt = gr.v.striped ? 1u : std::min(plan.haps_per_task, r.nhaps);
-        return (r.nhaps + hpt - 1) / hpt;                             // runs of near-equal length
+    // ---- runs of every region: all groups of a region walk the same cuts of its haplotypes, so the cuts, their costs
+    //      (steps of the wavefront = haplotype bases + separators of the run) and, per launch, their cost classes are
+    //      worked out once per region -- per task only a table lookup and one 48-byte store remain (16 000 tasks of
+    //      config 2: 0.39 -> 0.1 ms of the host's staging time). mode 0: runs of haps_per_task, mode 1: one haplotype
+    //      per task (striped reads) ------------------------------------------------------------------------------------
+    struct RunTable { uint32_t first = 0, count = 0; };               // slice of run_h0 / run_cost (run_h0 has count + 1 entries)
+    std::vector<RunTable> rt(2 * (size_t)num_region);
+    std::vector<uint32_t> run_h0, run_cost;
+    std::vector<uint8_t> run_cls;                                      // class of every run for the launch being laid out
+    auto table_of = [&](uint32_t region, bool striped) -> const RunTable& {
+        RunTable& t = rt[2 * (size_t)region + (striped ? 1 : 0)];
+        if (t.count == 0) {
+            const RegionDesc& r = plan.regions[region];
+            const uint32_t hpt = striped ? 1u : std::min(plan.haps_per_task, r.nhaps);
+            const uint32_t nruns = (r.nhaps + hpt - 1) / hpt;          // runs of near-equal length
+            const uint32_t* ho = hap_off + r.hap_first;
+            t.first = (uint32_t)run_h0.size(); t.count = nruns;
+            for (uint32_t run = 0; run <= nruns; ++run) run_h0.push_back((uint32_t)((uint64_t)r.nhaps * run / nruns));
+            run_cost.resize(run_h0.size());
+            for (uint32_t run = 0; run < nruns; ++run) {
+                const uint32_t h0 = run_h0[t.first + run], h1 = run_h0[t.first + run + 1];
+                run_cost[t.first + run] = ho[h1] - ho[h0] + (h1 - h0);
+            }
+        }
+        return t;
     };
+
+    // ---- pass A: group descriptors and launch segments -------------------------------------------------------------
+    plan.groups.reserve(groups.size());
+    uint64_t ntasks = 0;
     for (uint32_t gi : gorder) {
         const Group& gr = groups[gi];
-        const RegionDesc& r = plan.regions[gr.region];
         // row-parameter block of the group: every slot of the warp gets one, used or not
         GroupDesc gd{};
         for (uint32_t z = 0; z < (uint32_t)kMaxGroups; ++z) gd.read[z] = gr.reads[z];
@@ -182,16 +216,13 @@ int plan_job(uint32_t num_read, const uint32_t* read_off, uint32_t num_hap, cons
         gd.param_off = (uint32_t)plan.param_floats;
         plan.param_floats += slots * gd.nstripes * kParamPlanes * kw;
         plan.groups.push_back(gd);
-        if (plan.segs.empty() || !(plan.segs.back().v == gr.v)) plan.segs.push_back(LaunchSeg{gr.v, (uint32_t)cost.size(), 0});
-        const uint32_t nruns = runs_of(gr, r);
-        const uint32_t* ho = hap_off + r.hap_first;
-        for (uint32_t run = 0; run < nruns; ++run) {
-            const uint32_t h0 = (uint32_t)((uint64_t)r.nhaps * run / nruns), h1 = (uint32_t)((uint64_t)r.nhaps * (run + 1) / nruns);
-            cost.push_back(ho[h1] - ho[h0] + (h1 - h0));
-        }
+        if (plan.segs.empty() || !(plan.segs.back().v == gr.v)) plan.segs.push_back(LaunchSeg{gr.v, (uint32_t)ntasks, 0});
+        const uint32_t nruns = table_of(gr.region, gr.v.striped).count;
         plan.segs.back().task_count += nruns;
+        ntasks += nruns;
+        if (ntasks >= (1ull << 31)) { err = "more than 2^31 warp-tasks in one job: split it"; return PMM_ERR_INVALID; }
     }
-    plan.num_tasks = cost.size();
+    plan.num_tasks = ntasks;
 
     // ---- where the tasks go: the caller's buffer (the engine's pinned staging arena) or plan.tasks ------------------
     Task* dst = nullptr;
@@ -199,40 +230,65 @@ int plan_job(uint32_t num_read, const uint32_t* read_off, uint32_t num_hap, cons
         dst = task_dst(plan);
         if (!dst) { err = "no room for the task list"; return PMM_ERR_INVALID; }
     } else {
-        plan.tasks.resize(cost.size());
+        plan.tasks.resize(ntasks);
         dst = plan.tasks.data();
     }
 
     // ---- pass B: write every task at its final position.  Longest tasks first inside each launch (warps pull tasks
     //      in order, so the kernel's tail is made of the shortest ones): a counting sort on 64 cost classes, stable,
     //      linear in the number of tasks, no intermediate copy. -----------------------------------------------------------
-    std::vector<uint32_t> cmax(plan.segs.size(), 1);
-    std::vector<uint32_t> next(plan.segs.size() * 65, 0);              // per launch: write cursor of each cost class
+    run_cls.resize(run_cost.size());
+    std::vector<uint32_t> regs_in_seg;                                  // regions met in the launch being laid out ...
+    std::vector<uint32_t> groups_of(num_region, 0);                     // ... and how many of its groups each has
+    size_t gk = 0;
     for (size_t sg = 0; sg < plan.segs.size(); ++sg) {
         const LaunchSeg& seg = plan.segs[sg];
-        for (uint32_t k = 0; k < seg.task_count; ++k) cmax[sg] = std::max(cmax[sg], cost[seg.task_first + k]);
-        uint32_t* nx = next.data() + sg * 65;
-        for (uint32_t k = 0; k < seg.task_count; ++k) nx[63 - (uint32_t)((uint64_t)cost[seg.task_first + k] * 63 / cmax[sg]) + 1]++;
-        nx[0] = seg.task_first;
-        for (int b = 0; b < 64; ++b) nx[b + 1] += nx[b];
-    }
-    size_t sg = 0, k = 0;                                               // running launch index and task sequence number
-    for (size_t gk = 0; gk < gorder.size(); ++gk) {
-        const Group& gr = groups[gorder[gk]];
-        const RegionDesc& r = plan.regions[gr.region];
-        const GroupDesc& gd = plan.groups[gk];
-        const uint32_t nruns = runs_of(gr, r);
-        uint32_t rowbase[kMaxGroups];
-        for (uint32_t z = 0; z < (uint32_t)kMaxGroups; ++z) rowbase[z] = z < gr.n ? r.out_first + (gr.reads[z] - r.read_first) * r.nhaps : 0;
-        for (uint32_t run = 0; run < nruns; ++run, ++k) {
-            while (k >= (size_t)plan.segs[sg].task_first + plan.segs[sg].task_count) ++sg;
-            const uint32_t h0 = (uint32_t)((uint64_t)r.nhaps * run / nruns), h1 = (uint32_t)((uint64_t)r.nhaps * (run + 1) / nruns);
-            Task& t = dst[next[sg * 65 + 63 - (uint32_t)((uint64_t)cost[k] * 63 / cmax[sg])]++];
-            for (uint32_t z = 0; z < (uint32_t)kMaxGroups; ++z) {
-                t.read[z] = gr.reads[z];
-                t.out_base[z] = z < gr.n ? rowbase[z] + h0 : 0;
+        const bool striped = seg.v.striped;
+        // the groups of this launch: gorder[gk .. gend)
+        size_t gend = gk;
+        uint32_t cmax = 1;
+        regs_in_seg.clear();
+        for (uint64_t tasks = 0; gend < gorder.size() && tasks < seg.task_count; ++gend) {
+            const Group& gr = groups[gorder[gend]];
+            const RunTable& t = table_of(gr.region, striped);
+            if (groups_of[gr.region]++ == 0) {
+                regs_in_seg.push_back(gr.region);
+                for (uint32_t run = 0; run < t.count; ++run) cmax = std::max(cmax, run_cost[t.first + run]);
             }
-            t.hap_first = r.hap_first + h0; t.nhaps = h1 - h0; t.nreads = gr.n; t.param_off = gd.param_off;
+            tasks += t.count;
+        }
+        uint32_t next[65] = {0};                                        // write cursor of each cost class
+        for (uint32_t region : regs_in_seg) {
+            const RunTable& t = table_of(region, striped);
+            for (uint32_t run = 0; run < t.count; ++run) {
+                const uint8_t cls = (uint8_t)(63 - (uint32_t)((uint64_t)run_cost[t.first + run] * 63 / cmax));
+                run_cls[t.first + run] = cls;
+                next[cls + 1] += groups_of[region];
+            }
+            groups_of[region] = 0;
+        }
+        next[0] = seg.task_first;
+        for (int b = 0; b < 64; ++b) next[b + 1] += next[b];
+        for (; gk < gend; ++gk) {
+            const Group& gr = groups[gorder[gk]];
+            const RegionDesc& r = plan.regions[gr.region];
+            const GroupDesc& gd = plan.groups[gk];
+            const RunTable& rtab = table_of(gr.region, striped);
+            const uint32_t* h0s = run_h0.data() + rtab.first;
+            const uint8_t* cls = run_cls.data() + rtab.first;
+            Task proto;                                                  // everything of the task but its run
+            for (uint32_t z = 0; z < (uint32_t)kMaxGroups; ++z) {
+                proto.read[z] = gr.reads[z];
+                proto.out_base[z] = z < gr.n ? r.out_first + (gr.reads[z] - r.read_first) * r.nhaps : 0;
+            }
+            proto.nreads = gr.n; proto.param_off = gd.param_off;
+            for (uint32_t run = 0; run < rtab.count; ++run) {
+                const uint32_t h0 = h0s[run], h1 = h0s[run + 1];
+                Task& t = dst[next[cls[run]]++];
+                t = proto;
+                for (uint32_t z = 0; z < gr.n; ++z) t.out_base[z] += h0;
+                t.hap_first = r.hap_first + h0; t.nhaps = h1 - h0;
+            }
         }
     }
     return PMM_OK;

@@ -7,6 +7,8 @@ from acc_genomics_b200 import synth
 from acc_genomics_b200.engine import PairHMMEngine
 
 eng = PairHMMEngine(0)
+for kv in os.environ.get("PMM_OPTS", "").split():
+    eng.set_option(*kv.split("="))
 cases = [("cfg5 region 100x40", synth.config(5, scale=0.0004)[0]), ("cfg1 128x32", synth.config(1)[0])]
 rng = np.random.Generator(np.random.PCG64(3))
 cases.append(("toy 10x5", synth.region(rng, [151] * 10, [400] * 5)))
