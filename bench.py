@@ -63,7 +63,7 @@ def parse():
     ap.add_argument("--no-queue", action="store_true", help="skip the work-queue block")
     ap.add_argument("--no-plugin", action="store_true", help="skip the plugin-path e2e")
     ap.add_argument("--no-sw", action="store_true", help="skip the Smith-Waterman block (SURVEY.md section 8f row 4)")
-    ap.add_argument("--queue-jobs-per-gpu", type=int, default=96)
+    ap.add_argument("--queue-jobs-per-gpu", type=int, default=192)
     ap.add_argument("--timeline", default="", help="write the pool's per-job timeline of the queue run to this .jsonl")
     return ap.parse_args()
 
