@@ -234,3 +234,15 @@ def test_stage_launch_stage_without_fetch(engine, checker):
     raw1 = engine.fetch_raw(); m = engine.fetch_fallback_mask(); out2, _ = engine.fetch_log10(); raw2 = engine.fetch_raw()
     assert_bits_equal(raw1, raw2, "raw twice"); assert_bits_equal(out, out2, "log10 twice")
     assert np.array_equal(m, raw1 < np.float32(1e-28))
+
+
+@pytest.mark.parametrize("key,value", [("priority", "0"), ("priority", "3"), ("sync", "auto"), ("sync", "hybrid"), ("sync", "block")])
+def test_stream_priority_and_wait_modes_do_not_change_results(built, checker, key, value):
+    from acc_genomics_b200.engine import PairHMMEngine
+    e = PairHMMEngine(0)
+    e.set_option(key, value)
+    b = synth.config(3, seed=91, scale=0.04)[0]
+    raw, out, mask = e.forward(b)
+    raw_r, out_r, fb_r = checker.batch(b, threads=8)
+    assert_bits_equal(raw, raw_r, f"{key}={value} raw"); assert_bits_equal(out, out_r, f"{key}={value} log10")
+    e.close()

@@ -94,3 +94,21 @@ def test_bad_job_fails_alone_and_trace_records_the_rest(built, checker):
         assert r["d_start"] <= r["d_f32_end"] <= r["d_end"]
         assert r["t_take"] - 0.05 <= r["d_start"] and r["d_end"] <= r["t_fetched"] + 0.05      # device and host clocks line up
     pool.close()
+
+
+@pytest.mark.parametrize("contexts,sync", [(3, "spin"), (4, "auto"), (2, "block"), (5, "hybrid")])
+def test_every_feeder_shape_and_wait_mode_gives_the_same_answers(built, checker, contexts, sync, monkeypatch):
+    """Feeders drive their contexts in pairs (an odd one out alone); waits spin, sleep, poll or pick by themselves: the
+    results are the oracle's either way, and every job is accounted for once."""
+    from acc_genomics_b200.engine import PairHMMPool
+    monkeypatch.setenv("PMM_POOL_SYNC", sync)
+    pool = PairHMMPool(devices=[0], contexts_per_device=contexts)
+    regions = synth.config(5, scale=0.012, seed=31)                      # 30 ragged regions
+    jobs = [regions[k:k + 3] for k in range(0, len(regions), 3)] * 2     # 20 jobs, every one twice
+    want = [np.concatenate([checker.batch(b, threads=8)[1].ravel() for b in j]) for j in jobs[:10]] * 2
+    tickets = [pool.submit(j) for j in jobs]
+    for w, t in zip(want, tickets):
+        out, _, dev = pool.wait(t)
+        assert_bits_equal(out, w, f"{contexts} contexts, {sync}")
+    assert sum(d["jobs"] for d in pool.device_load()) == len(jobs)
+    pool.close()
