@@ -110,7 +110,7 @@ template <typename T, int K> __host__ __device__ constexpr int min_ctas()
 // other from the instruction caches and the double tasks run at the float kernel's lower occupancy.)
 __device__ __forceinline__ void count_fallback(const FallbackQueue& fq)
 {
-    // The pair itself is found again by build_fallback_kernel's scan of the results (which groups the failing pairs of
+    // The pair itself is found again by fallback_scan_kernel's scan of the results (which groups the failing pairs of
     // a read into one task); the float pass only keeps the total, which sizes those tasks.
     atomicAdd(fq.reserve, 1u);
 }
@@ -143,7 +143,7 @@ constexpr int kFlush = 1, kPush = 2, kFast = 4, kInline = 8;
 // kFlush -- the case where x86 flush-to-zero of intermediate products may have changed the reference's result.
 constexpr int kRetry = 16;
 // kList (double re-run): the task's haplotypes are not a run of consecutive ones but entries hap_first .. hap_first +
-// nhaps - 1 of a.hap_list (the failing haplotypes of one read, build_fallback_kernel).  The wavefront still flows from
+// nhaps - 1 of a.hap_list (the failing haplotypes of one read, fallback_scan_kernel).  The wavefront still flows from
 // one haplotype into the next; a lane re-points its stream pointer when it crosses a separator.
 constexpr int kList = 32;
 

@@ -56,7 +56,7 @@ struct ForwardArgs {
 };
 
 // What the float pass reports about results below 1e-28f (PairHMMWorker.cpp:176): their number (the pairs themselves
-// are found again by build_fallback_kernel) and, in fast mode, the pairs too close to the threshold to decide.
+// are found again by fallback_scan_kernel) and, in fast mode, the pairs too close to the threshold to decide.
 struct FallbackQueue {
     uint32_t* reserve;       // results below `lo` so far (== fallback count when the float pass is done)
     uint32_t  capacity;      // room in recheck_tasks
@@ -102,7 +102,7 @@ cudaError_t launch_forward_f32(int K, int W, bool striped, bool fast, const Forw
 // Exact float re-run of the single-pair tasks on the re-check list (fast mode), overwriting their results.
 cudaError_t launch_recheck_f32(const ForwardArgs& a, const FallbackQueue& fq, int ctas, cudaStream_t s);
 int recheck_f32_ctas_per_sm();
-// Double re-run of build_fallback_kernel's tasks, K in {4, 5, 6, 8} rows per lane from pick_f64_rows().  Results below
+// Double re-run of the tasks fallback_tasks_kernel wrote, K in {4, 5, 6, 8} rows per lane from pick_f64_rows().  Results below
 // a.tiny_threshold are recomputed in the same kernel with x86 flush-to-zero emulated on every product.
 cudaError_t launch_forward_f64(int K, bool striped, const ForwardArgs& a, int ctas, cudaStream_t s);
 int pick_f64_rows(uint32_t max_read_len);

@@ -16,6 +16,8 @@ struct RegionDesc { uint32_t read_first, nreads, hap_first, nhaps, out_first, ro
 
 // One unit of work for one warp.  Group g (lanes g*W .. g*W+W-1) owns read[g]; all groups walk the same run of
 // haplotypes [hap_first, hap_first + nhaps).  The result for (read[g], hap_first + n) goes to out[out_base[g] + n].
+// List tasks (the double re-run): one read; hap_first indexes the fallback list, whose entries hap_first .. hap_first +
+// nhaps - 1 name the haplotypes, and out_base[0] is the first of the task's slots (= hap_first).
 struct Task {
     uint32_t read[kMaxGroups];
     uint32_t out_base[kMaxGroups];
