@@ -39,7 +39,13 @@ namespace {
 #ifndef PMM_STEADY_UNROLL
 #define PMM_STEADY_UNROLL 4
 #endif
-constexpr int kSteadyUnroll = PMM_STEADY_UNROLL;     // steps per trip of the branch-free loop
+constexpr int kSteadyUnrollF32 = PMM_STEADY_UNROLL;  // steps per trip of the branch-free loop
+// the double kernel is bound by the latency of its dependent DP chains, not by issue slots: a longer trip gives ptxas
+// more independent work to put between them (measured on config 3: 2 steps 2.36 ms, 4 steps 2.30, 8 steps 2.28)
+#ifndef PMM_STEADY_UNROLL_F64
+#define PMM_STEADY_UNROLL_F64 8
+#endif
+constexpr int kSteadyUnrollF64 = PMM_STEADY_UNROLL_F64;
 
 __device__ __forceinline__ int base_class(unsigned ch)
 {
@@ -439,6 +445,7 @@ __device__ __forceinline__ void run_task(const ForwardArgs& a, const Task* tk, T
             fetch_hap(hn);                    // for the next window, a whole haplotype from now
             int send = next_sep < Tsteps ? next_sep : Tsteps;
             // kSteadyUnroll steps per trip: the element loads use one pointer with immediate offsets
+            constexpr int kSteadyUnroll = kIsFloat ? kSteadyUnrollF32 : kSteadyUnrollF64;
             const uint8_t* q = sp + t;
             #pragma unroll 1
             for (; t + kSteadyUnroll <= send; t += kSteadyUnroll, q += kSteadyUnroll) {
