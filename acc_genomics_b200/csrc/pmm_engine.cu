@@ -67,18 +67,32 @@ struct PinBuf {
 
 }  // namespace
 
+// What one launch produces, twice per context: launch i + 1's float pass runs while launch i's double re-run is still on
+// the GPU (on its own stream), so the two must not share results, fallback lists, control words or the pinned block the
+// results are copied to.  A fetch always refers to the set of the last launch.
+struct ResultSet {
+    DevBuf d_raw, d_fb_tasks, d_fb_idx, d_fb_hap, d_fb_rows, d_dres, d_ctrl;
+    PinBuf h_out;                       // control words | raw floats | fallback indices | doubles
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};    // launch starts, float pass over, double re-run over
+    cudaEvent_t ev_raw = nullptr, ev_lists = nullptr;   // the copies out of this set are over (its next user waits for them)
+};
+
 struct pmm_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t f64_stream = nullptr;  // fallback builders + double re-run: next to the following launch's float pass
     cudaStream_t copy_stream = nullptr; // D2H of the raw floats as soon as the float pass is over, under the double pass
     cudaStream_t list_stream = nullptr; // D2H of the control words and the fallback list behind the double pass
-    cudaEvent_t ev_raw = nullptr, ev_lists = nullptr;   // recorded after those copies; the next launch waits for them
+    ResultSet rs[2];
+    int cur = 0;                        // set of the last launch
+    ResultSet& R() { return rs[cur]; }
+    const ResultSet& R() const { return rs[cur]; }
     cudaEvent_t ev_h2d = nullptr;       // recorded after the input arena's H2D copy; the next stage waits before repacking
     bool h2d_pending = false;
     cudaEvent_t ev_ref = nullptr;       // recorded and waited for in pmm_create: origin of the context's device timeline ...
     double ref_host_s = 0;              // ... and the host's steady clock at that moment (pmm_get_timeline)
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_probe = nullptr;     // issue-rate probes
     cudaEvent_t ev_block = nullptr;     // "sync" = "block": waits sleep on this event instead of spinning on the stream
     cudaEvent_t ev_poll = nullptr;      // "sync" = "auto": spun on or polled
     bool block_sync = false;
@@ -93,6 +107,7 @@ struct pmm_ctx {
     Variant force{0, 0, false};         // "force_variant" option (tuning sweeps): K,W of the float kernel
     int f64_tasks_per_warp = 6;         // "f64_tasks_per_warp": tasks the double re-run aims at per resident warp ...
     int f64_max_run = 6;                // "f64_max_run": ... and the most haplotypes it puts into one task (tools/f64_sweep.py)
+    bool overlap = true;                // "overlap": consecutive launches overlap by one pass (off: a launch ends with its own re-run)
 
     // device-resident tables
     DevBuf tables;
@@ -100,8 +115,7 @@ struct pmm_ctx {
 
     // job state
     PinBuf h_in;  DevBuf d_in;          // one arena: read blob | descs | hap blob | descs | spos | tasks | regions
-    DevBuf d_params, d_stream, d_iyf, d_iyd, d_raw, d_fb_tasks, d_fb_idx, d_fb_hap, d_fb_rows, d_tiny_tasks, d_dres, d_ctrl, d_scratch, d_probe;
-    PinBuf h_out;                       // raw floats | fb idx | dres
+    DevBuf d_params, d_stream, d_iyf, d_iyd, d_tiny_tasks, d_scratch, d_scratch64, d_probe;
     size_t off_rblob = 0, off_rdesc = 0, off_hblob = 0, off_hdesc = 0, off_spos = 0, off_tasks = 0, off_regions = 0, off_groups = 0;
     uint32_t num_groups = 0;
     uint32_t num_read = 0, num_hap = 0, num_region = 0, num_tasks = 0, num_rows = 0;
@@ -170,6 +184,9 @@ int stage_common(pmm_ctx* c, uint32_t num_read, const uint32_t* read_off, uint32
     // the pinned input arena is about to be repacked: the previous job's H2D copy out of it must be over
     // (stage, launch, stage with no fetch in between)
     if (c->h2d_pending) { PMM_CUDA(c, cudaEventSynchronize(c->ev_h2d)); c->h2d_pending = false; }
+    // ... and the device-side inputs are about to be overwritten: the double re-runs of earlier launches read them on
+    // their own stream
+    for (ResultSet& r : c->rs) PMM_CUDA(c, cudaStreamWaitEvent(c->stream, r.ev[2], 0));
     int rc = ensure_tables(c);
     if (rc) return rc;
 
@@ -241,23 +258,26 @@ int stage_common(pmm_ctx* c, uint32_t num_read, const uint32_t* read_off, uint32
     PMM_CUDA(c, c->d_params.reserve(sizeof(float) * plan.param_floats));
     PMM_CUDA(c, c->d_iyf.reserve(sizeof(float) * num_hap));
     PMM_CUDA(c, c->d_iyd.reserve(sizeof(double) * num_hap));
-    PMM_CUDA(c, c->d_raw.reserve(sizeof(float) * pairs));
-    PMM_CUDA(c, c->d_fb_tasks.reserve(sizeof(Task) * pairs));
     if (c->fast) PMM_CUDA(c, c->d_tiny_tasks.reserve(sizeof(Task) * pairs));     // re-check list of the guard band
-    PMM_CUDA(c, c->d_fb_idx.reserve(sizeof(uint32_t) * pairs));
-    PMM_CUDA(c, c->d_fb_hap.reserve(sizeof(uint32_t) * pairs));
-    PMM_CUDA(c, c->d_fb_rows.reserve(sizeof(uint32_t) * 2 * plan.rows));
-    PMM_CUDA(c, c->d_dres.reserve(sizeof(double) * pairs));
-    PMM_CUDA(c, c->d_ctrl.reserve(sizeof(uint32_t) * kCtrlWords));
-    PMM_CUDA(c, c->h_out.reserve(256 + align_up(sizeof(float) * pairs) + align_up(sizeof(uint32_t) * pairs) + sizeof(double) * pairs + 256));
+    for (ResultSet& r : c->rs) {
+        PMM_CUDA(c, r.d_raw.reserve(sizeof(float) * pairs));
+        PMM_CUDA(c, r.d_fb_tasks.reserve(sizeof(Task) * pairs));
+        PMM_CUDA(c, r.d_fb_idx.reserve(sizeof(uint32_t) * pairs));
+        PMM_CUDA(c, r.d_fb_hap.reserve(sizeof(uint32_t) * pairs));
+        PMM_CUDA(c, r.d_fb_rows.reserve(sizeof(uint32_t) * 2 * plan.rows));
+        PMM_CUDA(c, r.d_dres.reserve(sizeof(double) * pairs));
+        PMM_CUDA(c, r.d_ctrl.reserve(sizeof(uint32_t) * kCtrlWords));
+        PMM_CUDA(c, r.h_out.reserve(256 + align_up(sizeof(float) * pairs) + align_up(sizeof(uint32_t) * pairs) + sizeof(double) * pairs + 256));
+    }
     // carry rows of the striped kernels: one haplotype (+2 separators) per warp, three rows of doubles
     {
         int ctas64 = 1;
         for (int k : {4, 5, 6, 8}) ctas64 = std::max(ctas64, forward_f64_ctas_per_sm(k, true));
         const int ctas32 = std::max(std::max(forward_f32_ctas_per_sm(kStripedK, 32, true, false), forward_f32_ctas_per_sm(kStripedK, 32, true, true)),
                                     recheck_f32_ctas_per_sm());
-        const size_t warps = (size_t)c->sm_count * std::max(ctas64, ctas32) * kWarpsPerCta;
-        PMM_CUDA(c, c->d_scratch.reserve(warps * 3 * (size_t)(max_hap + 8) * sizeof(double)));
+        // the float and the double kernel of neighbouring launches can be on the GPU together: a scratch of their own each
+        PMM_CUDA(c, c->d_scratch.reserve((size_t)c->sm_count * ctas32 * kWarpsPerCta * 3 * (size_t)(max_hap + 8) * sizeof(float)));
+        PMM_CUDA(c, c->d_scratch64.reserve((size_t)c->sm_count * ctas64 * kWarpsPerCta * 3 * (size_t)(max_hap + 8) * sizeof(double)));
     }
 
     cudaStream_t s = c->stream;
@@ -455,6 +475,14 @@ void parallel_for(uint64_t n, uint64_t grain, const std::function<void(uint64_t,
 // the same workers for the other engine of this library (sw_engine.cu: staging and CIGAR scatter)
 namespace pmm { void host_parallel_for(uint64_t n, uint64_t grain, const std::function<void(uint64_t, uint64_t)>& f) { parallel_for(n, grain, f); } }
 
+// The double re-run's stream, at the priority of the float pass's.  (Tried: one level above it, so that a re-run's blocks
+// take freed slots before the next float pass's -- no difference in throughput on configs 2, 3 and 4 or through the pool,
+// an FP32-pipe and an FP64-pipe kernel do not co-run to any advantage: the float pass leaves too few issue slots.)
+static cudaError_t create_f64_stream(cudaStream_t* out, int prio)
+{
+    return cudaStreamCreateWithPriority(out, cudaStreamNonBlocking, prio);
+}
+
 // No exception crosses the C boundary (include/pairhmm_cuda.h): allocation failures of the host-side vectors and
 // anything else thrown below an entry point become a status code and a message.
 template <class F> static int guarded(pmm_ctx* c, F&& f)
@@ -508,16 +536,21 @@ int pmm_create(int device, pmm_ctx** out)
     }
     c->stream = c->own_stream;
     if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&c->list_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        (e = cudaStreamCreateWithFlags(&c->list_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = create_f64_stream(&c->f64_stream, 0)) != cudaSuccess) {       // 0 = the default priority, like own_stream
         g_create_error = cudaGetErrorString(e);
         if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+        if (c->list_stream) cudaStreamDestroy(c->list_stream);
         cudaStreamDestroy(c->own_stream); delete c; return PMM_ERR_CUDA;
     }
-    for (auto& ev : c->ev) cudaEventCreate(&ev);
+    for (ResultSet& r : c->rs) {
+        for (auto& ev : r.ev) cudaEventCreate(&ev);
+        cudaEventCreateWithFlags(&r.ev_raw, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&r.ev_lists, cudaEventDisableTiming);
+    }
+    cudaEventCreate(&c->ev_probe);
     cudaEventCreateWithFlags(&c->ev_block, cudaEventBlockingSync | cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_poll, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&c->ev_raw, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&c->ev_lists, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_h2d, cudaEventDisableTiming);
     cudaEventCreate(&c->ev_ref);
     cudaEventRecord(c->ev_ref, c->own_stream);
@@ -532,16 +565,23 @@ void pmm_destroy(pmm_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->f64_stream) cudaStreamSynchronize(c->f64_stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     if (c->list_stream) cudaStreamSynchronize(c->list_stream);
-    for (DevBuf* b : {&c->tables, &c->d_in, &c->d_params, &c->d_stream, &c->d_iyf, &c->d_iyd, &c->d_raw, &c->d_fb_tasks, &c->d_fb_idx,
-                      &c->d_fb_hap, &c->d_fb_rows, &c->d_tiny_tasks, &c->d_dres, &c->d_ctrl, &c->d_scratch, &c->d_probe}) b->release();
-    c->h_in.release(); c->h_out.release();
-    for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+    for (DevBuf* b : {&c->tables, &c->d_in, &c->d_params, &c->d_stream, &c->d_iyf, &c->d_iyd, &c->d_tiny_tasks, &c->d_scratch,
+                      &c->d_scratch64, &c->d_probe}) b->release();
+    for (ResultSet& r : c->rs) {
+        for (DevBuf* b : {&r.d_raw, &r.d_fb_tasks, &r.d_fb_idx, &r.d_fb_hap, &r.d_fb_rows, &r.d_dres, &r.d_ctrl}) b->release();
+        r.h_out.release();
+        for (auto& ev : r.ev) if (ev) cudaEventDestroy(ev);
+        if (r.ev_raw) cudaEventDestroy(r.ev_raw);
+        if (r.ev_lists) cudaEventDestroy(r.ev_lists);
+    }
+    c->h_in.release();
+    if (c->ev_probe) cudaEventDestroy(c->ev_probe);
+    if (c->f64_stream) cudaStreamDestroy(c->f64_stream);
     if (c->ev_block) cudaEventDestroy(c->ev_block);
     if (c->ev_poll) cudaEventDestroy(c->ev_poll);
-    if (c->ev_raw) cudaEventDestroy(c->ev_raw);
-    if (c->ev_lists) cudaEventDestroy(c->ev_lists);
     if (c->list_stream) cudaStreamDestroy(c->list_stream);
     if (c->ev_h2d) cudaEventDestroy(c->ev_h2d);
     if (c->ev_ref) cudaEventDestroy(c->ev_ref);
@@ -574,12 +614,14 @@ int pmm_set_option(pmm_ctx* c, const char* key, const char* value)
         int least = 0, greatest = 0;
         PMM_CUDA(c, cudaDeviceGetStreamPriorityRange(&least, &greatest));        // numerically: greatest <= least
         const int prio = std::min(least, greatest + rank);
-        cudaStream_t ns = nullptr;
+        cudaStream_t ns = nullptr, nd = nullptr;
         PMM_CUDA(c, cudaStreamCreateWithPriority(&ns, cudaStreamNonBlocking, prio));
+        PMM_CUDA(c, create_f64_stream(&nd, prio));
         PMM_CUDA(c, cudaStreamSynchronize(c->own_stream));
+        PMM_CUDA(c, cudaStreamSynchronize(c->f64_stream));
         const bool was_own = c->stream == c->own_stream;
-        cudaStreamDestroy(c->own_stream);
-        c->own_stream = ns;
+        cudaStreamDestroy(c->own_stream); cudaStreamDestroy(c->f64_stream);
+        c->own_stream = ns; c->f64_stream = nd;
         if (was_own) c->stream = ns;
         return PMM_OK;
     }
@@ -593,6 +635,12 @@ int pmm_set_option(pmm_ctx* c, const char* key, const char* value)
         const int v = atoi(value);
         if (v < 1 || v > 64) return c->fail(PMM_ERR_INVALID, k + " out of range (1..64)");
         (k == "f64_max_run" ? c->f64_max_run : c->f64_tasks_per_warp) = v;
+        return PMM_OK;
+    }
+    if (k == "overlap") {
+        const std::string v(value);
+        if (v != "0" && v != "1" && v != "on" && v != "off") return c->fail(PMM_ERR_INVALID, "overlap is \"on\" or \"off\"");
+        c->overlap = v == "1" || v == "on";
         return PMM_OK;
     }
     if (k == "mode") {
@@ -649,17 +697,23 @@ int pmm_launch(pmm_ctx* c)
     if (!c->staged) return c->fail(PMM_ERR_STATE, "pmm_launch before pmm_stage_*");
     if (c->fast && c->d_tiny_tasks.cap < sizeof(Task) * c->pairs) return c->fail(PMM_ERR_STATE, "mode changed to fast after pmm_stage_*: stage the job again");
     cudaSetDevice(c->device);
-    cudaStream_t s = c->stream;
+    cudaStream_t s = c->stream, sd = c->f64_stream;
     char* db = static_cast<char*>(c->d_in.p);
+    // This launch takes the other result set: the previous launch's double re-run may still be using its own.
+    ResultSet& prev = c->rs[c->cur];
+    c->cur ^= 1;
+    ResultSet& R = c->rs[c->cur];
     // control words, hot ones on their own 128-byte lines: [0] fallback count, [1] flush count, [2] re-check count,
     // [3] tasks of the double re-run, [4] fallback slots handed out, [kCtrlHist ..) and [kCtrlClassCursor ..) the counting
     // sort of those tasks, [kCtrlCursors + 32 k] work-queue cursor of launch k
-    uint32_t* ctrl = static_cast<uint32_t*>(c->d_ctrl.p);
+    uint32_t* ctrl = static_cast<uint32_t*>(R.d_ctrl.p);
     uint32_t launches = 0;
     c->launched = false; c->have_raw = false; c->have_lists = false;
-    PMM_CUDA(c, cudaStreamWaitEvent(s, c->ev_raw, 0));          // the previous launch's copies out of d_raw, d_ctrl and the
-    PMM_CUDA(c, cudaStreamWaitEvent(s, c->ev_lists, 0));        // fallback list (no-ops the first time)
-    PMM_CUDA(c, cudaEventRecord(c->ev[0], s));
+    // the launch before the previous one used this set: its copies out of d_raw, d_ctrl and the fallback list (which
+    // follow its double re-run) must be over (no-ops the first times)
+    PMM_CUDA(c, cudaStreamWaitEvent(s, R.ev_raw, 0));
+    PMM_CUDA(c, cudaStreamWaitEvent(s, R.ev_lists, 0));
+    PMM_CUDA(c, cudaEventRecord(R.ev[0], s));
     PMM_CUDA(c, cudaMemsetAsync(ctrl, 0, sizeof(uint32_t) * kCtrlWords, s));
 
     ForwardArgs a{};
@@ -692,7 +746,7 @@ int pmm_launch(pmm_ctx* c)
         a.tasks = reinterpret_cast<Task*>(db + c->off_tasks) + seg.task_first;
         a.ntasks = seg.task_count; a.ntasks_dev = nullptr;
         a.counter = ctrl + cursor; cursor += 32;
-        a.out = c->d_raw.p;
+        a.out = R.d_raw.p;
         const int per_sm = forward_f32_ctas_per_sm(seg.v.K, seg.v.W, seg.v.striped, c->fast);
         if (per_sm <= 0) return c->fail(PMM_ERR_INVALID, "kernel variant unavailable");
         const int ctas = (int)std::min<uint64_t>((seg.task_count + kWarpsPerCta - 1) / kWarpsPerCta, (uint64_t)c->sm_count * per_sm);
@@ -707,62 +761,78 @@ int pmm_launch(pmm_ctx* c)
         PMM_CUDA(c, launch_recheck_f32(a, fq, c->sm_count * std::max(1, recheck_f32_ctas_per_sm()), s));
         ++launches;
     }
-    PMM_CUDA(c, cudaEventRecord(c->ev[1], s));
+    PMM_CUDA(c, cudaEventRecord(R.ev[1], s));
     // The raw floats are final now: copy them back on the copy stream while the double pass runs, so that a fetch can
     // take log10f of them (host libm) under it.
     {
-        char* ho = static_cast<char*>(c->h_out.p);
-        PMM_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev[1], 0));
-        PMM_CUDA(c, cudaMemcpyAsync(ho + 256, c->d_raw.p, sizeof(float) * c->pairs, cudaMemcpyDeviceToHost, c->copy_stream));
-        PMM_CUDA(c, cudaEventRecord(c->ev_raw, c->copy_stream));
+        char* ho = static_cast<char*>(R.h_out.p);
+        PMM_CUDA(c, cudaStreamWaitEvent(c->copy_stream, R.ev[1], 0));
+        PMM_CUDA(c, cudaMemcpyAsync(ho + 256, R.d_raw.p, sizeof(float) * c->pairs, cudaMemcpyDeviceToHost, c->copy_stream));
+        PMM_CUDA(c, cudaEventRecord(R.ev_raw, c->copy_stream));
     }
 
     // ---- double re-run (PairHMMWorker.cpp:176-184): the results below the threshold become tasks, the failing haplotypes
-    //      of a read together; their number is only known on the device ------------------------------------------------
+    //      of a read together; their number is only known on the device.  On its own stream: the next launch's float pass
+    //      (this stream) starts as soon as this one's is over and runs next to it ------------------------------------------
+    PMM_CUDA(c, cudaStreamWaitEvent(sd, R.ev[1], 0));
     const int KD = c->f64_rows;
     const int f64_ctas = c->sm_count * std::max(1, forward_f64_ctas_per_sm(KD, c->f64_striped));
     FallbackBuild fb{};
-    fb.raw = static_cast<float*>(c->d_raw.p);
+    fb.raw = static_cast<float*>(R.d_raw.p);
     fb.regions = reinterpret_cast<RegionDesc*>(db + c->off_regions);
     fb.reads = a.reads;
     fb.num_region = c->num_region; fb.num_rows = c->num_rows;
     fb.threshold = thr;
     fb.ctrl = ctrl;
-    fb.tasks = static_cast<Task*>(c->d_fb_tasks.p);
-    fb.out_index = static_cast<uint32_t*>(c->d_fb_idx.p);
-    fb.hap_list = static_cast<uint32_t*>(c->d_fb_hap.p);
-    fb.row_slot = static_cast<uint32_t*>(c->d_fb_rows.p);
+    fb.tasks = static_cast<Task*>(R.d_fb_tasks.p);
+    fb.out_index = static_cast<uint32_t*>(R.d_fb_idx.p);
+    fb.hap_list = static_cast<uint32_t*>(R.d_fb_hap.p);
+    fb.row_slot = static_cast<uint32_t*>(R.d_fb_rows.p);
     fb.spos = a.spos;
     fb.max_hap_len = c->max_hap_len;
     fb.capacity = (uint32_t)c->pairs;
     fb.single_stripe_rows = 32u * (uint32_t)KD;
     fb.target_tasks = (uint32_t)(f64_ctas * kWarpsPerCta * c->f64_tasks_per_warp);
     fb.max_run = (uint32_t)c->f64_max_run;
-    PMM_CUDA(c, launch_build_fallback(fb, c->sm_count, s));
+    PMM_CUDA(c, launch_build_fallback(fb, c->sm_count, sd));
     launches += 2;
-    a.inity = c->d_iyd.p; a.out = c->d_dres.p; a.tasks = fb.tasks; a.hap_list = fb.hap_list;
+    a.inity = c->d_iyd.p; a.out = R.d_dres.p; a.tasks = fb.tasks; a.hap_list = fb.hap_list;
     a.ntasks = 0; a.ntasks_dev = ctrl + 3; a.counter = ctrl + cursor; cursor += 32;
     a.tiny_threshold = ldexp(1.0, -800); a.tiny_count = ctrl + 1;
-    PMM_CUDA(c, launch_forward_f64(KD, c->f64_striped, a, f64_ctas, s));
+    a.scratch = c->d_scratch64.p;
+    PMM_CUDA(c, launch_forward_f64(KD, c->f64_striped, a, f64_ctas, sd));
     ++launches;
-    PMM_CUDA(c, cudaEventRecord(c->ev[2], s));
+    PMM_CUDA(c, cudaEventRecord(R.ev[2], sd));
+    // What is queued on the launch stream from here on (the next launch, an event of the caller's) comes after the
+    // PREVIOUS launch's double re-run: consecutive launches overlap by one pass, no further, and a pair of events around
+    // each pmm_launch of a steady sequence brackets exactly one float pass and one double re-run.
+    PMM_CUDA(c, cudaStreamWaitEvent(s, (c->overlap ? prev : R).ev[2], 0));
     // The length of the fallback list is only known on the device.  Copy the control words and a first slice of the list
     // (an eighth of the pairs) back right behind the double pass, so that the common case needs no further round trip;
     // the rest, if any, follows in the fetch.
     {
-        char* ho = static_cast<char*>(c->h_out.p);
+        char* ho = static_cast<char*>(R.h_out.p);
         uint32_t* hidx = reinterpret_cast<uint32_t*>(ho + 256 + align_up(sizeof(float) * c->pairs));
         double* hd = reinterpret_cast<double*>(reinterpret_cast<char*>(hidx) + align_up(sizeof(uint32_t) * c->pairs));
         c->spec = (uint32_t)std::min<uint64_t>(c->pairs, std::max<uint64_t>(1024, c->pairs / 8));
-        cudaStream_t ls = c->list_stream;                       // not the kernels' stream: the next job need not wait for these
-        PMM_CUDA(c, cudaStreamWaitEvent(ls, c->ev[2], 0));
-        PMM_CUDA(c, cudaMemcpyAsync(ho, c->d_ctrl.p, 12, cudaMemcpyDeviceToHost, ls));
-        PMM_CUDA(c, cudaMemcpyAsync(hidx, c->d_fb_idx.p, sizeof(uint32_t) * c->spec, cudaMemcpyDeviceToHost, ls));
-        PMM_CUDA(c, cudaMemcpyAsync(hd, c->d_dres.p, sizeof(double) * c->spec, cudaMemcpyDeviceToHost, ls));
-        PMM_CUDA(c, cudaEventRecord(c->ev_lists, ls));
+        cudaStream_t ls = c->list_stream;                       // not a kernels' stream: the next job need not wait for these
+        PMM_CUDA(c, cudaStreamWaitEvent(ls, R.ev[2], 0));
+        PMM_CUDA(c, cudaMemcpyAsync(ho, R.d_ctrl.p, 12, cudaMemcpyDeviceToHost, ls));
+        PMM_CUDA(c, cudaMemcpyAsync(hidx, R.d_fb_idx.p, sizeof(uint32_t) * c->spec, cudaMemcpyDeviceToHost, ls));
+        PMM_CUDA(c, cudaMemcpyAsync(hd, R.d_dres.p, sizeof(double) * c->spec, cudaMemcpyDeviceToHost, ls));
+        PMM_CUDA(c, cudaEventRecord(R.ev_lists, ls));
     }
     c->stats.kernel_launches = launches;
     c->launched = true;
+    return PMM_OK;
+}
+
+int pmm_join(pmm_ctx* c)
+{
+    if (!c) return PMM_ERR_INVALID;
+    if (!c->launched) return PMM_OK;
+    cudaSetDevice(c->device);
+    PMM_CUDA(c, cudaStreamWaitEvent(c->stream, c->R().ev[2], 0));
     return PMM_OK;
 }
 
@@ -771,11 +841,12 @@ int pmm_sync(pmm_ctx* c)
     if (!c) return PMM_ERR_INVALID;
     cudaSetDevice(c->device);
     PMM_CUDA(c, cudaStreamSynchronize(c->stream));
+    PMM_CUDA(c, cudaStreamSynchronize(c->f64_stream));
     PMM_CUDA(c, cudaStreamSynchronize(c->copy_stream));
     PMM_CUDA(c, cudaStreamSynchronize(c->list_stream));
     if (c->launched) {
-        cudaEventElapsedTime(&c->stats.ms_f32, c->ev[0], c->ev[1]);
-        cudaEventElapsedTime(&c->stats.ms_fallback, c->ev[1], c->ev[2]);
+        cudaEventElapsedTime(&c->stats.ms_f32, c->R().ev[0], c->R().ev[1]);
+        cudaEventElapsedTime(&c->stats.ms_fallback, c->R().ev[1], c->R().ev[2]);
     }
     return PMM_OK;
 }
@@ -830,7 +901,7 @@ static cudaError_t wait_stream(pmm_ctx* c, cudaStream_t st)
 struct HostOut { uint32_t* ctrl; float* raw; uint32_t* idx; double* dres; };
 static HostOut host_out(const pmm_ctx* c)
 {
-    char* ho = static_cast<char*>(c->h_out.p);
+    char* ho = static_cast<char*>(c->R().h_out.p);
     HostOut o;
     o.ctrl = reinterpret_cast<uint32_t*>(ho);                                       // 256 B header
     o.raw = reinterpret_cast<float*>(ho + 256);
@@ -863,15 +934,15 @@ static int ensure_lists(pmm_ctx* c)
     const uint32_t nfb = o.ctrl[0], spec = c->spec;
     uint64_t d2h = 12 + sizeof(float) * c->pairs + (sizeof(uint32_t) + sizeof(double)) * spec;
     if (nfb > spec) {
-        PMM_CUDA(c, cudaMemcpyAsync(o.idx + spec, static_cast<uint32_t*>(c->d_fb_idx.p) + spec, sizeof(uint32_t) * (nfb - spec), cudaMemcpyDeviceToHost, s));
-        PMM_CUDA(c, cudaMemcpyAsync(o.dres + spec, static_cast<double*>(c->d_dres.p) + spec, sizeof(double) * (nfb - spec), cudaMemcpyDeviceToHost, s));
-        PMM_CUDA(c, cudaEventRecord(c->ev_lists, s));
+        PMM_CUDA(c, cudaMemcpyAsync(o.idx + spec, static_cast<uint32_t*>(c->R().d_fb_idx.p) + spec, sizeof(uint32_t) * (nfb - spec), cudaMemcpyDeviceToHost, s));
+        PMM_CUDA(c, cudaMemcpyAsync(o.dres + spec, static_cast<double*>(c->R().d_dres.p) + spec, sizeof(double) * (nfb - spec), cudaMemcpyDeviceToHost, s));
+        PMM_CUDA(c, cudaEventRecord(c->R().ev_lists, s));
         PMM_CUDA(c, wait_stream(c, s));
         d2h += (sizeof(uint32_t) + sizeof(double)) * (nfb - spec);
     }
     c->stats.fallback_pairs = nfb; c->stats.flush_pairs = o.ctrl[1]; c->stats.recheck_pairs = o.ctrl[2]; c->stats.d2h_bytes = d2h;
-    cudaEventElapsedTime(&c->stats.ms_f32, c->ev[0], c->ev[1]);
-    cudaEventElapsedTime(&c->stats.ms_fallback, c->ev[1], c->ev[2]);
+    cudaEventElapsedTime(&c->stats.ms_f32, c->R().ev[0], c->R().ev[1]);
+    cudaEventElapsedTime(&c->stats.ms_fallback, c->R().ev[1], c->R().ev[2]);
     c->have_lists = true;
     return PMM_OK;
 }
@@ -1224,12 +1295,12 @@ int pmm_measure_fp32_peak(pmm_ctx* c, double* lane_instr_per_s, double* sm_mhz)
     PMM_CUDA(c, launch_fp32_probe(static_cast<float*>(c->d_probe.p), 25, ctas, s));
     double best = 0;
     for (int rep = 0; rep < 3; ++rep) {
-        PMM_CUDA(c, cudaEventRecord(c->ev[3], s));
+        PMM_CUDA(c, cudaEventRecord(c->ev_probe, s));
         PMM_CUDA(c, launch_fp32_probe(static_cast<float*>(c->d_probe.p), iters, ctas, s));
         cudaEvent_t e1; cudaEventCreate(&e1);
         PMM_CUDA(c, cudaEventRecord(e1, s));
         PMM_CUDA(c, cudaEventSynchronize(e1));
-        float ms = 0; cudaEventElapsedTime(&ms, c->ev[3], e1); cudaEventDestroy(e1);
+        float ms = 0; cudaEventElapsedTime(&ms, c->ev_probe, e1); cudaEventDestroy(e1);
         const double ops = (double)ctas * 256 * iters * 512.0;
         best = std::max(best, ops / (ms * 1e-3));
     }
@@ -1243,11 +1314,11 @@ int pmm_get_timeline(pmm_ctx* c, pmm_timeline_t* out)
     if (!c || !out) return PMM_ERR_INVALID;
     if (!c->launched) return c->fail(PMM_ERR_STATE, "pmm_get_timeline before pmm_launch");
     cudaSetDevice(c->device);
-    PMM_CUDA(c, cudaEventSynchronize(c->ev[2]));
+    PMM_CUDA(c, cudaEventSynchronize(c->R().ev[2]));
     float a = 0, b = 0, d = 0;
-    PMM_CUDA(c, cudaEventElapsedTime(&a, c->ev_ref, c->ev[0]));
-    PMM_CUDA(c, cudaEventElapsedTime(&b, c->ev_ref, c->ev[1]));
-    PMM_CUDA(c, cudaEventElapsedTime(&d, c->ev_ref, c->ev[2]));
+    PMM_CUDA(c, cudaEventElapsedTime(&a, c->ev_ref, c->R().ev[0]));
+    PMM_CUDA(c, cudaEventElapsedTime(&b, c->ev_ref, c->R().ev[1]));
+    PMM_CUDA(c, cudaEventElapsedTime(&d, c->ev_ref, c->R().ev[2]));
     out->ref_host_s = c->ref_host_s;
     out->kernels_start_s = a * 1e-3; out->f32_end_s = b * 1e-3; out->kernels_end_s = d * 1e-3;
     return PMM_OK;
@@ -1265,12 +1336,12 @@ int pmm_measure_fp64_peak(pmm_ctx* c, double* lane_instr_per_s)
     cudaEvent_t e1;
     PMM_CUDA(c, cudaEventCreate(&e1));
     for (int rep = 0; rep < 3; ++rep) {
-        cudaEventRecord(c->ev[3], s);
+        cudaEventRecord(c->ev_probe, s);
         cudaError_t e = launch_fp64_probe(static_cast<double*>(c->d_probe.p), iters, ctas, s);
         if (e == cudaSuccess) e = cudaEventRecord(e1, s);
         if (e == cudaSuccess) e = cudaEventSynchronize(e1);
         if (e != cudaSuccess) { cudaEventDestroy(e1); return c->fail_cuda(e, "fp64 probe"); }
-        float ms = 0; cudaEventElapsedTime(&ms, c->ev[3], e1);
+        float ms = 0; cudaEventElapsedTime(&ms, c->ev_probe, e1);
         best = std::max(best, (double)ctas * 256 * iters * 512.0 / (ms * 1e-3));
     }
     cudaEventDestroy(e1);

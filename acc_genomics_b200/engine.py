@@ -21,7 +21,7 @@ PMM_OK, PMM_ERR_INVALID, PMM_ERR_CUDA, PMM_ERR_NO_DEVICE, PMM_ERR_STATE = 0, 1, 
 EXPORTS = [
     "pmm_create", "pmm_destroy", "pmm_last_error", "pmm_device_count", "pmm_set_option",
     "pmm_forward_raw_serialized", "pmm_forward_log10", "pmm_forward_log10_serialized", "pmm_forward_log10_testcases",
-    "pmm_stage_flat", "pmm_stage_serialized", "pmm_fetch_fallback", "pmm_fetch_log10_indexed", "pmm_launch", "pmm_sync", "pmm_fetch_raw", "pmm_fetch_log10", "pmm_fetch_fallback_mask",
+    "pmm_stage_flat", "pmm_stage_serialized", "pmm_fetch_fallback", "pmm_fetch_log10_indexed", "pmm_launch", "pmm_join", "pmm_sync", "pmm_fetch_raw", "pmm_fetch_log10", "pmm_fetch_fallback_mask",
     "pmm_get_stats", "pmm_measure_fp32_peak", "pmm_measure_fp64_peak", "pmm_plan_flat", "pmm_host_table", "pmm_host_finish_log10",
     "pmm_pool_create", "pmm_pool_destroy", "pmm_pool_last_error", "pmm_pool_num_devices", "pmm_pool_submit_flat",
     "pmm_pool_wait", "pmm_pool_device_load", "pmm_pool_set_merge", "pmm_pool_trace", "pmm_pool_get_trace", "pmm_get_timeline",
@@ -100,7 +100,7 @@ def load_library() -> C.CDLL:
         L.pmm_stage_serialized.argtypes = [vp, vp, u64, vp, u64, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.pmm_fetch_fallback.argtypes = [vp, vp, vp, u64, C.POINTER(u64)]
         L.pmm_fetch_log10_indexed.argtypes = [vp, vp, u64, vp, u64, C.POINTER(u64)]
-        L.pmm_launch.argtypes = [vp]; L.pmm_sync.argtypes = [vp]
+        L.pmm_launch.argtypes = [vp]; L.pmm_sync.argtypes = [vp]; L.pmm_join.argtypes = [vp]
         L.pmm_fetch_raw.argtypes = [vp, vp, u64]
         L.pmm_fetch_log10.argtypes = [vp, vp, u64, C.POINTER(u64)]
         L.pmm_fetch_fallback_mask.argtypes = [vp, vp, u64]
@@ -232,6 +232,10 @@ class PairHMMEngine:
 
     def sync(self):
         self._ck(self.lib.pmm_sync(self.h))
+
+    def join(self):
+        """The launch stream waits for the last launch's double re-run (no host wait)."""
+        self._ck(self.lib.pmm_join(self.h))
 
     def fetch_raw(self) -> np.ndarray:
         out = np.empty(self._job["pairs"], dtype=np.float32)

@@ -12,7 +12,8 @@ ranks of the device time.
 
 The JSON line
   value         whole-job GCUPS (cells = sum(read_len) * sum(hap_len), /root/reference/pairhmm/host/main.cpp:305-313) with
-                inputs resident in HBM, CUDA events, L2 flushed between steps
+                inputs resident in HBM, CUDA events per step, L2 flushed between steps, launch overlap off
+                (value_overlapped_no_l2_flush: back-to-back launches as a streaming caller issues them)
   e2e           the same metric with HOST buffers: pack + H2D + kernels + D2H + host log10 inside the timed region.
                 `value` = through the work queue (pmm_pool_*, 4 contexts, neighbouring steps overlap); `serial_value` = one
                 context, nothing overlapped; `plugin_value` = through the reference-named classes PairHMMClient +
@@ -289,14 +290,34 @@ class Gpu:
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")        # > 126 MB L2
 
     def timed_launches(self, steps: int):
-        """Device time (s) of `steps` launches of the staged job, L2 flushed before each, CUDA events on the engine's stream."""
+        """Device time (s) of `steps` launches of the staged job, L2 flushed before each, CUDA events on the engine's stream.
+        Launch overlap is switched off for it: every launch ends with its own double re-run, so the per-step brackets add
+        up and the flush stays outside them.  The host runs ahead: no launch latency inside a bracket."""
         torch = self.torch
+        self.eng.set_option("overlap", "off")
+        self.eng.join()                                    # a double re-run of an earlier (overlapping) launch belongs to no bracket
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         for a, b in ev:
             self.flush.fill_(1)                            # evicts L2; on the same stream, outside the timed bracket
             a.record(); self.eng.launch(); b.record()
-        ev[-1][1].synchronize()                            # the host runs ahead: no launch latency inside a bracket
+        ev[-1][1].synchronize()
+        self.eng.set_option("overlap", "on")
         return sum(a.elapsed_time(b) for a, b in ev) * 1e-3
+
+    def timed_overlapped(self, steps: int):
+        """The same launches the way a streaming caller issues them: back to back with overlap on (the float pass of step
+        k + 1 beside the double re-run of step k), ONE region from the first launch to the end of the last re-run, no L2
+        flush (a fill between the steps would serialise them)."""
+        torch = self.torch
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.eng.join()
+        a.record()
+        for _ in range(steps):
+            self.eng.launch()
+        self.eng.join()
+        b.record()
+        b.synchronize()
+        return a.elapsed_time(b) * 1e-3
 
     def kernel_ms(self, reps: int):
         """(float pass ms, double re-run ms) from the engine's own events (read_params + forward launches | builders + double)."""
@@ -567,6 +588,7 @@ def _main(args, real_stdout):
     dev_s = gpu.timed_launches(args.steps)
     barrier()
     sampler.t1 = time.time()
+    dev_noflush_s = gpu.timed_overlapped(args.steps)
     clocks = sampler.stop()
     log("timed region done")
     f32_ms, fb_ms = gpu.kernel_ms(min(args.steps, 10))
@@ -622,13 +644,13 @@ def _main(args, real_stdout):
     peak64 = eng.measure_fp64_peak()
 
     # ---- max over ranks ------------------------------------------------------------------------------------------------------
-    vals = [dev_s, e2e_s, e2e_serial_s, plugin["s_per_step"] if plugin else 0.0, plugin["s_per_step_threads3"] if plugin else 0.0]
+    vals = [dev_s, e2e_s, e2e_serial_s, plugin["s_per_step"] if plugin else 0.0, plugin["s_per_step_threads3"] if plugin else 0.0, dev_noflush_s]
     for r in per:
         vals += [r["dev_s"], r["e2e_s"]]
     vals = max_over_ranks(vals, world, "cuda")
-    dev_s, e2e_s, e2e_serial_s, p1_s, p3_s = vals[:5]
+    dev_s, e2e_s, e2e_serial_s, p1_s, p3_s, dev_noflush_s = vals[:6]
     for k, r in enumerate(per):
-        r["dev_s"], r["e2e_s"] = vals[5 + 2 * k], vals[6 + 2 * k]
+        r["dev_s"], r["e2e_s"] = vals[6 + 2 * k], vals[7 + 2 * k]
 
     # ---- the work queue over all GPUs: rank 0 drives one pool, the other ranks sit at a CPU barrier with idle GPUs ----------------
     queue = queue_regs = queue_kept = None
@@ -663,6 +685,9 @@ def _main(args, real_stdout):
             "dtype": "f32 (exact op order, no FMA contraction) + f64 re-run of underflowed pairs", "data": "synthetic",
             "config": config_dict(args.config, args.scale, batches),
             "fallback_pairs": int(nfb), "flush_pairs": int(st["flush_pairs"]),
+            "value_overlapped_no_l2_flush": job_cells * args.steps / dev_noflush_s * 1e-9,
+            "value_overlapped_note": "not the headline: the same launches back to back on one context with launch overlap on (float "
+                                     "pass of step k+1 beside the double re-run of step k), one timed region, no L2 fill between steps",
             "e2e": {"value": job_cells * args.steps / e2e_s * 1e-9, "unit": UNIT, "h2d_bytes_per_step": int(st2["h2d_bytes"]),
                     "d2h_bytes_per_step": int(st2["d2h_bytes"]), "ms_per_step": e2e_s / args.steps * 1e3,
                     "path": "pmm_pool_submit_flat / pmm_pool_wait, 4 contexts (2 feeder threads) on the GPU: per step pack + H2D + kernels + D2H + host "

@@ -86,6 +86,9 @@ int  pmm_device_count(void);
  *                       "-1,0" keeps every variant in a launch of its own (no consolidation of rare ones)
  *   "f64_tasks_per_warp", "f64_max_run" = how the double re-run cuts a read's failing haplotypes into tasks: about
  *                       f64_tasks_per_warp tasks per resident warp (default 6), at most f64_max_run haplotypes each (6)
+ *   "overlap"         = "on" (default): the launch stream waits, after a launch, for the double re-run of the launch BEFORE, so
+ *                       consecutive launches overlap by one pass; "off": for its own re-run, every launch is complete on
+ *                       the launch stream when the next thing queued there starts (what per-launch event brackets need)
  *   "sync"            = "spin" (default): waits poll the stream, lowest latency for one context per core; "block":
  *                       waits sleep on a blocking event (for hosts with fewer cores than waiting threads); "hybrid": poll
  *                       for 60 us, then sleep; "auto": spin while fewer than cores/16 threads of the process do, else sleep.  The pool takes it from the environment variable PMM_POOL_SYNC, the task
@@ -128,7 +131,8 @@ int  pmm_forward_log10_testcases(pmm_ctx* ctx, const pmm_testcase_t* tc, uint64_
  *   pmm_stage_flat : pack into pinned memory, copy to the GPU, build the haplotype stream and the task queue
  *   pmm_launch     : float pass + fallback compaction + double re-run; asynchronous on the context's stream
  *   pmm_fetch_*    : wait, copy results back, (log10) finish on the host
- * pmm_launch may be called repeatedly on one staged job (bench.py times it with inputs resident in HBM). */
+ * pmm_launch may be called repeatedly on one staged job (bench.py times it with inputs resident in HBM); consecutive
+ * launches overlap by one pass: the float pass of launch i + 1 runs beside the double re-run of launch i. */
 int  pmm_stage_flat(pmm_ctx* ctx, uint32_t num_read, const uint32_t* read_off,
                     const uint8_t* bases, const uint8_t* q, const uint8_t* i, const uint8_t* d, const uint8_t* c,
                     uint32_t num_hap, const uint32_t* hap_off, const uint8_t* hap_bases,
@@ -137,6 +141,11 @@ int  pmm_stage_flat(pmm_ctx* ctx, uint32_t num_read, const uint32_t* read_off,
 int  pmm_stage_serialized(pmm_ctx* ctx, const void* reads_ser, uint64_t reads_bytes,
                           const void* haps_ser, uint64_t haps_bytes, int* num_read, int* num_hap);
 int  pmm_launch(pmm_ctx* ctx);
+/* The double re-run of a launch runs on a stream of its own, next to the float pass of the following launch; pmm_launch
+ * itself only makes the launch stream wait for the re-run of the launch BEFORE.  pmm_join makes the launch stream wait
+ * for the last launch's re-run too (no host wait): what a caller records on that stream afterwards -- an event closing
+ * a timed region, say -- comes after all kernels of all launches so far. */
+int  pmm_join(pmm_ctx* ctx);
 int  pmm_sync(pmm_ctx* ctx);
 int  pmm_fetch_raw(pmm_ctx* ctx, float* out_raw, uint64_t out_capacity);
 int  pmm_fetch_log10(pmm_ctx* ctx, double* out, uint64_t out_capacity, uint64_t* n_fallback);
