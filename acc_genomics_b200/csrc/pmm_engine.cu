@@ -631,6 +631,13 @@ int pmm_set_option(pmm_ctx* c, const char* key, const char* value)
         c->tasks_per_warp = v;
         return PMM_OK;
     }
+    if (k == "run_tiers") {
+        int d = -1, share = kRunTierShare, top = kRunTierTop;
+        if (std::sscanf(value, "%d,%d,%d", &d, &share, &top) < 1 || d < 0 || d > 64 || share < 1 || share > 100 || top < 1 || top > 64)
+            return c->fail(PMM_ERR_INVALID, "run_tiers is \"depth[,share[,top]]\", depth 0..64, share 1..100, top 1..64");
+        set_run_tiers(d, share, top);                // process-wide (the planner has no context)
+        return PMM_OK;
+    }
     if (k == "f64_tasks_per_warp" || k == "f64_max_run") {
         const int v = atoi(value);
         if (v < 1 || v > 64) return c->fail(PMM_ERR_INVALID, k + " out of range (1..64)");

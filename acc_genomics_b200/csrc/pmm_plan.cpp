@@ -8,6 +8,9 @@
 #include "pmm_plan.h"
 
 #include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
 #include <numeric>
 
 namespace pmm {
@@ -43,6 +46,28 @@ static Variant pick_variant_uncached(int R)
 }
 
 struct Group { Variant v; uint32_t region; uint32_t reads[kMaxGroups]; uint32_t n; };
+
+// Graded runs (plan_job): tasks per resident warp in each tier of run sizes (0 = runs of equal size, the round-1
+// behaviour), the share of a warp's launch one task may take (per cent), and the largest run.  Process-wide;
+// PMM_RUN_TIERS="depth,share,top" or set_run_tiers() for tuning sweeps.
+static std::atomic<int> g_tiers{-1};                                    // depth | share << 8 | top << 16
+static int pack_tiers(int d, int share, int top)
+{
+    d = std::max(0, std::min(64, d)); share = std::max(1, std::min(100, share)); top = std::max(1, std::min(64, top));
+    return d | share << 8 | top << 16;
+}
+RunTiers run_tiers()
+{
+    int v = g_tiers.load(std::memory_order_relaxed);
+    if (v < 0) {
+        int d = kRunTierDepth, share = kRunTierShare, top = kRunTierTop;
+        if (const char* e = std::getenv("PMM_RUN_TIERS")) std::sscanf(e, "%d,%d,%d", &d, &share, &top);
+        v = pack_tiers(d, share, top);
+        g_tiers.store(v, std::memory_order_relaxed);
+    }
+    return RunTiers{v & 255, (v >> 8) & 255, (v >> 16) & 255};
+}
+void set_run_tiers(int depth, int share, int top) { g_tiers.store(pack_tiers(depth, share, top), std::memory_order_relaxed); }
 
 // Every variant present costs one kernel launch, and a launch is inefficient when it has few tasks: it lasts at
 // least as long as its longest task, and its tail leaves most of the GPU idle.  A mixed-length job (config 5: 10 % of
@@ -138,7 +163,7 @@ int plan_job(uint32_t num_read, const uint32_t* read_off, uint32_t num_hap, cons
     // variant and shares its warp with the next 32/W - 1 reads.
     std::vector<Group> groups;
     std::vector<uint32_t> order;
-    uint64_t group_haps = 0;
+    uint64_t group_haps = 0, group_steps = 0;                          // summed over groups: haplotypes, wavefront steps
     for (uint32_t g = 0; g < num_region; ++g) {
         const pmm_region_t& r = regions[g];
         order.resize(r.num_read);
@@ -155,6 +180,7 @@ int plan_job(uint32_t num_read, const uint32_t* read_off, uint32_t num_hap, cons
             for (uint32_t z = gr.n; z < (uint32_t)kMaxGroups; ++z) gr.reads[z] = 0;
             groups.push_back(gr);
             group_haps += r.num_hap;
+            group_steps += hap_off[r.hap_first + r.num_hap] - hap_off[r.hap_first] + r.num_hap;
         }
     }
 
@@ -162,8 +188,34 @@ int plan_job(uint32_t num_read, const uint32_t* read_off, uint32_t num_hap, cons
     const uint64_t resident_warps = (uint64_t)std::max(1, sm_count) * 16;
     const uint64_t target_tasks = std::max<uint64_t>(1, resident_warps * (uint64_t)std::max(1, tasks_per_warp));
     plan.haps_per_task = (uint32_t)std::max<uint64_t>(1, (group_haps + target_tasks - 1) / target_tasks);
+    // Graded runs.  What a task pays once -- its row-parameter loads and weight table, the wavefront's fill and drain, the
+    // checked steps at both ends -- is about 3 % of a one-haplotype task, so long runs are cheaper; but the launch's tail is
+    // as long as its last tasks.  Warps pull tasks longest first, so both are had by cutting a region's haplotypes into runs
+    // of decreasing size: enough one-haplotype tasks for the last `depth` tasks of every resident warp, as many runs of
+    // two before them, the rest in runs of `top` (ncu, config 2: 9.7 % of the float pass's warp samples lay outside the
+    // steady loop with one haplotype per task).  A job with fewer than depth tasks per warp keeps one haplotype per task.
+    double f1 = 0.0, f2 = 0.0;
+    uint32_t top = plan.haps_per_task;
+    const RunTiers tiers = run_tiers();
+    if (tiers.depth > 0 && group_haps > 0) {
+        // resident warps of the launch most groups belong to (min_ctas<float, K> of pmm_kernels.cu x 4 warps)
+        std::vector<uint32_t> by_k(kMaxK + 2, 0);
+        for (const Group& g : groups) ++by_k[g.v.striped ? kMaxK + 1 : g.v.K];
+        const int kmaj = (int)(std::max_element(by_k.begin(), by_k.end()) - by_k.begin());
+        const uint64_t wr = (uint64_t)std::max(1, sm_count) * 4 * (kmaj <= 11 ? 4 : kmaj <= 14 ? 3 : 2);
+        const double u = (double)group_haps, u1 = (double)tiers.depth * wr, u2 = 2.0 * tiers.depth * wr;
+        // the largest run: even made of the job's longest haplotypes, a task may not take more than `share` per cent of
+        // the steps a warp does in the whole launch (config 4, 1-2 kb haplotypes and seven per warp: runs lose 5 %)
+        const double warp_steps = (double)group_steps / wr;
+        const uint32_t cap = (uint32_t)std::min<double>(tiers.top, warp_steps * tiers.share / 100.0 / (plan.max_hap_len + 1));
+        if (cap >= 2) {
+            f1 = std::min(1.0, u1 / u);
+            f2 = cap == 2 ? 1.0 - f1 : std::min(1.0 - f1, u2 / u);
+            top = std::max(top, cap);
+        }
+    }
     if (!force && !keep_all_variants)
-        merge_rare_variants(groups, plan.regions, hap_off, sm_count, plan.haps_per_task * (plan.max_hap_len + 1));
+        merge_rare_variants(groups, plan.regions, hap_off, sm_count, top * (plan.max_hap_len + 1));
 
     // launches ordered by variant (largest footprint first); stable within a variant
     std::vector<uint32_t> gorder(groups.size());
@@ -184,11 +236,20 @@ int plan_job(uint32_t num_read, const uint32_t* read_off, uint32_t num_hap, cons
         RunTable& t = rt[2 * (size_t)region + (striped ? 1 : 0)];
         if (t.count == 0) {
             const RegionDesc& r = plan.regions[region];
-            const uint32_t hpt = striped ? 1u : std::min(plan.haps_per_task, r.nhaps);
-            const uint32_t nruns = (r.nhaps + hpt - 1) / hpt;          // runs of near-equal length
             const uint32_t* ho = hap_off + r.hap_first;
+            // the region's haplotypes: `ones` runs of one at the end, `twos` runs of two before them, the rest in runs
+            // of near-equal length of at most `top` (striped reads: one haplotype per task)
+            const uint32_t n = r.nhaps;
+            const uint32_t ones = striped ? n : std::min<uint32_t>(n, (uint32_t)(f1 * n + 0.5));
+            const uint32_t twos = std::min<uint32_t>((n - ones) / 2, (uint32_t)(f2 * n / 2 + 0.5));
+            const uint32_t rest = n - ones - 2 * twos;
+            const uint32_t hpt = std::max(1u, std::min(top, rest));
+            const uint32_t nrest = (rest + hpt - 1) / hpt;
+            const uint32_t nruns = nrest + twos + ones;
             t.first = (uint32_t)run_h0.size(); t.count = nruns;
-            for (uint32_t run = 0; run <= nruns; ++run) run_h0.push_back((uint32_t)((uint64_t)r.nhaps * run / nruns));
+            for (uint32_t run = 0; run < nrest; ++run) run_h0.push_back((uint32_t)((uint64_t)rest * run / nrest));
+            for (uint32_t run = 0; run < twos; ++run) run_h0.push_back(rest + 2 * run);
+            for (uint32_t run = 0; run <= ones; ++run) run_h0.push_back(rest + 2 * twos + run);
             run_cost.resize(run_h0.size());
             for (uint32_t run = 0; run < nruns; ++run) {
                 const uint32_t h0 = run_h0[t.first + run], h1 = run_h0[t.first + run + 1];

@@ -28,6 +28,13 @@ struct Plan {
 // one LDS.128 per 4 rows, and 3 SHFL + LDG + 2 sum FADD + address/loop overhead per step).
 inline double step_cost(int K) { return 12.25 * K + 9.0; }
 
+// Graded runs (plan_job): `depth` tasks per resident warp in each tier of run sizes (0 = runs of equal size); no task
+// longer than `share` per cent of a warp's steps in the launch; at most `top` haplotypes per run.
+struct RunTiers { int depth, share, top; };
+constexpr int kRunTierDepth = 2, kRunTierShare = 40, kRunTierTop = 4;
+RunTiers run_tiers();
+void set_run_tiers(int depth, int share, int top);
+
 // Best (K, W) for a read of R bases.
 Variant pick_variant(int R);
 

@@ -74,6 +74,11 @@ int  pmm_device_count(void);
  *                       stream priority), larger = later; replaces the context's own stream.  Decides whose thread blocks take
  *                       the SM slots another context's kernel frees at its tail
  *   "tasks_per_warp"  = target queue depth per resident warp used when cutting regions into warp-tasks
+ *   "run_tiers"       = "depth[,share[,top]]", graded runs: a region's haplotypes are cut into runs of decreasing size (long
+ *                       runs first, so what a task pays once is paid rarely; one-haplotype tasks last, so the launch's tail
+ *                       stays short): `depth` tasks per resident warp in each tier (default 2; 0 = runs of equal size), no
+ *                       task longer than `share` per cent of a warp's steps in the launch (40), at most `top` haplotypes
+ *                       per run (4).  Process-wide
  *   "mode"            = "exact" (default): every multiply and add of the float pass is rounded on its own, results are
  *                       bit-identical to the reference's AVX code.  "fast": the float cell update is contracted to
  *                       4 FMUL + 4 FFMA per cell (12 -> 8 instructions); results agree with the reference to a few
