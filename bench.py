@@ -417,7 +417,7 @@ def measure_plugin(batch, steps: int, local: int, threads: int):
         for _ in range(steps):
             hostlayer.worker_forward(jobs[0])
         return (time.perf_counter() - t0) / steps, jobs[0].out.copy()
-    per = max(2, steps // threads)
+    per = max(8, steps // threads)                 # batches per thread: the start and the end of the run are ragged
     go = threading.Barrier(threads + 1)
 
     def work(j):
