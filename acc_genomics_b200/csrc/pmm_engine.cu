@@ -631,6 +631,12 @@ int pmm_set_option(pmm_ctx* c, const char* key, const char* value)
         c->tasks_per_warp = v;
         return PMM_OK;
     }
+    if (k == "small_job_widening") {
+        const std::string v(value);
+        if (v != "0" && v != "1" && v != "on" && v != "off") return c->fail(PMM_ERR_INVALID, "small_job_widening is \"on\" or \"off\"");
+        set_small_job_widening(v == "1" || v == "on");   // process-wide (the planner has no context)
+        return PMM_OK;
+    }
     if (k == "run_tiers") {
         int d = -1, share = kRunTierShare, top = kRunTierTop;
         if (std::sscanf(value, "%d,%d,%d", &d, &share, &top) < 1 || d < 0 || d > 64 || share < 1 || share > 100 || top < 1 || top > 64)

@@ -17,7 +17,7 @@ namespace pmm {
 
 // Maximise useful FP work per issue slot, 12*R / (W * step_cost(K)), subject to R + 1 <= K * W (one boundary row),
 // with a mild penalty for variants whose register count lowers occupancy.
-static Variant pick_variant_uncached(int R);
+static Variant pick_variant_uncached(int R, int wmin);
 
 Variant pick_variant(int R)
 {
@@ -25,17 +25,30 @@ Variant pick_variant(int R)
     constexpr int kMemo = 1024;
     static const std::vector<Variant> memo = [] {
         std::vector<Variant> m(kMemo);
-        for (int r = 0; r < kMemo; ++r) m[r] = pick_variant_uncached(r);
+        for (int r = 0; r < kMemo; ++r) m[r] = pick_variant_uncached(r, 8);
         return m;
     }();
-    return R >= 0 && R < kMemo ? memo[R] : pick_variant_uncached(R);
+    return R >= 0 && R < kMemo ? memo[R] : pick_variant_uncached(R, 8);
 }
 
-static Variant pick_variant_uncached(int R)
+
+
+// The same choice among the variants with at least wmin lanes per read (small jobs, see plan_job).
+Variant pick_variant_wide(int R, int wmin)
+{
+    constexpr int kMemo = 1024;
+    static const std::vector<Variant> memo16 = [] { std::vector<Variant> m(kMemo); for (int r = 0; r < kMemo; ++r) m[r] = pick_variant_uncached(r, 16); return m; }();
+    static const std::vector<Variant> memo32 = [] { std::vector<Variant> m(kMemo); for (int r = 0; r < kMemo; ++r) m[r] = pick_variant_uncached(r, 32); return m; }();
+    if (wmin <= 8) return pick_variant(R);
+    if (R >= 0 && R < kMemo) return (wmin >= 32 ? memo32 : memo16)[R];
+    return pick_variant_uncached(R, wmin);
+}
+
+static Variant pick_variant_uncached(int R, int wmin)
 {
     Variant best{kStripedK, 32, true};
     double best_eff = -1.0;
-    for (int W = 8; W <= 32; W *= 2)
+    for (int W = wmin; W <= 32; W *= 2)
         for (int K = 4; K <= kMaxK; ++K) {
             if (!forward_f32_has_variant(K, W) || R + 1 > K * W) continue;
             double eff = 12.0 * R / (W * step_cost(K));
@@ -50,6 +63,15 @@ struct Group { Variant v; uint32_t region; uint32_t reads[kMaxGroups]; uint32_t 
 // Graded runs (plan_job): tasks per resident warp in each tier of run sizes (0 = runs of equal size, the round-1
 // behaviour), the share of a warp's launch one task may take (per cent), and the largest run.  Process-wide;
 // PMM_RUN_TIERS="depth,share,top" or set_run_tiers() for tuning sweeps.
+static std::atomic<int> g_widen{-1};
+bool small_job_widening()
+{
+    int v = g_widen.load(std::memory_order_relaxed);
+    if (v < 0) { const char* e = std::getenv("PMM_SMALL_JOB_WIDENING"); v = e && *e ? (std::atoi(e) != 0) : 1; g_widen.store(v, std::memory_order_relaxed); }
+    return v != 0;
+}
+void set_small_job_widening(bool on) { g_widen.store(on ? 1 : 0, std::memory_order_relaxed); }
+
 static std::atomic<int> g_tiers{-1};                                    // depth | share << 8 | top << 16
 static int pack_tiers(int d, int share, int top)
 {
@@ -158,6 +180,28 @@ int plan_job(uint32_t num_read, const uint32_t* read_off, uint32_t num_hap, cons
     }
     plan.rows = rows;
 
+    // ---- small jobs: more lanes per read ---------------------------------------------------------------------------
+    // The variant that wastes the fewest issue slots (151 bases: 19 rows x 8 lanes) makes long tasks -- a 450-base
+    // haplotype is 110 000 instructions, ~90 us for a warp alone on its SMSP.  A job with fewer such tasks than the GPU has
+    // SMSPs is over when its longest task is, so it is cut finer instead: with 16 or 32 lanes per read a task is a half
+    // or a quarter as long and there are two or four times as many (a 10 x 5 toy region: float pass 85 -> ~30 us).  Wider
+    // while the tasks still find at most two warps per SMSP.
+    int wmin = 8;
+    if (!force && small_job_widening()) {
+        uint64_t t0 = 0;                                                // one-haplotype tasks with the default variants
+        for (uint32_t g = 0; g < num_region; ++g) {
+            const pmm_region_t& r = regions[g];
+            double warps = 0;
+            for (uint32_t k = 0; k < r.num_read; ++k) {
+                const Variant v = pick_variant((int)(read_off[r.read_first + k + 1] - read_off[r.read_first + k]));
+                warps += v.striped ? 1.0 : v.W / 32.0;
+            }
+            t0 += (uint64_t)(warps + 0.999) * r.num_hap;
+        }
+        const uint64_t two_per_smsp = (uint64_t)std::max(1, sm_count) * 8;
+        wmin = t0 * 4 <= two_per_smsp ? 32 : t0 * 2 <= two_per_smsp ? 16 : 8;
+    }
+
     // ---- read groups --------------------------------------------------------------------------------------------
     // Reads of a region are sorted by length (longest first); the longest unassigned read picks the (K, W)
     // variant and shares its warp with the next 32/W - 1 reads.
@@ -174,7 +218,7 @@ int plan_job(uint32_t num_read, const uint32_t* read_off, uint32_t num_hap, cons
             const int R = (int)(read_off[order[k] + 1] - read_off[order[k]]);
             Group gr; gr.region = g; gr.n = 0;
             gr.v = (force && !force->striped && forward_f32_has_variant(force->K, force->W) && R + 1 <= force->K * force->W)
-                       ? *force : pick_variant(R);
+                       ? *force : pick_variant_wide(R, wmin);
             const uint32_t G = gr.v.striped ? 1u : (uint32_t)(32 / gr.v.W);
             for (; gr.n < G && k < r.num_read; ++k) gr.reads[gr.n++] = order[k];
             for (uint32_t z = gr.n; z < (uint32_t)kMaxGroups; ++z) gr.reads[z] = 0;

@@ -35,8 +35,14 @@ constexpr int kRunTierDepth = 2, kRunTierShare = 40, kRunTierTop = 4;
 RunTiers run_tiers();
 void set_run_tiers(int depth, int share, int top);
 
-// Best (K, W) for a read of R bases.
+// Small jobs (fewer one-haplotype tasks than two warps per SMSP could take after widening) get more lanes per read, i.e.
+// shorter and more tasks; process-wide switch for tuning (PMM_SMALL_JOB_WIDENING=0).
+bool small_job_widening();
+void set_small_job_widening(bool on);
+
+// Best (K, W) for a read of R bases; pick_variant_wide: among the variants with at least wmin lanes per read.
 Variant pick_variant(int R);
+Variant pick_variant_wide(int R, int wmin);
 
 // Returns PMM_OK or PMM_ERR_INVALID with a message.
 int plan_job(uint32_t num_read, const uint32_t* read_off, uint32_t num_hap, const uint32_t* hap_off,

@@ -74,6 +74,9 @@ int  pmm_device_count(void);
  *                       stream priority), larger = later; replaces the context's own stream.  Decides whose thread blocks take
  *                       the SM slots another context's kernel frees at its tail
  *   "tasks_per_warp"  = target queue depth per resident warp used when cutting regions into warp-tasks
+ *   "small_job_widening" = "on" (default): a job with fewer warp-tasks than the GPU can spread over its SMSPs gets 16 or 32
+ *                       lanes per read instead of the variant that wastes the fewest issue slots -- shorter, more numerous
+ *                       tasks, i.e. a shorter critical path for a per-region caller.  Process-wide
  *   "run_tiers"       = "depth[,share[,top]]", graded runs: a region's haplotypes are cut into runs of decreasing size (long
  *                       runs first, so what a task pays once is paid rarely; one-haplotype tasks last, so the launch's tail
  *                       stays short): `depth` tasks per resident warp in each tier (default 2; 0 = runs of equal size), no

@@ -42,7 +42,8 @@ def test_variant_choice(built):
     from acc_genomics_b200 import engine
 
     def variant(length):
-        b = synth.region(np.random.Generator(np.random.PCG64(1)), [length] * 8, [length + 50] * 2)
+        # a job large enough to fill the GPU: small ones get wider lanes, see test_small_jobs_get_wider_lanes
+        b = synth.region(np.random.Generator(np.random.PCG64(1)), [length] * 400, [length + 50] * 24)
         t = engine.plan(b)[0]
         return t["K"], t["W"], t["striped"]
     assert variant(151) == (19, 8, False)        # 4 reads per warp, 151 + 1 boundary row = all 152 rows used
@@ -91,3 +92,21 @@ def test_rare_variants_join_the_next_larger_launch(built):
     tasks = engine.plan(half)
     assert {(t["K"], t["W"]) for t in tasks} == {(19, 8), (13, 8)}
     coverage(half, tasks)
+
+
+def test_small_jobs_get_wider_lanes(built):
+    """Fewer tasks than the GPU has SMSPs: 16 or 32 lanes per read (shorter, more numerous tasks) instead of 8."""
+    from acc_genomics_b200 import engine
+    rng = np.random.Generator(np.random.PCG64(11))
+    tiny = synth.region(rng, [151] * 10, [400] * 5)              # 3 groups x 5 haplotypes at 19 x 8
+    tasks = engine.plan(tiny)
+    assert {(t["K"], t["W"]) for t in tasks} == {(5, 32)} and len(tasks) == 50
+    coverage([tiny], tasks)
+    small = synth.region(rng, [151] * 100, [400] * 20)           # 25 groups x 20 = 500 tasks: 16 lanes
+    tasks = engine.plan(small)
+    assert {(t["K"], t["W"]) for t in tasks} == {(10, 16)}
+    coverage([small], tasks)
+    medium = synth.region(rng, [151] * 100, [400] * 40)          # 1000 tasks: the default
+    assert {(t["K"], t["W"]) for t in engine.plan(medium)} == {(19, 8)}
+    # the same job on a GPU an eighth the size is not small
+    assert {(t["K"], t["W"]) for t in engine.plan(small, sm_count=16)} == {(19, 8)}
