@@ -27,7 +27,7 @@ def check(engine, checker, b, what):
     return raw, out, mask
 
 
-def test_golden_vectors(engine, golden):
+def test_golden_vectors(engine, golden, widening):
     """Committed vectors minted from the reference's own AVX code (tests/golden/make_golden.py)."""
     cases, _ = golden
     for name, (b, raw_bits, log10_bits, mask) in cases.items():
@@ -84,7 +84,16 @@ def test_every_entry_point_agrees(engine, checker):
     assert_bits_equal(out, out_r, "pmm_forward_log10"); assert nfb == int(fb_r.sum())
 
 
-def test_all_small_lengths(engine, checker):
+@pytest.fixture(params=["on", "off"])
+def widening(request, engine):
+    """Small jobs get 16 or 32 lanes per read by default; "off" keeps the variants a large job of the same reads would use
+    (so the narrow variants see the small edge cases too)."""
+    engine.set_option("small_job_widening", request.param)
+    yield request.param
+    engine.set_option("small_job_widening", "on")
+
+
+def test_all_small_lengths(engine, checker, widening):
     """Read lengths 1..70 x haplotype lengths 1..40: every boundary-row count, lane count and short-haplotype
     (shorter than the wavefront) combination of the small variants."""
     rng = np.random.Generator(np.random.PCG64(21))
@@ -92,7 +101,7 @@ def test_all_small_lengths(engine, checker):
     check(engine, checker, b, "small lengths")
 
 
-def test_lengths_around_every_variant_boundary(engine, checker):
+def test_lengths_around_every_variant_boundary(engine, checker, widening):
     rng = np.random.Generator(np.random.PCG64(22))
     lens = sorted({k * w + d for w in (8, 16, 32) for k in range(4, 17) for d in (-2, -1, 0, 1)})
     lens = [x for x in lens if x <= 520]
