@@ -2,7 +2,6 @@
 #include "PairHMMWorker.h"
 
 #include <algorithm>
-#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -39,18 +38,14 @@ void PairHMMWorker::compute() {
 // tile's way out stay exposed, which is why the first tile is half the size of the others.  More tiles shrink the
 // exposed part but cost GPU efficiency (fewer warp-tasks per launch, more launches), and a small batch gains nothing.
 // PAIRHMM_WORKER_TILES overrides (tuning).
-// Tiles exist to overlap one batch's own way in and out with its kernels.  When at least two other workers of the process
-// are inside run() at the same moment (a caller with several threads, one client each), their batches already fill
-// those gaps, and cutting a batch only costs GPU efficiency (every tile is a launch with its own ramp and tail): one tile
-// then.  Measured on config 2 (tools/plugin_threads.py, GCUPS with 4 tiles / 1 tile per batch): one caller thread
-// 1 855 / 1 346, two 2 007 / 1 949, three 2 039 / 2 126, four 2 041 / 2 131.
-static std::atomic<int> g_running{0};
-struct RunningGuard { RunningGuard() { g_running.fetch_add(1, std::memory_order_relaxed); } ~RunningGuard() { g_running.fetch_sub(1, std::memory_order_relaxed); } };
-
+// Tried (round 2, tools/plugin_threads.py): one tile per batch while three or more workers of the process are inside run() --
+// their batches fill the gaps tiles exist for, and an uncut batch is a more efficient launch.  One process, three / four
+// caller threads: 2 126 / 2 131 GCUPS against 2 039 / 2 041 with four tiles.  Eight processes of three threads on a 32-core
+// host (one per GPU): 1 600-2 040 per process and noisy, against a steady 1 970-2 030 with four tiles -- an uncut batch
+// puts 0.3 ms of serialization and packing on one thread.  The steady one stays.
 static int pick_tiles(uint64_t cells, int num_read) {
   if (const char* e = getenv("PAIRHMM_WORKER_TILES")) { const int v = atoi(e); if (v >= 1) return std::min(v, std::max(1, num_read)); }
   if (cells < 1200000000ull) return 1;
-  if (g_running.load(std::memory_order_relaxed) > 2) return 1;
   const int t = (int)std::min<uint64_t>(6, std::max<uint64_t>(3, cells / 1100000000ull));
   return std::min(t, std::max(1, num_read));
 }
@@ -81,7 +76,6 @@ void PairHMMWorker::run() {
   fallback_index_.clear(); fallback_value_.clear(); final_.clear(); final_rows_ = 0;
   ran_ = true;
   if (num_read_ == 0 || num_hap_ == 0) return;
-  RunningGuard running;
 
   // Rows (reads) per accelerator call.  Upper bound: the engine's job limits.
   uint64_t hap_bytes = 0, hap_bases = 0, read_bases = 0, max_read = 1;
