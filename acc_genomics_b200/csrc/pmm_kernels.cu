@@ -86,6 +86,39 @@ template <bool FLUSH> __device__ __forceinline__ float flush(float x) { return x
 
 template <typename T> __device__ __forceinline__ T ld_cg(const T* p) { return __ldcg(p); }
 
+// ---- TMA bulk copy (cp.async.bulk, global -> shared) completing on an mbarrier: how a warp stages its task's match-weight
+//      tile.  One lane issues the copy; every lane that is to read the tile waits for the barrier's phase. ----------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+[[maybe_unused]] __device__ __forceinline__ void mbar_init(uint64_t* mbar, uint32_t arrivals)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(mbar)), "r"(arrivals) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+[[maybe_unused]] __device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* mbar)
+{
+    // the tile's previous contents were read through the generic proxy; the copy writes through the async proxy
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(mbar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
+}
+// The same tile by cp.async (LDGSTS): every lane copies 16 bytes per instruction, global -> shared without a register.
+[[maybe_unused]] __device__ __forceinline__ void cp_async_16(void* dst_smem, const void* src_gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+[[maybe_unused]] __device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+[[maybe_unused]] __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t phase)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                 :: "r"(smem_u32(mbar)), "r"(phase) : "memory");
+}
+
 template <typename T, int K>
 __host__ __device__ constexpr int wtab_elems() { return 5 * ((K + Arith<T>::kVec - 1) / Arith<T>::kVec) * 32 * Arith<T>::kVec; }
 
@@ -153,9 +186,22 @@ constexpr int kRetry = 16;
 // one haplotype into the next; a lane re-points its stream pointer when it crosses a separator.
 constexpr int kList = 32;
 
+static_assert(!kTileCopy || (wtab_floats(19) == (uint32_t)wtab_elems<float, 19>() && wtab_floats(4) == (uint32_t)wtab_elems<float, 4>() &&
+                             wtab_floats(10) == (uint32_t)wtab_elems<float, 10>()), "the planner's tile size is the kernel's table size");
+
+// Builds with PMM_TILE_COPY != 0 (pmm_types.h): the float pass of one-stripe reads takes its weight table ready-made from
+// read_params_kernel's tile and stages it by cp.async (1: 16 bytes per lane and instruction) or by one TMA bulk copy per task
+// (2: cp.async.bulk + mbarrier).  Both are parity-green and both measured slower than building the table in the kernel from
+// three planes (config 2 float pass 1.775 ms; cp.async 1.787; TMA 1.795 -- its latency is the longest, and a task's first
+// step needs the table), so the default build keeps the in-kernel build.
+template <typename T, bool STRIPED, int F> __host__ __device__ constexpr bool tile_by_tma()
+{
+    return kTileCopy != 0 && sizeof(T) == 4 && !STRIPED && (F & 8 /* kInline */) == 0;
+}
+
 template <typename T, int K, int W, bool STRIPED, int F>
 __device__ __forceinline__ void run_task(const ForwardArgs& a, const Task* tk, T* wtab, const int lane,
-                                         const uint32_t gwarp, const FallbackQueue& fq)
+                                         const uint32_t gwarp, const FallbackQueue& fq, uint64_t* mbar, uint32_t& phase)
 {
     using A = Arith<T>;
     constexpr bool FLUSH = (F & kFlush) != 0, PUSH = (F & kPush) != 0, FAST = (F & kFast) != 0, INLINE = (F & kInline) != 0;
@@ -212,8 +258,36 @@ __device__ __forceinline__ void run_task(const ForwardArgs& a, const Task* tk, T
         T pX0 = (T)0;                                                // pC[0] as the X update of row 0 sees it
         unsigned padmask = 0;
         __syncwarp();                                                // previous task / stripe done with wtab
-        if constexpr (kIsFloat && !INLINE) {
-            // float pass: the rows were prepared once per read by read_params_kernel; W consecutive lanes read
+        if constexpr (tile_by_tma<T, STRIPED, F>()) {
+            // float pass, one stripe: read_params_kernel left the group's weight tile in the layout of wtab; lane 0 has the
+            // TMA unit copy it (12.8 KB for K = 19) while all lanes load their 5 K transition parameters -- W consecutive
+            // lanes read consecutive floats, all loads independent -- and everyone waits for the tile's barrier phase.
+            constexpr int KW = K * W;
+            constexpr uint32_t kTileBytes = (uint32_t)wtab_elems<float, K>() * (uint32_t)sizeof(float);   // == wtab_floats(K)
+            const float* gb = a.params + tk->param_off;
+            const float* gtile = gb + (size_t)kParamPlanes * 32 * K;
+            if constexpr (kTileCopy == 2) {
+                if (lane == 0) bulk_copy_g2s(wtab, gtile, kTileBytes, mbar);
+            } else {
+                #pragma unroll
+                for (uint32_t o = 0; o < kTileBytes; o += 512)
+                    cp_async_16(reinterpret_cast<char*>(wtab) + o + lane * 16, reinterpret_cast<const char*>(gtile) + o + lane * 16);
+            }
+            const float* pb = gb + (size_t)g * (kParamPlanes * KW) + l;
+            #pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const float* pj = pb + j * W;
+                pMM[j] = __ldg(pj + 0 * KW); pG[j] = __ldg(pj + 1 * KW); pMX[j] = __ldg(pj + 2 * KW);
+                pMY[j] = __ldg(pj + 3 * KW); pC[j] = __ldg(pj + 4 * KW);
+            }
+            // boundary rows: the rows above the read (all rows of an unused slot)
+            const int first = valid ? pad - l * K : K;                // rows j < first of this lane are boundary rows
+            padmask = first >= K ? (1u << K) - 1u : first > 0 ? (1u << first) - 1u : 0u;
+            pX0 = (padmask & 1u) ? 0.0f : pC[0];
+            if constexpr (kTileCopy == 2) { mbar_wait(mbar, phase); phase ^= 1u; }
+            else { cp_async_wait_all(); __syncwarp(); }
+        } else if constexpr (kIsFloat && !INLINE) {
+            // striped float pass: the rows were prepared once per read by read_params_kernel; W consecutive lanes read
             // consecutive floats, all 8K loads are independent
             constexpr int KW = K * W;
             const float* pb = a.params + tk->param_off + ((size_t)(STRIPED ? 0 : g) * nstripes + stripe) * (kParamPlanes * KW) + l;
@@ -471,8 +545,14 @@ template <typename T, int K, int W, bool STRIPED, int F>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, min_ctas<T, K>()) pmm_forward_kernel(const ForwardArgs a, const FallbackQueue fq)
 {
     extern __shared__ uint4 smem_raw[];
+    __shared__ uint64_t tile_bar[kWarpsPerCta];                  // one transaction barrier per warp (weight tile by TMA)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     T* wtab = reinterpret_cast<T*>(smem_raw) + warp * wtab_elems<T, K>();
+    uint32_t phase = 0;
+    if constexpr (tile_by_tma<T, STRIPED, F>() && kTileCopy == 2) {
+        if (lane == 0) mbar_init(&tile_bar[warp], 1);
+        __syncwarp();
+    }
     const uint32_t ntasks = a.ntasks_dev ? *a.ntasks_dev : a.ntasks;
     const uint32_t gwarp = blockIdx.x * kWarpsPerCta + warp;
     for (;;) {
@@ -480,7 +560,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, min_ctas<T, K>()) pmm_forwa
         if (lane == 0) ti = atomicAdd(a.counter, 1u);
         ti = __shfl_sync(0xffffffffu, ti, 0);
         if (ti >= ntasks) break;
-        run_task<T, K, W, STRIPED, F & ~kRetry>(a, a.tasks + ti, wtab, lane, gwarp, fq);
+        run_task<T, K, W, STRIPED, F & ~kRetry>(a, a.tasks + ti, wtab, lane, gwarp, fq, &tile_bar[warp], phase);
         if constexpr ((F & kRetry) != 0) {
             // Intermediate products below DBL_MIN are flushed to zero on the reference's x86 (FTZ on); they can only
             // influence results that are themselves tiny.  Everything below tiny_threshold (2^-800, scaled by 2^1020) is
@@ -499,7 +579,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, min_ctas<T, K>()) pmm_forwa
                     Task one = tk;
                     one.hap_first = tk.hap_first + n; one.nhaps = 1; one.out_base[0] = tk.out_base[0] + n;
                     if (lane == 0) atomicAdd(a.tiny_count, 1u);
-                    run_task<T, K, W, STRIPED, (F & ~kRetry) | kFlush>(a, &one, wtab, lane, gwarp, fq);
+                    run_task<T, K, W, STRIPED, (F & ~kRetry) | kFlush>(a, &one, wtab, lane, gwarp, fq, &tile_bar[warp], phase);
                 }
             }
         }
@@ -635,9 +715,16 @@ __global__ void __launch_bounds__(128) read_params_kernel(const uint8_t* __restr
                                                           DeviceTables tab, float* __restrict__ params)
 {
     if (blockIdx.x >= ngroups) return;
+    // the quality -> probability table is looked up four times per row: staged in shared memory
+    __shared__ float s_ph2pr[128];
+    if (threadIdx.x < 128) s_ph2pr[threadIdx.x] = __ldg(tab.ph2pr_f + threadIdx.x);
+    __syncthreads();
     const GroupDesc gd = groups[blockIdx.x];
     const uint32_t K = gd.K, W = gd.W, KW = K * W, rows = gd.nstripes * KW;
     const uint32_t slots = gd.nstripes > 1 ? 1u : 32u / W;
+    // one-stripe groups: the weight tile behind the planes (pmm_types.h), staged by the forward kernel with one bulk copy
+    float* tile = (gd.nstripes > 1 || !kTileCopy) ? nullptr : params + gd.param_off + (size_t)kParamPlanes * 32 * K;
+    const uint32_t cls_stride = ((K + 3) / 4) * 128;
     for (uint32_t slot = 0; slot < slots; ++slot) {
         const bool valid = slot < gd.nreads;
         ReadDesc rd = {0u, 0u, 0u};
@@ -653,11 +740,11 @@ __global__ void __launch_bounds__(128) read_params_kernel(const uint8_t* __restr
                 const int q_ = b[rd.stride] & 127, i_ = b[2 * rd.stride] & 127;
                 const int d_ = b[3 * rd.stride] & 127, c_ = b[4 * rd.stride] & 127;
                 const int mx = max(i_, d_), mn = min(i_, d_);
-                const float pc = __ldg(tab.ph2pr_f + c_), dm = __ldg(tab.ph2pr_f + q_);
+                const float pc = s_ph2pr[c_], dm = s_ph2pr[q_];
                 v[0] = __ldg(tab.m2m_f + ((mx * (mx + 1)) >> 1) + mn);
                 v[1] = __fsub_rn(1.0f, pc);
-                v[2] = __ldg(tab.ph2pr_f + i_);
-                v[3] = __ldg(tab.ph2pr_f + d_);
+                v[2] = s_ph2pr[i_];
+                v[3] = s_ph2pr[d_];
                 v[4] = pc;
                 v[5] = __fsub_rn(1.0f, dm);
                 v[6] = __fdiv_rn(dm, 3.0f);
@@ -666,6 +753,15 @@ __global__ void __launch_bounds__(128) read_params_kernel(const uint8_t* __restr
             float* o = base + (size_t)s * kParamPlanes * KW + idx;
             #pragma unroll
             for (int p = 0; p < kParamPlanes; ++p) o[(size_t)p * KW] = v[p];
+            if (tile) {
+                const unsigned cls = __float_as_uint(v[7]);
+                float* t = tile + (j / 4) * 128 + (slot * W + l) * 4 + (j % 4);
+                #pragma unroll
+                for (int h = 0; h < 5; ++h) {
+                    const bool match = (cls == (unsigned)h) || cls == 4 || h == 4;
+                    t[h * cls_stride] = match ? v[5] : v[6];
+                }
+            }
         }
     }
 }

@@ -315,11 +315,12 @@ int plan_job(uint32_t num_read, const uint32_t* read_off, uint32_t num_hap, cons
         const uint32_t kw = gd.K * gd.W;
         gd.nstripes = gr.v.striped ? (read_off[gr.reads[0] + 1] - read_off[gr.reads[0]] + kw) / kw : 1u;
         const uint64_t slots = gr.v.striped ? 1u : 32u / gd.W;
-        if (plan.param_floats + slots * gd.nstripes * kParamPlanes * kw >= (1ull << 32)) {
+        if (plan.param_floats + slots * gd.nstripes * kParamPlanes * kw + wtab_floats(kMaxK) >= (1ull << 32)) {
             err = "row parameters of one job exceed 16 GiB: split it"; return PMM_ERR_INVALID;
         }
         gd.param_off = (uint32_t)plan.param_floats;
         plan.param_floats += slots * gd.nstripes * kParamPlanes * kw;
+        if (!gr.v.striped) plan.param_floats += wtab_floats(gr.v.K);     // the group's weight tile, see pmm_types.h
         plan.groups.push_back(gd);
         if (plan.segs.empty() || !(plan.segs.back().v == gr.v)) plan.segs.push_back(LaunchSeg{gr.v, (uint32_t)ntasks, 0});
         const uint32_t nruns = table_of(gr.region, gr.v.striped).count;

@@ -35,8 +35,19 @@ static_assert(sizeof(Task) == 48, "Task layout");
 // [stripe][plane][j][l]: plane p of the row that is row j of lane l -- consecutive lanes read consecutive addresses.
 // Planes: 0 pMM, 1 pGAPM, 2 pMX, 3 pMY, 4 pXX = pYY, 5 match weight 1 - e, 6 mismatch weight e / 3, 7 base class
 // as an integer (0..4, kPadClass for a boundary row above the read or an unused slot).
+// Behind the planes of a one-stripe group comes (builds with PMM_TILE_COPY != 0) its match-weight tile, wtab_floats(K) floats: the [5 haplotype classes]
+// [K rows] weights of the group's (up to 32/W) reads in exactly the layout the forward kernel keeps in shared memory --
+// element (class h, row j, lane) at h * (KQ * 128) + (j / 4) * 128 + lane * 4 + j % 4, KQ = ceil(K / 4) -- so that a warp
+// stages it with one bulk copy (TMA, cp.async.bulk) per task instead of rebuilding it from the planes.
+// PMM_TILE_COPY (build option): 0 = no tile, every task builds its table from planes 5-7 (the default: fastest, see
+// DESIGN.md section 4.1b); 1 = tile staged by cp.async; 2 = by one TMA bulk copy per task.
+#ifndef PMM_TILE_COPY
+#define PMM_TILE_COPY 0
+#endif
+constexpr int kTileCopy = PMM_TILE_COPY;
 constexpr int kParamPlanes = 8;
 constexpr uint32_t kPadClass = 5;
+inline constexpr uint32_t wtab_floats(int K) { return kTileCopy ? 5u * (uint32_t)((K + 3) / 4) * 128u : 0u; }
 struct GroupDesc {
     uint32_t read[kMaxGroups];
     uint32_t nreads;
