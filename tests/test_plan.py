@@ -110,3 +110,28 @@ def test_small_jobs_get_wider_lanes(built):
     assert {(t["K"], t["W"]) for t in engine.plan(medium)} == {(19, 8)}
     # the same job on a GPU an eighth the size is not small
     assert {(t["K"], t["W"]) for t in engine.plan(small, sm_count=16)} == {(19, 8)}
+
+
+def test_graded_runs_cover_every_pair_and_put_long_runs_first(built):
+    """Large jobs: a region's haplotypes are cut into runs of decreasing size (what a task pays once is paid rarely, the
+    launch's tail is made of one-haplotype tasks).  Every pair still appears exactly once; within a launch the tasks are
+    ordered longest first; a job with few tasks per warp keeps one haplotype per task."""
+    from acc_genomics_b200 import engine
+    big = synth.config(2)                                        # 250 groups x 64 haplotypes: 13.5 per resident warp
+    tasks = engine.plan(big)
+    coverage(big, tasks)
+    sizes = sorted({t["num_hap"] for t in tasks})
+    assert sizes[0] == 1 and sizes[-1] >= 3 and len(tasks) < 12000          # 16 000 without grading
+    ones = sum(t["num_hap"] == 1 for t in tasks)
+    assert 2000 <= ones <= 5000                                   # about two per resident warp (1 184), not all of them
+    hap_len = np.diff(big[0].hap_off)
+    cost = [int(hap_len[t["hap_first"]:t["hap_first"] + t["num_hap"]].sum()) + t["num_hap"] for t in tasks]
+    cmax = max(cost)
+    cls = [63 - c * 63 // cmax for c in cost]                     # the planner's 64 cost classes
+    assert cls == sorted(cls), "tasks of a launch are queued longest first (by cost class)"
+    few = synth.config(4)                                         # 256 groups x 32 long haplotypes: 7 per warp
+    assert {t["num_hap"] for t in engine.plan(few)} == {1}
+    job = synth.config(5, scale=0.01)                             # 25 regions of 100 x 40
+    tj = engine.plan(job)
+    coverage(job, tj)
+    assert max(t["num_hap"] for t in tj) == 4 and min(t["num_hap"] for t in tj) == 1
