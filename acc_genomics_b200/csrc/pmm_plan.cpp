@@ -3,8 +3,9 @@
 // What the reference does at this point is device-specific load balancing for its FPGA processing units
 // (/root/reference/pairhmm/interface/PairHMMFpgaInterface.cpp:67-170) and tiling to the device limits
 // (/root/reference/pairhmm/client/PairHMMWorker.cpp:217-221).  On the GPU there are no length limits; the
-// planner's job is to keep lanes full (pick K x W per read length), keep the wavefront bubbles rare (runs of
-// haplotypes per task) and keep the work queue deep enough for ~2400 resident warps.
+// planner's job is to keep lanes full (pick K x W per read length; wider lanes for jobs too small to fill the GPU), to
+// make what a task pays once rare without lengthening the launch's tail (graded runs of haplotypes per task, longest
+// first) and to keep the work queue deep enough for the 1 200 - 2 400 resident warps.
 #include "pmm_plan.h"
 
 #include <algorithm>
@@ -228,7 +229,8 @@ int plan_job(uint32_t num_read, const uint32_t* read_off, uint32_t num_hap, cons
         }
     }
 
-    // ---- runs of haplotypes: about tasks_per_warp queued tasks per resident warp --------------------------------
+    // ---- runs of haplotypes: at least about tasks_per_warp queued tasks per resident warp (a bound that only jobs of more
+    //      than ~38 000 group x haplotype units reach; below it the graded runs decide) --------------------------------
     const uint64_t resident_warps = (uint64_t)std::max(1, sm_count) * 16;
     const uint64_t target_tasks = std::max<uint64_t>(1, resident_warps * (uint64_t)std::max(1, tasks_per_warp));
     plan.haps_per_task = (uint32_t)std::max<uint64_t>(1, (group_haps + target_tasks - 1) / target_tasks);
