@@ -527,6 +527,16 @@ def measure_sw(local: int, sm_mhz):
            "call_gcups": cells / best[1] * 1e-6, "alu_pipe_bound_gcups": bound, "frac_of_alu_bound": cells / best[0] * 1e-6 / bound,
            "backtrack_mb": st["bytes_backtrack"] / 1e6,
            "path": "sw_align_batch (include/smithwaterman_cuda.h): host buffers in, CIGARs out; kernel_ms from CUDA events"}
+    # the same kernel with the GPU full: 64 windows x 260 alternates (one window's worth of pairs leaves most warps a single
+    # pair, so the small batch above is bounded by its longest pairs)
+    big = sw.haplotype_pairs(1, 16640, ref_len=(250, 500), per_ref=260)
+    big_cells = sum(len(r) * len(a) for r, a in big)
+    kb = float("inf")
+    for _ in range(3):
+        al.align(big, 0)
+        kb = min(kb, al.stats()["ms_kernel"])
+    rec["large_batch"] = {"pairs": len(big), "cells": big_cells, "kernel_ms": kb, "kernel_gcups": big_cells / kb * 1e-6,
+                          "frac_of_alu_bound": big_cells / kb * 1e-6 / bound}
     try:
         import oracle
         ref = oracle.sw_reference()
