@@ -194,7 +194,7 @@ static_assert(!kTileCopy || (wtab_floats(19) == (uint32_t)wtab_elems<float, 19>(
 // (2: cp.async.bulk + mbarrier).  Both are parity-green and both measured slower than building the table in the kernel from
 // three planes (config 2 float pass 1.775 ms; cp.async 1.787; TMA 1.795 -- its latency is the longest, and a task's first
 // step needs the table), so the default build keeps the in-kernel build.
-template <typename T, bool STRIPED, int F> __host__ __device__ constexpr bool tile_by_tma()
+template <typename T, bool STRIPED, int F> __host__ __device__ constexpr bool tile_staged()
 {
     return kTileCopy != 0 && sizeof(T) == 4 && !STRIPED && (F & 8 /* kInline */) == 0;
 }
@@ -258,7 +258,7 @@ __device__ __forceinline__ void run_task(const ForwardArgs& a, const Task* tk, T
         T pX0 = (T)0;                                                // pC[0] as the X update of row 0 sees it
         unsigned padmask = 0;
         __syncwarp();                                                // previous task / stripe done with wtab
-        if constexpr (tile_by_tma<T, STRIPED, F>()) {
+        if constexpr (tile_staged<T, STRIPED, F>()) {
             // float pass, one stripe: read_params_kernel left the group's weight tile in the layout of wtab; lane 0 has the
             // TMA unit copy it (12.8 KB for K = 19) while all lanes load their 5 K transition parameters -- W consecutive
             // lanes read consecutive floats, all loads independent -- and everyone waits for the tile's barrier phase.
@@ -549,7 +549,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, min_ctas<T, K>()) pmm_forwa
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     T* wtab = reinterpret_cast<T*>(smem_raw) + warp * wtab_elems<T, K>();
     uint32_t phase = 0;
-    if constexpr (tile_by_tma<T, STRIPED, F>() && kTileCopy == 2) {
+    if constexpr (tile_staged<T, STRIPED, F>() && kTileCopy == 2) {
         if (lane == 0) mbar_init(&tile_bar[warp], 1);
         __syncwarp();
     }
