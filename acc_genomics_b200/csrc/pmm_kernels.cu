@@ -125,7 +125,7 @@ __host__ __device__ constexpr int wtab_elems() { return 5 * ((K + Arith<T>::kVec
 // ---------------------------------------------------------------------------------------------------------
 // The forward kernel.
 // ---------------------------------------------------------------------------------------------------------
-// Resident CTAs per SM the register allocator must leave room for: the state of a lane is 8 registers per row
+// Resident CTAs (of four warps) per SM the register allocator must leave room for: the state of a lane is 8 registers per row
 // (5 parameters + M, X, Y), so K decides the occupancy step (64K registers / 128 threads).
 // Measured (tools/occ_check.py): 15 and 16 rows per lane at two CTAs per SM (up to 255 registers) beat three CTAs at 168
 // registers by 5.6 % (config 4, K = 16 / W = 16: 2 343 -> 2 475 GCUPS); for K <= 14 the difference is within 2 %.
@@ -542,7 +542,7 @@ __device__ __forceinline__ void run_task(const ForwardArgs& a, const Task* tk, T
 }
 
 template <typename T, int K, int W, bool STRIPED, int F>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, min_ctas<T, K>()) pmm_forward_kernel(const ForwardArgs a, const FallbackQueue fq)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, min_ctas<T, K>() * (4 / kWarpsPerCta)) pmm_forward_kernel(const ForwardArgs a, const FallbackQueue fq)
 {
     extern __shared__ uint4 smem_raw[];
     __shared__ uint64_t tile_bar[kWarpsPerCta];                  // one transaction barrier per warp (weight tile by TMA)

@@ -5,7 +5,16 @@
 namespace pmm {
 
 constexpr int kMaxGroups = 4;           // reads per warp: 32 / W, W >= 8
-constexpr int kWarpsPerCta = 4;
+// Warps per CTA of the forward kernels.  Every warp works alone (its own tasks, its own slice of shared memory; no
+// __syncthreads anywhere), so the CTA size only decides the granularity at which the SM's registers and shared memory are
+// taken and given back.  Measured with 1 (build option WARPS_PER_CTA): no difference anywhere -- in particular a one-warp
+// CTA of the double kernel does not slip in beside the float kernel's eight warps per SM, because registers are per
+// SMSP (16 384 each, two float warps of 7 424 leave 1 536): DESIGN.md section 4.5.
+#ifndef PMM_WARPS_PER_CTA
+#define PMM_WARPS_PER_CTA 4
+#endif
+constexpr int kWarpsPerCta = PMM_WARPS_PER_CTA;
+static_assert(kWarpsPerCta == 1 || kWarpsPerCta == 2 || kWarpsPerCta == 4, "warps per CTA");
 constexpr int kF64K = 6;                // rows per lane of the double kernel (W = 32): 191-base reads in one stripe
 constexpr int kMaxK = 20;               // most rows per lane of any float variant
 constexpr int kStripedK = 8;            // rows per lane of the striped float kernel (W = 32)
