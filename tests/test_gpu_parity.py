@@ -154,6 +154,11 @@ def test_invalid_inputs_are_rejected(engine):
     assert e.value.code == PMM_ERR_STATE
     with pytest.raises(PmmError):
         engine.forward_raw_serialized(b"\x05\x00\x00\x00\x10", b"\x01\x00\x00\x00", 16)   # truncated wire format
+    for key, value in (("run_tiers", "x"), ("run_tiers", "2,0,4"), ("run_tiers", "99"), ("small_job_widening", "maybe"),
+                       ("tasks_per_warp", "0"), ("no_such_option", "1")):
+        with pytest.raises(PmmError):
+            engine.set_option(key, value)
+    engine.set_option("run_tiers", "2,40,4"); engine.set_option("small_job_widening", "on")     # the defaults, accepted
 
 
 def test_repeat_launch_is_idempotent(engine):
